@@ -1,0 +1,189 @@
+"""Synthetic inputs for the BASELINE.json configurations.
+
+Everything here is host-side setup: the parameter dictionary of examples/run_test.py:7-56 of the
+reference, reduced with units.py, turned into a cgpe_config plus a start state.  Used by
+bench.py, the tests and smoke(); the Model drop-in (src/modules/Model.py) builds the same
+things through the espressomd-shaped facade instead.
+"""
+import copy
+import math
+
+import numpy as np
+
+from . import _abi, topology, units
+
+# examples/run_test.py:7-56 of the reference
+EXAMPLE_PARAMETERS = {
+    "Thermal properties": {"Temperature": 300},
+    "System properties": {
+        "Number of polymers": 1,
+        "Concentration acid particles": 1e-2,
+        "Concentration salt particles": 2 * 1e-2,
+        "Number of monomers": 100,
+        "NH monomers": 32,
+        "NH2 monomers": 2,
+        "bond length": 3.85,
+        "bond constant": 200.0,
+        "bending constant": 0.002,
+        "dihedral constant": 0.002,
+    },
+    "Particles properties": {
+        "NH": {"index": 0, "charge": +1, "sigma": 2 * 2.75, "epsilon": 0.32},
+        "N": {"index": 1, "charge": 0, "sigma": 2 * 3.298, "epsilon": 0.305},
+        "B": {"index": 2, "charge": +1, "sigma": 2 * 2.42, "epsilon": 0.20},
+        "CH2": {"index": 3, "charge": 0, "sigma": 2 * 3.800, "epsilon": 0.47},
+        "Na": {"index": 4, "charge": +1, "sigma": 2 * 2.21, "epsilon": 0.45},
+        "Cl": {"index": 5, "charge": -1, "sigma": 2 * 3.550, "epsilon": 0.43},
+        "NH2": {"index": 6, "charge": +1, "sigma": 2 * 2.99, "epsilon": 0.38},
+        "N2": {"index": 7, "charge": 0, "sigma": 2 * 3.684, "epsilon": 0.31},
+    },
+    "pH properties": {"pK1": 8.18, "pK2": 10.02, "NUM_PHS": 12, "pHmin": 4.0, "pHmax": 12.0},
+    "Montecarlo properties": {"N_BLOCKS": 16, "DESIRED_BLOCK_SIZE": 200, "PROB_REACTION": 0.7},
+    "Simulation configuration": {
+        "time step": 0.001,
+        "USE_WCA": True,
+        "USE_ELECTROSTATICS": True,
+        "USE_FENE": False,
+        "USE_BENDING": True,
+        "USE_DIHEDRAL_POT": True,
+        "USE_P3M": False,
+    },
+}
+
+
+def example_parameters(n_mon=100, c_salt=2e-2, **overrides):
+    """The reference's example dictionary for a chain of `n_mon` beads; the site counts follow
+    the every-third-bead pattern of M.py:126-155."""
+    p = copy.deepcopy(EXAMPLE_PARAMETERS)
+    role = topology.chain_site_pattern(n_mon)
+    p["System properties"]["Number of monomers"] = int(n_mon)
+    p["System properties"]["NH monomers"] = int(np.sum(role == 1))
+    p["System properties"]["NH2 monomers"] = int(np.sum(role == 2))
+    p["System properties"]["Concentration salt particles"] = float(c_salt)
+    for section, values in overrides.items():
+        p[section].update(values)
+    return p
+
+
+def reduced_units(params):
+    s = params["System properties"]
+    return units.reduce_parameters(
+        params["Thermal properties"]["Temperature"], s["Concentration acid particles"],
+        s["Concentration salt particles"], s["Number of polymers"], s["Number of monomers"],
+        s["NH monomers"], s["NH2 monomers"], s["bond length"], s["bond constant"],
+        s["bending constant"], s["dihedral constant"], params["Particles properties"])
+
+
+def num_samples(params):
+    """P.py:360-368."""
+    mc = params["Montecarlo properties"]
+    n = int(mc["N_BLOCKS"] * mc["DESIRED_BLOCK_SIZE"] / mc["PROB_REACTION"])
+    return n, int((n - 10) / 2)
+
+
+class Workload:
+    """A cgpe_config + start state + sampling schedule for R replicas of one chain."""
+
+    def __init__(self, params, pH, c_salt=None, replica_offset=0, seed=12, device=-1, deprotonated=True):
+        self.params = params
+        sp = params["System properties"]
+        sc = params["Simulation configuration"]
+        pH = np.atleast_1d(np.asarray(pH, dtype=np.float64))
+        R = pH.size
+        self.ru = ru = reduced_units(params)
+        n_mon = sp["Number of monomers"]
+        tix = ru.type_index
+        c_salt_r = np.full(R, sp["Concentration salt particles"]) if c_salt is None else np.broadcast_to(
+            np.asarray(c_salt, np.float64), (R,)).copy()
+        self.pH = pH
+        self.kappa = np.array([units.kappa_per_nm(c) for c in c_salt_r]) * ru.sim_length_nm
+        self.r_cut = 1.0 / self.kappa                                   # M.py:106
+        eps, sig = topology.wca_tables(tix, ru.sigma, ru.epsilon)
+        reactions = [
+            dict(type_prot=tix["NH"], type_deprot=tix["N"], type_ion=tix["B"], seed=77,
+                 q_prot=ru.charge["NH"], q_deprot=ru.charge["N"], q_ion=ru.charge["B"],
+                 pK=params["pH properties"]["pK1"], kT=1.0,
+                 exclusion_range=topology.combination_sigma(ru.sigma["N"], ru.sigma["B"])),
+            dict(type_prot=tix["NH2"], type_deprot=tix["N2"], type_ion=tix["B"], seed=77,
+                 q_prot=ru.charge["NH2"], q_deprot=ru.charge["N2"], q_ion=ru.charge["B"],
+                 pK=params["pH properties"]["pK2"], kT=1.0,
+                 exclusion_range=topology.combination_sigma(ru.sigma["N2"], ru.sigma["B"])),
+        ]
+        self.cfg = _abi.make_config(
+            n_replicas=R, replica_offset=replica_offset, n_chains=1, n_beads=n_mon, n_ion_slots=0,
+            n_types=len(tix), bond_kind=_abi.BOND_FENE if sc["USE_FENE"] else _abi.BOND_HARMONIC,
+            use_angle=int(sc["USE_BENDING"]), use_dihedral=int(sc["USE_DIHEDRAL_POT"]), dihedral_mult=3,
+            use_wca=int(sc["USE_WCA"]), use_dh=int(sc["USE_ELECTROSTATICS"]),
+            bond_k=ru.k_bond, bond_r0=ru.bond_length, fene_drmax=4.0,
+            angle_k=ru.k_bending, angle_phi0=math.pi * 2.0 / 3.0,
+            dihedral_k=ru.k_dihedral, dihedral_phase=math.pi,
+            dh_prefactor=ru.coulomb_prefactor, box_l=ru.box_length, time_step=sc["time step"],
+            pH=float(pH[0]), kappa=float(self.kappa[0]), r_cut=float(self.r_cut[0]), kT=1.0, gamma=1.0,
+            wca_eps=eps, wca_sig=sig, reactions=reactions, device=device)
+        # topology + start state: every site starts deprotonated (M.py:130-147)
+        role = topology.chain_site_pattern(n_mon)
+        if deprotonated:
+            names = np.array(["CH2", "N", "N2"])[role]
+        else:
+            names = np.array(["CH2", "NH", "NH2"])[role]
+        self.type = np.array([tix[n] for n in names], dtype=np.uint8)
+        self.q = np.array([ru.charge[n] for n in names], dtype=np.float32)
+        pos = topology.linear_polymer_positions(1, n_mon, bond_length=ru.bond_length, seed=seed,
+                                                min_distance=0.9 * ru.bond_length, box_l=None)[0]
+        pos += 0.5 * ru.box_length - pos.mean(axis=0)
+        self.xyzq = np.concatenate([pos, self.q[:, None]], axis=1).astype(np.float32)
+        self.n_sites = (int(np.sum(role == 1)), int(np.sum(role == 2)))
+        ns, nsi = num_samples(params)
+        p = params["Montecarlo properties"]["PROB_REACTION"]
+        self.sample_kwargs = dict(
+            md_steps_per_burst=500, use_md=bool(sc["USE_WCA"]),
+            mc_blocks=((0, 5 * self.n_sites[0] + 1), (1, 5 * self.n_sites[1] + 1)),   # E.py:94-95
+            q_snapshot_every=nsi, schedule_seed=10, p_burst1=p, p_burst2=p * 2.0 / (n_mon - 2))
+        self.num_samples = ns
+
+    @property
+    def R(self):
+        return self.cfg.n_replicas
+
+    def init_engine(self, engine, thermostat_seed=1434):
+        """Load the start state and per-replica parameters into a freshly created engine."""
+        engine.set_state(self.xyzq, None, self.type)
+        engine.set_replica_params(pH=self.pH, kappa=self.kappa, r_cut=self.r_cut)
+        engine.set_thermostat_seed(thermostat_seed)                     # E.py:62
+        return engine
+
+    def sample_params(self, engine, n_samples):
+        kw = dict(self.sample_kwargs)
+        every = kw["q_snapshot_every"]
+        rows = (n_samples + every - 1) // every if every > 0 else 0
+        return engine.sample_params(n_samples, q_snapshot_rows=rows, **kw)
+
+
+def config_c1(**kw):
+    """C1: single chain N=50, Debye-Hueckel at 10 mM, pH = pK1."""
+    return Workload(example_parameters(50, c_salt=1e-2), pH=[8.18], **kw)
+
+
+def config_c2(**kw):
+    """C2: 64 pH points x N=100 chain (examples/run_test.py scale)."""
+    return Workload(example_parameters(100, c_salt=2e-2), pH=np.linspace(4.0, 12.0, 64), **kw)
+
+
+C3_SALT_MOLAR = (1e-3, 2e-3, 5e-3, 1e-2, 2e-2, 5e-2, 1e-1, 2e-1)
+
+
+def config_c3_shard(rank=0, world=8, n_ph=128, n_mon=1000, **kw):
+    """C3: 128 pH x 8 ionic strengths of N=1000 chains; rank `rank` of `world` holds the
+    contiguous block of replicas [rank*R/world, (rank+1)*R/world) of the pH-major grid, i.e. with
+    world=8 one ionic strength per GPU.  With world < 8 the grid shrinks to `world` ionic
+    strengths (weak scaling: 128 replicas per GPU)."""
+    salts = C3_SALT_MOLAR[:world] if world <= 8 else C3_SALT_MOLAR
+    n_total = n_ph * len(salts)
+    per = n_total // world
+    lo = rank * per
+    idx = np.arange(lo, lo + per)
+    pH_grid = np.linspace(2.0, 12.0, n_ph)
+    pH = pH_grid[idx % n_ph]
+    c_salt = np.array(salts)[idx // n_ph]
+    return Workload(example_parameters(n_mon, c_salt=float(c_salt[0])), pH=pH, c_salt=c_salt,
+                    replica_offset=int(lo), **kw)
