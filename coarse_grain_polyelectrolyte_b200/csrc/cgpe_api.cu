@@ -1,0 +1,697 @@
+// cgpe_api.cu — the C-ABI of libcgpe.so (include/cgpe.h): handle management, validation, host
+// <-> device copies and kernel launches.  No torch types, no C++ types across the boundary.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "chain_engine.cuh"
+
+using namespace cgpe;
+
+struct cgpe_handle {
+  cgpe_config cfg;
+  DevParams p;
+  DevState g;
+  ChainLaunch launch;
+  cudaStream_t own_stream, stream;
+  cudaEvent_t ev0, ev1;
+  int device;
+  bool have_state;
+  bool timing_pending;
+  int last_launches;
+  // scratch / result buffers on device
+  double *d_obs; float *d_qdist; size_t obs_cap, qdist_cap; int last_ns, last_qrows;
+  double *d_tmp_d; int *d_tmp_i; float4 *d_tmp_f4;     // [R*8] doubles, [R*3] ints, [R][P] float4
+  cgpe_trial_record *d_trace; size_t trace_cap;
+  std::vector<void *> allocs;
+  char err[512];
+};
+
+static char g_err[512] = "";
+
+static int fail(cgpe_handle *h, int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(h ? h->err : g_err, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(h, CGPE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+namespace {
+
+struct DeviceGuard {
+  int prev;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); }
+  ~DeviceGuard() { int cur; cudaGetDevice(&cur); if (cur != prev) cudaSetDevice(prev); }
+};
+
+template <typename T>
+cudaError_t dev_alloc(cgpe_handle *h, T **ptr, size_t n) {
+  cudaError_t e = cudaMalloc((void **)ptr, sizeof(T) * (n > 0 ? n : 1));
+  if (e == cudaSuccess) {
+    h->allocs.push_back((void *)*ptr);
+    e = cudaMemset(*ptr, 0, sizeof(T) * (n > 0 ? n : 1));
+  }
+  return e;
+}
+
+int validate(const cgpe_config *c) {
+  if (!c) return fail(nullptr, CGPE_ERR_INVALID, "config is NULL");
+  if (c->abi_version != CGPE_ABI_VERSION)
+    return fail(nullptr, CGPE_ERR_INVALID, "abi_version %d != %d", c->abi_version, CGPE_ABI_VERSION);
+  if (c->n_replicas < 1 || c->n_chains < 1 || c->n_beads < 1 || c->n_ion_slots < 0)
+    return fail(nullptr, CGPE_ERR_INVALID, "n_replicas, n_chains, n_beads must be >= 1");
+  if (c->n_types < 1 || c->n_types > CGPE_MAX_TYPES) return fail(nullptr, CGPE_ERR_INVALID, "n_types out of range");
+  if (c->n_reactions < 0 || c->n_reactions > CGPE_MAX_REACTIONS)
+    return fail(nullptr, CGPE_ERR_INVALID, "n_reactions out of range");
+  if (!(c->box_l > 0.0) || !(c->time_step > 0.0))
+    return fail(nullptr, CGPE_ERR_INVALID, "box_l and time_step must be positive");
+  if (c->use_dh && (!(c->r_cut > 0.0) || c->r_cut > 0.5 * c->box_l))
+    return fail(nullptr, CGPE_ERR_INVALID, "r_cut must lie in (0, box_l/2]");
+  if (c->bond_kind < CGPE_BOND_NONE || c->bond_kind > CGPE_BOND_FENE)
+    return fail(nullptr, CGPE_ERR_INVALID, "unknown bond_kind");
+  if (c->use_dihedral && (c->dihedral_mult < 0 || c->dihedral_mult > 12))
+    return fail(nullptr, CGPE_ERR_INVALID, "dihedral_mult out of range");
+  for (int m = 0; m < c->n_reactions; ++m) {
+    const cgpe_reaction &r = c->reactions[m];
+    if (r.type_prot < 0 || r.type_prot >= c->n_types || r.type_deprot < 0 || r.type_deprot >= c->n_types ||
+        r.type_prot == r.type_deprot)
+      return fail(nullptr, CGPE_ERR_INVALID, "reaction %d: bad type indices", m);
+    if (!(r.kT > 0.0)) return fail(nullptr, CGPE_ERR_INVALID, "reaction %d: kT must be positive", m);
+    for (int m2 = 0; m2 < m; ++m2) {
+      const cgpe_reaction &q = c->reactions[m2];
+      if (q.type_prot == r.type_prot || q.type_prot == r.type_deprot || q.type_deprot == r.type_prot ||
+          q.type_deprot == r.type_deprot)
+        return fail(nullptr, CGPE_ERR_INVALID, "reactions %d and %d share a particle type", m2, m);
+    }
+  }
+  return CGPE_OK;
+}
+
+// (re)build the WCA table {24 eps, sigma^2, rc^2, eps} incl. the non-interacting row/column, and
+// the list radius that depends on it
+int upload_wca(cgpe_handle *h) {
+  const int T = h->cfg.n_types, S = T + 1;
+  std::vector<float4> tab((size_t)S * S, make_float4(0.f, 0.f, 0.f, 0.f));
+  double rc_max = 0.0;
+  for (int a = 0; a < T; ++a)
+    for (int b = 0; b < T; ++b) {
+      const double eps = h->cfg.wca_eps[a * CGPE_MAX_TYPES + b], sig = h->cfg.wca_sig[a * CGPE_MAX_TYPES + b];
+      if (eps < 0.0 || sig < 0.0) return fail(h, CGPE_ERR_INVALID, "WCA epsilon and sigma must be >= 0");
+      if (eps == 0.0 || sig == 0.0) continue;
+      const double rc2 = 1.2599210498948731648 * sig * sig;
+      tab[(size_t)a * S + b] = make_float4((float)(24.0 * eps), (float)(sig * sig), (float)rc2, (float)eps);
+      rc_max = std::fmax(rc_max, std::sqrt(rc2));
+    }
+  CU(cudaMemcpyAsync(h->g.wca_tab, tab.data(), sizeof(float4) * tab.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const double rl = rc_max + h->p.skin;
+  if (h->cfg.use_wca && rl > 0.5 * h->cfg.box_l) return fail(h, CGPE_ERR_INVALID, "WCA cutoff + skin exceeds box_l/2");
+  h->p.rlist_w2 = (float)(rl * rl);
+  return CGPE_OK;
+}
+
+// Row capacities of the two Verlet lists.  cap_dh follows the list radius (sites sit >= 3 bonds
+// apart along the backbone; room is left for coiled states); cap_wca takes what is left of the
+// 227 KB shared-memory budget, up to 64 entries.  Explicit values in the config win.
+int choose_capacities(cgpe_handle *h) {
+  DevParams &p = h->p;
+  const int n_chg = p.n_chg;
+  if (h->cfg.cap_dh > 0) p.cap_d = h->cfg.cap_dh;
+  else {
+    int cap = (int)(24 + 3.0 * (h->cfg.r_cut + p.skin));
+    cap = (cap + 7) / 8 * 8;
+    if (cap > 248) cap = 248;
+    p.cap_d = cap;
+  }
+  if (p.cap_d > (n_chg > 1 ? n_chg - 1 : 1)) p.cap_d = n_chg > 1 ? n_chg - 1 : 1;
+  if (h->cfg.cap_wca > 0) p.cap_w = h->cfg.cap_wca;
+  else {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    p.cap_w = 0;
+    const size_t fixed = chain_smem_bytes(p), budget = (size_t)prop.sharedMemPerBlockOptin;
+    long cap = budget > fixed + 64 ? (long)((budget - fixed - 64) / (2 * (size_t)p.P)) : 0;
+    if (cap > 64) cap = 64;
+    if (cap < 4) cap = 4;   // too little: chain_launch_shape / the smem check will refuse
+    p.cap_w = (int)cap;
+  }
+  if (p.cap_w > (p.P > 1 ? p.P - 1 : 1)) p.cap_w = p.P > 1 ? p.P - 1 : 1;
+  h->launch = chain_launch_shape(p);
+  return CGPE_OK;
+}
+
+int check_device_errors(cgpe_handle *h) {
+  std::vector<int> err(h->p.R);
+  CU(cudaMemcpyAsync(err.data(), h->g.err, sizeof(int) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  int any = 0, first = -1;
+  for (int r = 0; r < h->p.R; ++r)
+    if (err[r]) { any |= err[r]; if (first < 0) first = r; }
+  if (!any) return CGPE_OK;
+  CU(cudaMemsetAsync(h->g.err, 0, sizeof(int) * h->p.R, h->stream));
+  if (any & kErrNonFinite) return fail(h, CGPE_ERR_NUMERIC, "non-finite coordinate or velocity (first replica %d)", first);
+  if (any & kErrFene) return fail(h, CGPE_ERR_NUMERIC, "FENE bond stretched beyond d_r_max (first replica %d)", first);
+  if (any & kErrWcaCap)
+    return fail(h, CGPE_ERR_CAPACITY, "WCA neighbour list overflow (cap_wca=%d, first replica %d): raise cap_wca", h->p.cap_w, first);
+  return fail(h, CGPE_ERR_CAPACITY, "Debye-Hueckel neighbour list overflow (cap_dh=%d, first replica %d): raise cap_dh", h->p.cap_d, first);
+}
+
+int require_engine(cgpe_handle *h) {
+  if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
+  if (h->launch.items == 0)
+    return fail(h, CGPE_ERR_UNSUPPORTED, "P=%d particles per replica exceed the shared-memory engine (max 2048)", h->p.P);
+  return CGPE_OK;
+}
+
+void begin_timing(cgpe_handle *h) { cudaEventRecord(h->ev0, h->stream); h->last_launches = 0; }
+void end_timing(cgpe_handle *h, int launches) {
+  cudaEventRecord(h->ev1, h->stream);
+  h->timing_pending = true;
+  h->last_launches = launches;
+}
+
+uint32_t bernoulli_threshold(double p) {
+  if (!(p > 0.0)) return 0u;
+  if (p >= 1.0) return 16777216u;
+  return (uint32_t)std::ceil(p * 16777216.0);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cgpe_abi_version(void) { return CGPE_ABI_VERSION; }
+
+const char *cgpe_last_error(const cgpe_handle *h) { return h ? h->err : g_err; }
+
+int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
+  if (!out) return fail(nullptr, CGPE_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (cfg->n_ion_slots > 0) return fail(nullptr, CGPE_ERR_UNSUPPORTED, "explicit ions are not implemented yet");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, CGPE_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                cudaGetErrorString(ce));
+  int dev = cfg->device;
+  if (dev < 0) cudaGetDevice(&dev);
+  if (dev >= ndev) return fail(nullptr, CGPE_ERR_INVALID, "device %d out of range (%d devices)", dev, ndev);
+
+  cgpe_handle *h = new (std::nothrow) cgpe_handle();
+  if (!h) return fail(nullptr, CGPE_ERR_CUDA, "out of host memory");
+  h->cfg = *cfg;
+  h->device = dev;
+  h->err[0] = 0;
+  DeviceGuard guard(dev);
+
+  DevParams &p = h->p;
+  std::memset(&p, 0, sizeof(p));
+  p.R = cfg->n_replicas; p.N = cfg->n_beads; p.NC = cfg->n_chains * cfg->n_beads;
+  p.P = p.NC + cfg->n_ion_slots; p.T = cfg->n_types; p.n_rx = cfg->n_reactions;
+  p.bond_kind = cfg->bond_kind; p.use_angle = cfg->use_angle; p.use_dih = cfg->use_dihedral;
+  p.dih_mult = cfg->dihedral_mult; p.use_wca = cfg->use_wca; p.use_dh = cfg->use_dh;
+  p.replica_offset = cfg->replica_offset;
+  p.bond_k = (float)cfg->bond_k; p.bond_r0 = (float)cfg->bond_r0;
+  p.fene_drmax2 = (float)(cfg->fene_drmax * cfg->fene_drmax);
+  p.angle_k = (float)cfg->angle_k; p.angle_phi0 = (float)cfg->angle_phi0;
+  p.dih_k = (float)cfg->dihedral_k;
+  p.dih_cos_phase = (float)std::cos(cfg->dihedral_phase); p.dih_sin_phase = (float)std::sin(cfg->dihedral_phase);
+  p.dh_pref = (float)cfg->dh_prefactor;
+  p.box_l = (float)cfg->box_l; p.inv_box_l = (float)(1.0 / cfg->box_l);
+  p.dt = (float)cfg->time_step; p.half_dt = (float)(0.5 * cfg->time_step); p.dt_d = cfg->time_step;
+  const double skin = cfg->skin > 0.0 ? cfg->skin : 0.8;
+  p.skin = (float)skin; p.half_skin2 = (float)(0.25 * skin * skin);
+  p.force_cap = 0.f;
+  p.thermostat_seed = 0u;
+  for (int m = 0; m < p.n_rx; ++m) {
+    const cgpe_reaction &r = cfg->reactions[m];
+    DevReaction &d = p.rx[m];
+    d.type_prot = r.type_prot; d.type_deprot = r.type_deprot; d.type_ion = r.type_ion;
+    d.seed = (uint32_t)r.seed;
+    d.q_prot = (float)r.q_prot; d.q_deprot = (float)r.q_deprot; d.q_ion = (float)r.q_ion;
+    d.inv_kT = (float)(1.0 / r.kT); d.pK = r.pK;
+  }
+  // chargeable particles are fixed at set_state; size the lists for "every third bead" + ions
+  p.n_chg = 0;
+  p.cap_w = cfg->cap_wca; p.cap_d = cfg->cap_dh;   // 0: chosen at set_state (choose_capacities)
+  if (p.cap_w > 255 || p.cap_d > 255 || p.cap_w < 0 || p.cap_d < 0) { delete h; return fail(nullptr, CGPE_ERR_INVALID, "list capacities must be <= 255"); }
+
+  auto bail = [&](cudaError_t e, const char *what) {
+    fail(nullptr, CGPE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    cgpe_destroy(h);
+    return CGPE_ERR_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  h->stream = h->own_stream;
+  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  const size_t RP = (size_t)p.R * p.P, nrx = p.n_rx > 0 ? p.n_rx : 1;
+  DevState &g = h->g;
+#define ALLOC(ptr, n) if ((e = dev_alloc(h, &(ptr), (n))) != cudaSuccess) return bail(e, "cudaMalloc " #ptr)
+  ALLOC(g.pos, RP); ALLOC(g.vel, RP); ALLOC(g.frc, RP); ALLOC(g.type, RP);
+  ALLOC(g.wca_tab, (size_t)(p.T + 1) * (p.T + 1));
+  ALLOC(g.chg, RP);
+  ALLOC(g.lst_prot, (size_t)p.R * nrx * p.P); ALLOC(g.lst_deprot, (size_t)p.R * nrx * p.P);
+  ALLOC(g.cnt, (size_t)p.R * nrx * 2);
+  ALLOC(g.kappa, p.R); ALLOC(g.rcut, p.R); ALLOC(g.kT, p.R); ALLOC(g.gamma, p.R); ALLOC(g.pH, p.R);
+  ALLOC(g.time, p.R); ALLOC(g.md_counter, p.R); ALLOC(g.md_steps, p.R); ALLOC(g.samples_done, p.R);
+  ALLOC(g.rebuilds, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
+  ALLOC(g.f_valid, p.R); ALLOC(g.err, p.R);
+  ALLOC(h->d_tmp_d, (size_t)p.R * 8); ALLOC(h->d_tmp_i, (size_t)p.R * 3); ALLOC(h->d_tmp_f4, RP);
+#undef ALLOC
+  std::vector<double> d(p.R);
+  std::vector<float> f(p.R);
+  auto up_f = [&](float *dst, double v) { for (auto &x : f) x = (float)v; return cudaMemcpy(dst, f.data(), sizeof(float) * p.R, cudaMemcpyHostToDevice); };
+  if ((e = up_f(g.kappa, cfg->kappa)) != cudaSuccess) return bail(e, "upload kappa");
+  if ((e = up_f(g.rcut, cfg->use_dh ? cfg->r_cut : 1.0)) != cudaSuccess) return bail(e, "upload rcut");
+  if ((e = up_f(g.kT, cfg->kT)) != cudaSuccess) return bail(e, "upload kT");
+  if ((e = up_f(g.gamma, cfg->gamma)) != cudaSuccess) return bail(e, "upload gamma");
+  for (auto &x : d) x = cfg->pH;
+  if ((e = cudaMemcpy(g.pH, d.data(), sizeof(double) * p.R, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload pH");
+  if ((rc = upload_wca(h)) != CGPE_OK) { std::snprintf(g_err, 512, "%s", h->err); cgpe_destroy(h); return rc; }
+  *out = h;
+  return CGPE_OK;
+}
+
+void cgpe_destroy(cgpe_handle *h) {
+  if (!h) return;
+  DeviceGuard guard(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  for (void *ptr : h->allocs) cudaFree(ptr);
+  if (h->d_obs) cudaFree(h->d_obs);
+  if (h->d_qdist) cudaFree(h->d_qdist);
+  if (h->d_trace) cudaFree(h->d_trace);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int cgpe_device_info(const cgpe_handle *hc, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, char *name,
+                     int32_t name_len) {
+  cgpe_handle *h = const_cast<cgpe_handle *>(hc);
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, h->device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (name && name_len > 0) std::snprintf(name, (size_t)name_len, "%s", prop.name);
+  return CGPE_OK;
+}
+
+int cgpe_set_stream(cgpe_handle *h, void *cuda_stream) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  DeviceGuard guard(h->device);
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return CGPE_OK;
+}
+
+int cgpe_synchronize(cgpe_handle *h) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  DeviceGuard guard(h->device);
+  CU(cudaStreamSynchronize(h->stream));
+  return h->have_state ? check_device_errors(h) : CGPE_OK;
+}
+
+int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const uint8_t *type) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!xyzq || !type) return fail(h, CGPE_ERR_INVALID, "xyzq and type are required");
+  DeviceGuard guard(h->device);
+  DevParams &p = h->p;
+  const size_t RP = (size_t)p.R * p.P;
+  for (size_t k = 0; k < RP; ++k) {
+    if (type[k] > p.T) return fail(h, CGPE_ERR_INVALID, "type index %d out of range at particle %zu", (int)type[k], k);
+    if (!std::isfinite(xyzq[4 * k]) || !std::isfinite(xyzq[4 * k + 1]) || !std::isfinite(xyzq[4 * k + 2]))
+      return fail(h, CGPE_ERR_INVALID, "non-finite coordinate at particle %zu", k);
+  }
+  // particles that can carry charge: charged now, or of a type a reaction can charge
+  unsigned reactive = 0;
+  for (int m = 0; m < p.n_rx; ++m) reactive |= (1u << h->cfg.reactions[m].type_prot) | (1u << h->cfg.reactions[m].type_deprot);
+  std::vector<int> chg(RP, 0);
+  int n_chg = -1;
+  for (int r = 0; r < p.R; ++r) {
+    int n = 0;
+    for (int i = 0; i < p.P; ++i) {
+      const size_t k = (size_t)r * p.P + i;
+      if (xyzq[4 * k + 3] != 0.f || ((reactive >> type[k]) & 1u) || i >= p.NC) chg[(size_t)r * p.P + n++] = i;
+    }
+    if (n_chg >= 0 && n != n_chg) return fail(h, CGPE_ERR_INVALID, "replicas differ in the number of chargeable particles");
+    n_chg = n;
+  }
+  std::vector<int> chg_packed((size_t)p.R * (n_chg > 0 ? n_chg : 1));
+  for (int r = 0; r < p.R; ++r)
+    for (int i = 0; i < n_chg; ++i) chg_packed[(size_t)r * n_chg + i] = chg[(size_t)r * p.P + i];
+  p.n_chg = n_chg;
+  {
+    int rc_cap = choose_capacities(h);
+    if (rc_cap) return rc_cap;
+  }
+  if (h->launch.items != 0) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    if (h->launch.smem > (size_t)prop.sharedMemPerBlockOptin)
+      return fail(h, CGPE_ERR_UNSUPPORTED, "replica needs %zu B of shared memory, device offers %zu B per block",
+                  h->launch.smem, (size_t)prop.sharedMemPerBlockOptin);
+  }
+  // bookkeeping lists in particle-id order
+  const size_t nrx = p.n_rx > 0 ? p.n_rx : 1;
+  std::vector<int> lp((size_t)p.R * nrx * p.P, 0), ld((size_t)p.R * nrx * p.P, 0), cnt((size_t)p.R * nrx * 2, 0);
+  for (int r = 0; r < p.R; ++r)
+    for (int m = 0; m < p.n_rx; ++m) {
+      int np = 0, nd = 0;
+      const size_t o = ((size_t)r * nrx + m) * p.P;
+      for (int i = 0; i < p.P; ++i) {
+        const int t = type[(size_t)r * p.P + i];
+        if (t == h->cfg.reactions[m].type_prot) lp[o + np++] = i;
+        else if (t == h->cfg.reactions[m].type_deprot) ld[o + nd++] = i;
+      }
+      cnt[((size_t)r * nrx + m) * 2] = np; cnt[((size_t)r * nrx + m) * 2 + 1] = nd;
+    }
+  std::vector<float> zero;
+  if (!vel) zero.assign(RP * 4, 0.f);
+  CU(cudaMemcpyAsync(h->g.pos, xyzq, sizeof(float4) * RP, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->g.vel, vel ? vel : zero.data(), sizeof(float4) * RP, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->g.type, type, RP, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->g.chg, chg_packed.data(), sizeof(int) * chg_packed.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->g.lst_prot, lp.data(), sizeof(int) * lp.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->g.lst_deprot, ld.data(), sizeof(int) * ld.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->g.cnt, cnt.data(), sizeof(int) * cnt.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->g.f_valid, 0, sizeof(int) * p.R, h->stream));
+  CU(cudaMemsetAsync(h->g.err, 0, sizeof(int) * p.R, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_state = true;
+  return CGPE_OK;
+}
+
+int cgpe_get_state(cgpe_handle *h, float *xyzq, float *vel, uint8_t *type) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
+  DeviceGuard guard(h->device);
+  const size_t RP = (size_t)h->p.R * h->p.P;
+  if (xyzq) CU(cudaMemcpyAsync(xyzq, h->g.pos, sizeof(float4) * RP, cudaMemcpyDeviceToHost, h->stream));
+  if (vel) CU(cudaMemcpyAsync(vel, h->g.vel, sizeof(float4) * RP, cudaMemcpyDeviceToHost, h->stream));
+  if (type) CU(cudaMemcpyAsync(type, h->g.type, RP, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_device_errors(h);
+}
+
+int cgpe_set_replica_params(cgpe_handle *h, const double *pH, const double *kappa, const double *r_cut,
+                            const double *kT, const double *gamma) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  DeviceGuard guard(h->device);
+  const int R = h->p.R;
+  std::vector<float> f(R);
+  auto up = [&](float *dst, const double *src) {
+    for (int r = 0; r < R; ++r) f[r] = (float)src[r];
+    cudaError_t e = cudaMemcpyAsync(dst, f.data(), sizeof(float) * R, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    return e;
+  };
+  if (r_cut) {
+    double rc_max = 0.0;
+    for (int r = 0; r < R; ++r) {
+      if (!(r_cut[r] > 0.0) || r_cut[r] + h->p.skin > 0.5 * h->cfg.box_l)
+        return fail(h, CGPE_ERR_INVALID, "r_cut + skin must lie in (0, box_l/2] (replica %d: %g)", r, r_cut[r]);
+      rc_max = std::fmax(rc_max, r_cut[r]);
+    }
+    h->cfg.r_cut = rc_max;
+    if (h->have_state) {
+      int rc_cap = choose_capacities(h);
+      if (rc_cap) return rc_cap;
+    }
+    CU(up(h->g.rcut, r_cut));
+  }
+  if (kappa) CU(up(h->g.kappa, kappa));
+  if (kT) {
+    for (int r = 0; r < R; ++r) if (kT[r] < 0.0) return fail(h, CGPE_ERR_INVALID, "kT must be >= 0");
+    CU(up(h->g.kT, kT));
+  }
+  if (gamma) {
+    for (int r = 0; r < R; ++r) if (gamma[r] < 0.0) return fail(h, CGPE_ERR_INVALID, "gamma must be >= 0");
+    CU(up(h->g.gamma, gamma));
+  }
+  if (pH) {
+    CU(cudaMemcpyAsync(h->g.pH, pH, sizeof(double) * R, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  if (kappa || r_cut || kT || gamma) CU(cudaMemsetAsync(h->g.f_valid, 0, sizeof(int) * R, h->stream));
+  return CGPE_OK;
+}
+
+int cgpe_set_wca(cgpe_handle *h, const double *eps, const double *sig) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!eps || !sig) return fail(h, CGPE_ERR_INVALID, "eps and sig are required");
+  DeviceGuard guard(h->device);
+  std::memcpy(h->cfg.wca_eps, eps, sizeof(h->cfg.wca_eps));
+  std::memcpy(h->cfg.wca_sig, sig, sizeof(h->cfg.wca_sig));
+  int rc = upload_wca(h);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(h->g.f_valid, 0, sizeof(int) * h->p.R, h->stream));
+  return CGPE_OK;
+}
+
+int cgpe_set_thermostat_seed(cgpe_handle *h, int32_t seed) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  DeviceGuard guard(h->device);
+  if (seed >= 0) {
+    h->p.thermostat_seed = (uint32_t)seed;
+    CU(cudaMemsetAsync(h->g.md_counter, 0, sizeof(long long) * h->p.R, h->stream));
+  }
+  CU(cudaMemsetAsync(h->g.f_valid, 0, sizeof(int) * h->p.R, h->stream));
+  return CGPE_OK;
+}
+
+int cgpe_set_force_cap(cgpe_handle *h, double cap) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (cap < 0.0) return fail(h, CGPE_ERR_INVALID, "force cap must be >= 0");
+  DeviceGuard guard(h->device);
+  h->p.force_cap = (float)cap;
+  CU(cudaMemsetAsync(h->g.f_valid, 0, sizeof(int) * h->p.R, h->stream));
+  return CGPE_OK;
+}
+
+int cgpe_set_time(cgpe_handle *h, double t) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  DeviceGuard guard(h->device);
+  std::vector<double> v(h->p.R, t);
+  CU(cudaMemcpyAsync(h->g.time, v.data(), sizeof(double) * h->p.R, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return CGPE_OK;
+}
+
+int cgpe_get_time(cgpe_handle *h, double *t) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!t) return fail(h, CGPE_ERR_INVALID, "t is NULL");
+  DeviceGuard guard(h->device);
+  CU(cudaMemcpyAsync(t, h->g.time, sizeof(double) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return CGPE_OK;
+}
+
+int cgpe_md_run(cgpe_handle *h, int32_t n_steps) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (n_steps < 0) return fail(h, CGPE_ERR_INVALID, "n_steps must be >= 0");
+  int rc = require_engine(h);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  begin_timing(h);
+  CU(launch_md_run(h->p, h->g, h->launch, n_steps, h->stream));
+  end_timing(h, 1);
+  return CGPE_OK;
+}
+
+int cgpe_steepest_descent(cgpe_handle *h, int32_t n_steps, double f_max, double gamma, double max_displacement) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (n_steps < 0 || f_max < 0.0 || gamma < 0.0 || max_displacement < 0.0)
+    return fail(h, CGPE_ERR_INVALID, "steepest descent parameters must be >= 0");
+  int rc = require_engine(h);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  begin_timing(h);
+  CU(launch_steepest_descent(h->p, h->g, h->launch, n_steps, (float)f_max, (float)gamma, (float)max_displacement, h->stream));
+  end_timing(h, 1);
+  return CGPE_OK;
+}
+
+int cgpe_mc_run(cgpe_handle *h, int32_t reaction_id, int32_t n_trials, cgpe_trial_record *trace) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (reaction_id < 0 || reaction_id >= h->p.n_rx) return fail(h, CGPE_ERR_INVALID, "reaction_id out of range");
+  if (n_trials < 0) return fail(h, CGPE_ERR_INVALID, "n_trials must be >= 0");
+  int rc = require_engine(h);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  cgpe_trial_record *d_trace = nullptr;
+  const size_t n_rec = (size_t)h->p.R * n_trials;
+  if (trace && n_rec > 0) {
+    if (n_rec > h->trace_cap) {
+      if (h->d_trace) cudaFree(h->d_trace);
+      h->d_trace = nullptr; h->trace_cap = 0;
+      CU(cudaMalloc((void **)&h->d_trace, sizeof(cgpe_trial_record) * n_rec));
+      h->trace_cap = n_rec;
+    }
+    d_trace = h->d_trace;
+  }
+  begin_timing(h);
+  CU(launch_mc_run(h->p, h->g, h->launch, reaction_id, n_trials, d_trace, h->stream));
+  end_timing(h, 1);
+  if (d_trace) {
+    CU(cudaMemcpyAsync(trace, d_trace, sizeof(cgpe_trial_record) * n_rec, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return check_device_errors(h);
+  }
+  return CGPE_OK;
+}
+
+int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!sp || sp->n_samples < 0 || sp->n_mc_blocks < 0 || sp->n_mc_blocks > CGPE_MAX_MC_BLOCKS ||
+      sp->md_steps_per_burst < 0)
+    return fail(h, CGPE_ERR_INVALID, "bad sample params");
+  for (int b = 0; b < sp->n_mc_blocks; ++b)
+    if (sp->mc_reaction[b] < 0 || sp->mc_reaction[b] >= h->p.n_rx || sp->mc_trials[b] < 0)
+      return fail(h, CGPE_ERR_INVALID, "bad MC block %d", b);
+  int rc = require_engine(h);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  const size_t n_obs = (size_t)h->p.R * (sp->n_samples > 0 ? sp->n_samples : 1) * CGPE_N_OBS;
+  const int rows = sp->q_snapshot_every > 0 ? sp->q_snapshot_rows : 0;
+  const size_t n_q = (size_t)h->p.R * (rows > 0 ? rows : 0) * h->p.N;
+  if (n_obs > h->obs_cap) {
+    if (h->d_obs) cudaFree(h->d_obs);
+    h->d_obs = nullptr; h->obs_cap = 0;
+    CU(cudaMalloc((void **)&h->d_obs, sizeof(double) * n_obs));
+    h->obs_cap = n_obs;
+  }
+  if (n_q > h->qdist_cap) {
+    if (h->d_qdist) cudaFree(h->d_qdist);
+    h->d_qdist = nullptr; h->qdist_cap = 0;
+    CU(cudaMalloc((void **)&h->d_qdist, sizeof(float) * n_q));
+    h->qdist_cap = n_q;
+  }
+  if (n_q > 0) CU(cudaMemsetAsync(h->d_qdist, 0, sizeof(float) * n_q, h->stream));
+  h->last_ns = sp->n_samples; h->last_qrows = rows;
+  begin_timing(h);
+  CU(launch_sample_loop(h->p, h->g, h->launch, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
+                        h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
+  end_timing(h, 1);
+  return CGPE_OK;
+}
+
+int cgpe_fetch_samples(cgpe_handle *h, double *obs, float *qdist) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!h->d_obs) return fail(h, CGPE_ERR_STATE, "no sample loop has run");
+  DeviceGuard guard(h->device);
+  if (obs && h->last_ns > 0)
+    CU(cudaMemcpyAsync(obs, h->d_obs, sizeof(double) * (size_t)h->p.R * h->last_ns * CGPE_N_OBS, cudaMemcpyDeviceToHost, h->stream));
+  if (qdist && h->last_qrows > 0)
+    CU(cudaMemcpyAsync(qdist, h->d_qdist, sizeof(float) * (size_t)h->p.R * h->last_qrows * h->p.N, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_device_errors(h);
+}
+
+int cgpe_sample_loop(cgpe_handle *h, const cgpe_sample_params *sp, double *obs, float *qdist) {
+  int rc = cgpe_sample_loop_async(h, sp);
+  if (rc) return rc;
+  return cgpe_fetch_samples(h, obs, qdist);
+}
+
+int cgpe_energy(cgpe_handle *h, double *out) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!out) return fail(h, CGPE_ERR_INVALID, "out is NULL");
+  if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
+  DeviceGuard guard(h->device);
+  CU(launch_energy(h->p, h->g, h->d_tmp_d, h->stream));
+  CU(cudaMemcpyAsync(out, h->d_tmp_d, sizeof(double) * h->p.R * CGPE_N_ENERGY, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_device_errors(h);
+}
+
+int cgpe_forces(cgpe_handle *h, float *out) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!out) return fail(h, CGPE_ERR_INVALID, "out is NULL");
+  if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
+  DeviceGuard guard(h->device);
+  CU(launch_forces(h->p, h->g, h->d_tmp_f4, h->stream));
+  CU(cudaMemcpyAsync(out, h->d_tmp_f4, sizeof(float4) * (size_t)h->p.R * h->p.P, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_device_errors(h);
+}
+
+int cgpe_md_forces(cgpe_handle *h, float *out) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!out) return fail(h, CGPE_ERR_INVALID, "out is NULL");
+  int rc = require_engine(h);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  CU(launch_md_forces(h->p, h->g, h->launch, h->d_tmp_f4, h->stream));
+  CU(cudaMemcpyAsync(out, h->d_tmp_f4, sizeof(float4) * (size_t)h->p.R * h->p.P, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_device_errors(h);
+}
+
+int cgpe_observables(cgpe_handle *h, double *rg, double *ree, int32_t *counts) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
+  DeviceGuard guard(h->device);
+  const int R = h->p.R;
+  CU(launch_observables(h->p, h->g, h->d_tmp_d, h->d_tmp_d + R, h->d_tmp_i, h->stream));
+  if (rg) CU(cudaMemcpyAsync(rg, h->d_tmp_d, sizeof(double) * R, cudaMemcpyDeviceToHost, h->stream));
+  if (ree) CU(cudaMemcpyAsync(ree, h->d_tmp_d + R, sizeof(double) * R, cudaMemcpyDeviceToHost, h->stream));
+  if (counts) CU(cudaMemcpyAsync(counts, h->d_tmp_i, sizeof(int) * R * 3, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_device_errors(h);
+}
+
+int cgpe_min_dist(cgpe_handle *h, double *out) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!out) return fail(h, CGPE_ERR_INVALID, "out is NULL");
+  if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
+  DeviceGuard guard(h->device);
+  CU(launch_min_dist(h->p, h->g, h->d_tmp_d, h->stream));
+  CU(cudaMemcpyAsync(out, h->d_tmp_d, sizeof(double) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_device_errors(h);
+}
+
+int cgpe_get_counters(cgpe_handle *h, int64_t *md_steps, int64_t *trials, int64_t *accepted, int64_t *list_rebuilds) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  DeviceGuard guard(h->device);
+  const int R = h->p.R, nrx = h->p.n_rx;
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+  if (md_steps) CU(cudaMemcpyAsync(md_steps, h->g.md_steps, sizeof(int64_t) * R, cudaMemcpyDeviceToHost, h->stream));
+  if (trials && nrx > 0) CU(cudaMemcpyAsync(trials, h->g.trials, sizeof(int64_t) * R * nrx, cudaMemcpyDeviceToHost, h->stream));
+  if (accepted && nrx > 0) CU(cudaMemcpyAsync(accepted, h->g.accepted, sizeof(int64_t) * R * nrx, cudaMemcpyDeviceToHost, h->stream));
+  if (list_rebuilds) CU(cudaMemcpyAsync(list_rebuilds, h->g.rebuilds, sizeof(int64_t) * R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return CGPE_OK;
+}
+
+int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  DeviceGuard guard(h->device);
+  float t = 0.f;
+  if (h->timing_pending) {
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+  }
+  if (ms) *ms = t;
+  if (n_launches) *n_launches = h->last_launches;
+  return CGPE_OK;
+}
+
+}  // extern "C"

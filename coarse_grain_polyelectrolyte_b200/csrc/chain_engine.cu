@@ -1,0 +1,775 @@
+// chain_engine.cu — the hot path: one persistent CTA per replica, whole replica resident in
+// shared memory (sm_100a, up to 227 KB per CTA).
+//
+//   * positions+charge float4 in shared memory, velocity / force / list reference position in
+//     registers of the owning thread (thread t owns particles t, t+blockDim, ...);
+//   * two Verlet lists in shared memory (uint16 ids): a short one for WCA (all particles, radius
+//     max WCA cutoff + skin) and one for Debye-Hueckel over the particles that can carry charge
+//     (titratable sites [+ ions], radius r_cut + skin); rebuilt when any particle has moved
+//     more than skin/2, detected with one __syncthreads_or per step;
+//   * bonded terms are computed once by an owner thread (bond (i-1,i), angle (i-1,i,i+1),
+//     dihedral (i-1,i,i+1,i+2) belong to bead i) and handed to the partner beads through three
+//     conflict-free shared-memory slots, so a step costs two block barriers;
+//   * the constant-pH trial moves run on warp 0: Philox draws for 32 trials at a time, Delta-E as
+//     a warp-shuffle reduction over the site's list rows, decision and O(1) list bookkeeping;
+//   * the sampling loop of EnsembleDynamics.perform_sampling (E.py:88-106) runs entirely inside
+//     one launch: MD bursts, MC blocks, observables, no host round trip per sample.
+//
+// Reference call sites replaced (relative to /root/reference/src/modules):
+//   integrator.run            EnsembleDynamics.py:41,52,58,64,73,90,92
+//   reaction.reaction         EnsembleDynamics.py:70-71,94-95
+//   calc_rg / calc_re / number_of_particles   EnsembleDynamics.py:97-101
+#include "chain_engine.cuh"
+
+namespace cgpe {
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up (same function on host, for the size, and on device, for the pointers)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ size_t chain_smem_layout(const DevParams &p, ChainSmem *s, unsigned char *base) {
+  size_t o = 0;
+  const int TT = (p.T + 1) * (p.T + 1);
+  auto take = [&](size_t bytes, size_t align) { o = align_up(o, align); size_t at = o; o += bytes; return at; };
+  size_t a_pos = take(sizeof(float4) * p.P, 16);
+  size_t a_tab = take(sizeof(float4) * TT, 16);
+  size_t a_red = take(sizeof(double) * 32 * 4, 8);
+  size_t a_slot = take(sizeof(float) * 9 * p.NC, 4);
+  size_t a_fd = take(sizeof(float) * 3 * (p.n_chg > 0 ? p.n_chg : 1), 4);
+  size_t a_cnt = take(sizeof(int) * kMaxRx * 2, 4);
+  size_t a_flag = take(sizeof(int) * 4, 4);
+  size_t a_wl = take(sizeof(uint16_t) * (size_t)p.cap_w * p.P, 4);
+  size_t a_dl = take(sizeof(uint16_t) * (size_t)p.cap_d * (p.n_chg > 0 ? p.n_chg : 1), 4);
+  size_t a_chg = take(sizeof(uint16_t) * (p.n_chg > 0 ? p.n_chg : 1), 2);
+  size_t a_cidx = take(sizeof(uint16_t) * p.P, 2);
+  size_t a_lp = take(sizeof(uint16_t) * (size_t)(p.n_rx > 0 ? p.n_rx : 1) * (p.n_chg > 0 ? p.n_chg : 1), 2);
+  size_t a_ld = take(sizeof(uint16_t) * (size_t)(p.n_rx > 0 ? p.n_rx : 1) * (p.n_chg > 0 ? p.n_chg : 1), 2);
+  size_t a_wn = take((size_t)p.P, 1);
+  size_t a_dn = take((size_t)(p.n_chg > 0 ? p.n_chg : 1), 1);
+  size_t a_type = take((size_t)p.P, 1);
+  if (s) {
+    s->pos = reinterpret_cast<float4 *>(base + a_pos);
+    s->tab = reinterpret_cast<float4 *>(base + a_tab);
+    s->red = reinterpret_cast<double *>(base + a_red);
+    s->slot = reinterpret_cast<float *>(base + a_slot);
+    s->fd = reinterpret_cast<float *>(base + a_fd);
+    s->cnt = reinterpret_cast<int *>(base + a_cnt);
+    s->flag = reinterpret_cast<int *>(base + a_flag);
+    s->wl = reinterpret_cast<uint16_t *>(base + a_wl);
+    s->dl = reinterpret_cast<uint16_t *>(base + a_dl);
+    s->chg = reinterpret_cast<uint16_t *>(base + a_chg);
+    s->cidx = reinterpret_cast<uint16_t *>(base + a_cidx);
+    s->lp = reinterpret_cast<uint16_t *>(base + a_lp);
+    s->ld = reinterpret_cast<uint16_t *>(base + a_ld);
+    s->wn = base + a_wn;
+    s->dn = base + a_dn;
+    s->type = base + a_type;
+  }
+  return align_up(o, 16);
+}
+
+size_t chain_smem_bytes(const DevParams &p) { return chain_smem_layout(p, nullptr, nullptr); }
+
+namespace {
+
+// per-thread registers: ITEMS particles per thread
+template <int ITEMS>
+struct Thr {
+  float x[ITEMS][3], v[ITEMS][3], f[ITEMS][3], ref[ITEMS][3];
+};
+
+struct Ctx {
+  const DevParams &p;
+  const DevState &g;
+  ChainSmem s;
+  int r;              // replica (local)
+  int tid, nt, lane, warp;
+  float kappa, rc2, neg_kappa_log2e, rlist_d2, gamma, noise_pref;
+  int err;            // thread-local error bits, merged at exit
+  long long rebuilds; // uniform
+};
+
+__device__ __forceinline__ float dist2(const Ctx &c, float4 a, float4 b, V3 *d) {
+  d->x = min_image(a.x - b.x, c.p.box_l, c.p.inv_box_l);
+  d->y = min_image(a.y - b.y, c.p.box_l, c.p.inv_box_l);
+  d->z = min_image(a.z - b.z, c.p.box_l, c.p.inv_box_l);
+  return fmaf(d->x, d->x, fmaf(d->y, d->y, d->z * d->z));
+}
+
+// ---- load / store ------------------------------------------------------------------------------
+template <int ITEMS>
+__device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
+  const DevParams &p = c.p;
+  const size_t base = (size_t)c.r * p.P;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i < p.P) {
+      const float4 pq = c.g.pos[base + i], vv = c.g.vel[base + i];
+      c.s.pos[i] = pq;
+      t.x[k][0] = pq.x; t.x[k][1] = pq.y; t.x[k][2] = pq.z;
+      t.v[k][0] = vv.x; t.v[k][1] = vv.y; t.v[k][2] = vv.z;
+      float4 ff = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f_valid) ff = c.g.frc[base + i];
+      t.f[k][0] = ff.x; t.f[k][1] = ff.y; t.f[k][2] = ff.z;
+      c.s.type[i] = c.g.type[base + i];
+      c.s.cidx[i] = 0xFFFFu;
+      c.s.wn[i] = 0;
+    }
+  }
+  for (int i = c.tid; i < 9 * p.NC; i += c.nt) c.s.slot[i] = 0.0f;
+  for (int i = c.tid; i < (p.T + 1) * (p.T + 1); i += c.nt) c.s.tab[i] = c.g.wca_tab[i];
+  for (int i = c.tid; i < p.n_chg; i += c.nt) {
+    c.s.chg[i] = (uint16_t)c.g.chg[(size_t)c.r * p.n_chg + i];
+    c.s.dn[i] = 0;
+    c.s.fd[i] = c.s.fd[p.n_chg + i] = c.s.fd[2 * p.n_chg + i] = 0.0f;
+  }
+  for (int m = 0; m < p.n_rx; ++m) {
+    const int *gp = c.g.lst_prot + ((size_t)c.r * p.n_rx + m) * p.P;
+    const int *gd = c.g.lst_deprot + ((size_t)c.r * p.n_rx + m) * p.P;
+    const int np = c.g.cnt[((size_t)c.r * p.n_rx + m) * 2], nd = c.g.cnt[((size_t)c.r * p.n_rx + m) * 2 + 1];
+    for (int i = c.tid; i < np; i += c.nt) c.s.lp[(size_t)m * p.n_chg + i] = (uint16_t)gp[i];
+    for (int i = c.tid; i < nd; i += c.nt) c.s.ld[(size_t)m * p.n_chg + i] = (uint16_t)gd[i];
+    if (c.tid == 0) { c.s.cnt[m * 2] = np; c.s.cnt[m * 2 + 1] = nd; }
+  }
+  __syncthreads();
+  for (int i = c.tid; i < p.n_chg; i += c.nt) c.s.cidx[c.s.chg[i]] = (uint16_t)i;
+  __syncthreads();
+}
+
+template <int ITEMS>
+__device__ void store_state(Ctx &c, Thr<ITEMS> &t, bool store_forces) {
+  const DevParams &p = c.p;
+  const size_t base = (size_t)c.r * p.P;
+  __syncthreads();
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i < p.P) {
+      const float q = c.s.pos[i].w;
+      c.g.pos[base + i] = make_float4(t.x[k][0], t.x[k][1], t.x[k][2], q);
+      c.g.vel[base + i] = make_float4(t.v[k][0], t.v[k][1], t.v[k][2], 0.f);
+      if (store_forces) c.g.frc[base + i] = make_float4(t.f[k][0], t.f[k][1], t.f[k][2], 0.f);
+      c.g.type[base + i] = c.s.type[i];
+      if (!isfinite(t.x[k][0] + t.x[k][1] + t.x[k][2] + t.v[k][0] + t.v[k][1] + t.v[k][2])) bad = 1;
+    }
+  }
+  if (bad) c.err |= kErrNonFinite;
+  for (int m = 0; m < p.n_rx; ++m) {
+    int *gp = c.g.lst_prot + ((size_t)c.r * p.n_rx + m) * p.P;
+    int *gd = c.g.lst_deprot + ((size_t)c.r * p.n_rx + m) * p.P;
+    const int np = c.s.cnt[m * 2], nd = c.s.cnt[m * 2 + 1];
+    for (int i = c.tid; i < np; i += c.nt) gp[i] = c.s.lp[(size_t)m * p.n_chg + i];
+    for (int i = c.tid; i < nd; i += c.nt) gd[i] = c.s.ld[(size_t)m * p.n_chg + i];
+    if (c.tid == 0) { c.g.cnt[((size_t)c.r * p.n_rx + m) * 2] = np; c.g.cnt[((size_t)c.r * p.n_rx + m) * 2 + 1] = nd; }
+  }
+  if (c.err) atomicOr(&c.g.err[c.r], c.err);
+  if (c.tid == 0 && c.rebuilds) c.g.rebuilds[c.r] += c.rebuilds;
+}
+
+// ---- Verlet lists ------------------------------------------------------------------------------
+// Requires s.pos current and visible (barrier before).  Rows are written and later read by the
+// same thread, so the MD loop needs no barrier after this; the MC warp gets one anyway.
+template <int ITEMS>
+__device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
+  const DevParams &p = c.p;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i < p.P) {
+      t.ref[k][0] = t.x[k][0]; t.ref[k][1] = t.x[k][1]; t.ref[k][2] = t.x[k][2];
+      if (p.use_wca) {
+        const float4 pi = c.s.pos[i];
+        int n = 0;
+        for (int j = 0; j < p.P; ++j) {
+          V3 d;
+          const float r2 = dist2(c, pi, c.s.pos[j], &d);
+          if (r2 < p.rlist_w2 && j != i) {
+            if (n < p.cap_w) c.s.wl[(size_t)n * p.P + i] = (uint16_t)j;
+            ++n;
+          }
+        }
+        if (n > p.cap_w) { c.err |= kErrWcaCap; n = p.cap_w; }
+        c.s.wn[i] = (unsigned char)n;
+      }
+    }
+  }
+  if (p.use_dh) {
+    for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
+      const int i = c.s.chg[ci];
+      const float4 pi = c.s.pos[i];
+      int n = 0;
+      for (int cj = 0; cj < p.n_chg; ++cj) {
+        const int j = c.s.chg[cj];
+        V3 d;
+        const float r2 = dist2(c, pi, c.s.pos[j], &d);
+        if (r2 < c.rlist_d2 && cj != ci) {
+          if (n < p.cap_d) c.s.dl[(size_t)n * p.n_chg + ci] = (uint16_t)j;
+          ++n;
+        }
+      }
+      if (n > p.cap_d) { c.err |= kErrDhCap; n = p.cap_d; }
+      c.s.dn[ci] = (unsigned char)n;
+    }
+  }
+  c.rebuilds += 1;
+}
+
+// ---- forces ------------------------------------------------------------------------------------
+// Phase 1 reads s.pos (must be visible), phase 2 gathers the slots.  thermostat: add
+// -gamma v + sqrt(24 gamma kT/dt)(U-1/2) with U from Philox(counter, particle) (E.py:61-63).
+template <int ITEMS>
+__device__ void compute_forces(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsigned long long counter) {
+  const DevParams &p = c.p;
+  const int NC = p.NC;
+  float *sa = c.s.slot, *sb = c.s.slot + 3 * NC, *sc = c.s.slot + 6 * NC;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    V3 f = {0.f, 0.f, 0.f};
+    if (i < p.P) {
+      const float4 pi4 = c.s.pos[i];
+      const V3 pi = xyz(pi4);
+      if (i < NC) {
+        const int l = i % p.N;  // index within the chain
+        if (l >= 1) {
+          const V3 pm1 = xyz(c.s.pos[i - 1]);
+          V3 to_prev = {0.f, 0.f, 0.f}, to_next = {0.f, 0.f, 0.f};
+          if (p.bond_kind != CGPE_BOND_NONE) {  // bond (i-1,i): M.py:159-160
+            V3 fb;
+            bond_term(p, pi, pm1, &fb, &c.err);
+            f = f + fb;
+            to_prev = to_prev - fb;
+          }
+          const bool has_angle = p.use_angle && l <= p.N - 2;  // M.py:161-165
+          const bool has_dih = p.use_dih && l <= p.N - 3;      // M.py:166-170
+          if (has_angle || has_dih) {
+            const V3 pp1 = xyz(c.s.pos[i + 1]);
+            if (has_angle) {
+              V3 fl, fm, fr;
+              angle_term(p, pm1, pi, pp1, &fl, &fm, &fr);
+              to_prev = to_prev + fl; f = f + fm; to_next = to_next + fr;
+            }
+            if (has_dih) {
+              const V3 pp2 = xyz(c.s.pos[i + 2]);
+              V3 f1, f2, f3, f4;
+              dihedral_term(p, pm1, pi, pp1, pp2, &f1, &f2, &f3, &f4);
+              to_prev = to_prev + f1; f = f + f2; to_next = to_next + f3;
+              sc[i + 2] = f4.x; sc[NC + i + 2] = f4.y; sc[2 * NC + i + 2] = f4.z;
+            }
+            sb[i + 1] = to_next.x; sb[NC + i + 1] = to_next.y; sb[2 * NC + i + 1] = to_next.z;
+          }
+          sa[i - 1] = to_prev.x; sa[NC + i - 1] = to_prev.y; sa[2 * NC + i - 1] = to_prev.z;
+        }
+      }
+      if (p.use_wca) {
+        const int ti = c.s.type[i];
+        if (ti < p.T) {
+          const int n = c.s.wn[i];
+          for (int e = 0; e < n; ++e) {
+            const int j = c.s.wl[(size_t)e * p.P + i];
+            const int tj = c.s.type[j];
+            V3 d;
+            const float r2 = dist2(c, pi4, c.s.pos[j], &d);
+            const float4 tab = c.s.tab[ti * (p.T + 1) + tj];
+            if (r2 < tab.z) f = f + wca_force_over_r(tab, r2) * d;
+          }
+        }
+      }
+    }
+    t.f[k][0] = f.x; t.f[k][1] = f.y; t.f[k][2] = f.z;
+  }
+  if (p.use_dh) {
+    for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
+      const int i = c.s.chg[ci];
+      const float4 pi4 = c.s.pos[i];
+      V3 f = {0.f, 0.f, 0.f};
+      if (pi4.w != 0.0f) {
+        const int n = c.s.dn[ci];
+        for (int e = 0; e < n; ++e) {
+          const int j = c.s.dl[(size_t)e * p.n_chg + ci];
+          const float4 pj4 = c.s.pos[j];
+          V3 d;
+          const float r2 = dist2(c, pi4, pj4, &d);
+          if (pj4.w != 0.0f && r2 < c.rc2) {
+            float fr;
+            dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr);
+            f = f + (p.dh_pref * pi4.w * pj4.w * fr) * d;
+          }
+        }
+      }
+      c.s.fd[ci] = f.x; c.s.fd[p.n_chg + ci] = f.y; c.s.fd[2 * p.n_chg + ci] = f.z;
+    }
+  }
+  __syncthreads();
+  const uint32_t k0 = p.thermostat_seed, k1 = (uint32_t)(p.replica_offset + c.r);
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i < p.P) {
+      float fx = t.f[k][0], fy = t.f[k][1], fz = t.f[k][2];
+      if (i < NC) {
+        fx += sa[i] + sb[i] + sc[i];
+        fy += sa[NC + i] + sb[NC + i] + sc[NC + i];
+        fz += sa[2 * NC + i] + sb[2 * NC + i] + sc[2 * NC + i];
+      }
+      if (p.use_dh) {
+        const int ci = c.s.cidx[i];
+        if (ci != 0xFFFF) { fx += c.s.fd[ci]; fy += c.s.fd[p.n_chg + ci]; fz += c.s.fd[2 * p.n_chg + ci]; }
+      }
+      if (thermostat && c.s.type[i] < p.T) {
+        const uint4 o = philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)i, kTagLangevin, k0, k1);
+        fx += fmaf(-c.gamma, t.v[k][0], c.noise_pref * centred_u23(o.x));
+        fy += fmaf(-c.gamma, t.v[k][1], c.noise_pref * centred_u23(o.y));
+        fz += fmaf(-c.gamma, t.v[k][2], c.noise_pref * centred_u23(o.z));
+      }
+      if (p.force_cap > 0.0f) {  // system.force_cap (E.py:32,48,51)
+        const float n2 = fx * fx + fy * fy + fz * fz;
+        if (n2 > p.force_cap * p.force_cap) {
+          const float sc_ = p.force_cap * rsqrtf(n2);
+          fx *= sc_; fy *= sc_; fz *= sc_;
+        }
+      }
+      t.f[k][0] = fx; t.f[k][1] = fy; t.f[k][2] = fz;
+    }
+  }
+}
+
+// ---- velocity Verlet + Langevin (R2) ------------------------------------------------------------
+template <int ITEMS>
+__device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long &counter, bool &f_valid,
+                         bool &lists_valid) {
+  const DevParams &p = c.p;
+  if (n_steps <= 0) return;
+  if (!lists_valid) { build_lists(c, t); lists_valid = true; }
+  if (!f_valid) { compute_forces(c, t, true, counter); f_valid = true; }
+  for (int step = 0; step < n_steps; ++step) {
+    int moved = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int i = c.tid + k * c.nt;
+      if (i < p.P) {
+        float d2 = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          t.v[k][a] = fmaf(p.half_dt, t.f[k][a], t.v[k][a]);
+          t.x[k][a] = fmaf(p.dt, t.v[k][a], t.x[k][a]);
+          const float d = t.x[k][a] - t.ref[k][a];
+          d2 = fmaf(d, d, d2);
+        }
+        float4 *sp = &c.s.pos[i];
+        sp->x = t.x[k][0]; sp->y = t.x[k][1]; sp->z = t.x[k][2];
+        moved |= !(d2 <= p.half_skin2);  // also true for NaN
+      }
+    }
+    if (__syncthreads_or(moved)) build_lists(c, t);
+    counter += 1;
+    compute_forces(c, t, true, counter);
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) t.v[k][a] = fmaf(p.half_dt, t.f[k][a], t.v[k][a]);
+  }
+}
+
+// ---- constant-pH trial moves (R1), warp 0 -------------------------------------------------------
+__device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_ctr, long long &accepted,
+                         cgpe_trial_record *trace) {
+  const DevParams &p = c.p;
+  if (c.warp == 0 && n_trials > 0) {
+    const DevReaction rx = p.rx[m];
+    uint16_t *lp = c.s.lp + (size_t)m * p.n_chg, *ld = c.s.ld + (size_t)m * p.n_chg;
+    int n_p = c.s.cnt[m * 2], n_d = c.s.cnt[m * 2 + 1];
+    const float arg_fwd = (float)(2.302585092994045684 * (c.g.pH[c.r] - rx.pK));
+    const uint32_t k0 = rx.seed, k1 = (uint32_t)(p.replica_offset + c.r);
+    long long acc = 0;
+    for (int base = 0; base < n_trials; base += 32) {
+      const unsigned long long cnt = trial_ctr + (unsigned long long)(base + c.lane);
+      const uint4 o = philox4x32_10((uint32_t)cnt, (uint32_t)(cnt >> 32), 0u, kTagMc + (uint32_t)m, k0, k1);
+      const int nb = min(32, n_trials - base);
+      for (int tt = 0; tt < nb; ++tt) {
+        const uint32_t a0 = __shfl_sync(0xffffffffu, o.x, tt), a1 = __shfl_sync(0xffffffffu, o.y, tt),
+                       a2 = __shfl_sync(0xffffffffu, o.z, tt);
+        const bool fwd = (a0 >> 31) == 0;
+        const int n_src = fwd ? n_p : n_d, n_dst = fwd ? n_d : n_p;
+        uint16_t *src = fwd ? lp : ld, *dst = fwd ? ld : lp;
+        const float u = u24(a2);
+        if (n_src == 0) {
+          if (trace && c.lane == 0) {
+            cgpe_trial_record rec = {-1, -1, (int8_t)(fwd ? 1 : -1), 0, 0, 0, 0.f, 0.f, u};
+            trace[base + tt] = rec;
+          }
+          continue;
+        }
+        const int k = (int)__umulhi(a1, (uint32_t)n_src);
+        const int i = src[k];
+        const int t_old = fwd ? rx.type_prot : rx.type_deprot, t_new = fwd ? rx.type_deprot : rx.type_prot;
+        const float4 pi4 = c.s.pos[i];
+        const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = q_new - pi4.w;
+        float de = 0.f;
+        if (p.use_wca) {
+          const int n = c.s.wn[i];
+          for (int e = c.lane; e < n; e += 32) {
+            const int j = c.s.wl[(size_t)e * p.P + i];
+            const int tj = c.s.type[j];
+            if (tj < p.T) {
+              V3 d;
+              const float r2 = dist2(c, pi4, c.s.pos[j], &d);
+              float en = 0.f;
+              if (t_new < p.T) en += wca_energy(c.s.tab[t_new * (p.T + 1) + tj], r2);
+              if (t_old < p.T) en -= wca_energy(c.s.tab[t_old * (p.T + 1) + tj], r2);
+              de += en;
+            }
+          }
+        }
+        if (p.use_dh && dq != 0.f) {
+          const int ci = c.s.cidx[i];
+          const int n = c.s.dn[ci];
+          float sum = 0.f;
+          for (int e = c.lane; e < n; e += 32) {
+            const int j = c.s.dl[(size_t)e * p.n_chg + ci];
+            const float4 pj4 = c.s.pos[j];
+            V3 d;
+            const float r2 = dist2(c, pi4, pj4, &d);
+            if (pj4.w != 0.f && r2 < c.rc2) {
+              float fr;
+              sum = fmaf(pj4.w, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), sum);
+            }
+          }
+          de = fmaf(p.dh_pref * dq, sum, de);
+        }
+        de = warp_sum(de);
+        // bf = N_react/(N_prod+1) exp(-dE/kT + nu ln10 (pH-pK))   
+        const float arg = (fwd ? arg_fwd : -arg_fwd) - rx.inv_kT * de;
+        const float bf = ((float)n_src / (float)(n_dst + 1)) * exp2f(arg * kLog2e);
+        const bool accept = u < bf;
+        if (trace && c.lane == 0) {
+          cgpe_trial_record rec = {i, -1, (int8_t)(fwd ? 1 : -1), (int8_t)accept, 0, 0, de, bf, u};
+          trace[base + tt] = rec;
+        }
+        if (accept) {
+          if (c.lane == 0) {
+            c.s.type[i] = (unsigned char)t_new;
+            c.s.pos[i].w = q_new;
+            src[k] = src[n_src - 1];
+            dst[n_dst] = (uint16_t)i;
+          }
+          if (fwd) { n_p -= 1; n_d += 1; } else { n_d -= 1; n_p += 1; }
+          acc += 1;
+          __syncwarp();
+        }
+      }
+    }
+    if (c.lane == 0) { c.s.cnt[m * 2] = n_p; c.s.cnt[m * 2 + 1] = n_d; }
+    accepted += acc;  // only meaningful on warp 0; thread 0 writes it back
+  }
+  trial_ctr += (unsigned long long)n_trials;
+  __syncthreads();
+}
+
+// ---- observables (R5, R6) ----------------------------------------------------------------------
+// Rg, Ree of chain 0 from unfolded coordinates; double accumulation (N*12 flop per sample).
+template <int ITEMS>
+__device__ void chain_observables(Ctx &c, Thr<ITEMS> &t, double *rg, double *ree) {
+  const DevParams &p = c.p;
+  const float4 p0 = c.s.pos[0];
+  double sx = 0, sy = 0, sz = 0, s2 = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i < p.N) {
+      const double dx = (double)t.x[k][0] - p0.x, dy = (double)t.x[k][1] - p0.y, dz = (double)t.x[k][2] - p0.z;
+      sx += dx; sy += dy; sz += dz; s2 += dx * dx + dy * dy + dz * dz;
+    }
+  }
+  sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); s2 = warp_sum(s2);
+  __syncthreads();
+  if (c.lane == 0) { c.s.red[c.warp * 4] = sx; c.s.red[c.warp * 4 + 1] = sy; c.s.red[c.warp * 4 + 2] = sz; c.s.red[c.warp * 4 + 3] = s2; }
+  __syncthreads();
+  const int nw = (c.nt + 31) / 32;
+  double tx = 0, ty = 0, tz = 0, t2 = 0;
+  for (int w = 0; w < nw; ++w) { tx += c.s.red[w * 4]; ty += c.s.red[w * 4 + 1]; tz += c.s.red[w * 4 + 2]; t2 += c.s.red[w * 4 + 3]; }
+  const double inv = 1.0 / p.N;
+  // mean |r - r_cm|^2 = mean |d|^2 - |mean d|^2 with d = r - r_0 (shifted to the chain, so no cancellation)
+  const double v = t2 * inv - (tx * tx + ty * ty + tz * tz) * inv * inv;
+  *rg = sqrt(v > 0.0 ? v : 0.0);
+  const float4 pe = c.s.pos[p.N - 1];
+  const double ex = (double)pe.x - p0.x, ey = (double)pe.y - p0.y, ez = (double)pe.z - p0.z;
+  *ree = sqrt(ex * ex + ey * ey + ez * ez);
+}
+
+__device__ void init_ctx(Ctx &c) {
+  const DevParams &p = c.p;
+  c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+  c.kappa = c.g.kappa[c.r];
+  const float rc = c.g.rcut[c.r];
+  c.rc2 = rc * rc;
+  c.neg_kappa_log2e = -c.kappa * kLog2e;
+  c.rlist_d2 = (rc + p.skin) * (rc + p.skin);
+  c.gamma = c.g.gamma[c.r];
+  c.noise_pref = sqrtf(24.0f * c.gamma * c.g.kT[c.r] / p.dt);
+  c.err = 0;
+  c.rebuilds = 0;
+}
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+// ---- kernels -----------------------------------------------------------------------------------
+template <int ITEMS>
+__global__ void __launch_bounds__(1024, 1)
+k_md_run(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, int n_steps) {
+  Ctx c{p, g};
+  c.r = blockIdx.x;
+  chain_smem_layout(p, &c.s, smem_raw);
+  init_ctx(c);
+  Thr<ITEMS> t;
+  bool f_valid = g.f_valid[c.r] != 0, lists_valid = false;
+  unsigned long long counter = (unsigned long long)g.md_counter[c.r];
+  load_state(c, t, f_valid);
+  md_steps(c, t, n_steps, counter, f_valid, lists_valid);
+  store_state(c, t, true);
+  if (c.tid == 0) {
+    g.md_counter[c.r] = (long long)counter;
+    g.md_steps[c.r] += n_steps;
+    g.time[c.r] += (double)n_steps * p.dt_d;
+    g.f_valid[c.r] = f_valid ? 1 : 0;
+  }
+}
+
+// steepest descent (M.py:78-79): x += clamp(gamma f, +-max_disp), forces without thermostat
+template <int ITEMS>
+__global__ void __launch_bounds__(1024, 1)
+k_steepest_descent(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, int n_steps,
+                   float f_max, float sd_gamma, float max_disp) {
+  Ctx c{p, g};
+  c.r = blockIdx.x;
+  chain_smem_layout(p, &c.s, smem_raw);
+  init_ctx(c);
+  Thr<ITEMS> t;
+  load_state(c, t, false);
+  build_lists(c, t);
+  compute_forces(c, t, false, 0ull);
+  for (int step = 0; step < n_steps; ++step) {
+    int moved = 0, big = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int i = c.tid + k * c.nt;
+      if (i < p.P) {
+        float d2 = 0.f, n2 = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float dp = fminf(fmaxf(sd_gamma * t.f[k][a], -max_disp), max_disp);
+          t.x[k][a] += dp;
+          n2 = fmaf(t.f[k][a], t.f[k][a], n2);
+          const float d = t.x[k][a] - t.ref[k][a];
+          d2 = fmaf(d, d, d2);
+        }
+        float4 *sp = &c.s.pos[i];
+        sp->x = t.x[k][0]; sp->y = t.x[k][1]; sp->z = t.x[k][2];
+        moved |= !(d2 <= p.half_skin2);
+        big |= !(n2 < f_max * f_max);
+      }
+    }
+    // __syncthreads_or is a vote (zero / non-zero), so the two questions need two barriers
+    const int any_moved = __syncthreads_or(moved);
+    if (!__syncthreads_or(big)) break;  // every |f| < f_max: converged (never with f_max = 0)
+    if (any_moved) build_lists(c, t);
+    compute_forces(c, t, false, 0ull);
+  }
+  store_state(c, t, false);
+  if (c.tid == 0) g.f_valid[c.r] = 0;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(1024, 1)
+k_mc_run(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, int m, int n_trials,
+         cgpe_trial_record *trace) {
+  Ctx c{p, g};
+  c.r = blockIdx.x;
+  chain_smem_layout(p, &c.s, smem_raw);
+  init_ctx(c);
+  Thr<ITEMS> t;
+  load_state(c, t, true);
+  build_lists(c, t);
+  __syncthreads();
+  unsigned long long trial_ctr = (unsigned long long)g.trials[(size_t)c.r * p.n_rx + m];
+  long long accepted = 0;
+  mc_block(c, m, n_trials, trial_ctr, accepted, trace ? trace + (size_t)c.r * n_trials : nullptr);
+  store_state(c, t, true);
+  if (c.tid == 0) {
+    g.trials[(size_t)c.r * p.n_rx + m] = (long long)trial_ctr;
+    g.accepted[(size_t)c.r * p.n_rx + m] += accepted;
+    if (n_trials > 0) g.f_valid[c.r] = 0;
+  }
+}
+
+// forces exactly as the MD loop computes them, no thermostat (parity / debugging)
+template <int ITEMS>
+__global__ void __launch_bounds__(1024, 1)
+k_md_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, float4 *out) {
+  Ctx c{p, g};
+  c.r = blockIdx.x;
+  chain_smem_layout(p, &c.s, smem_raw);
+  init_ctx(c);
+  Thr<ITEMS> t;
+  load_state(c, t, false);
+  build_lists(c, t);
+  compute_forces(c, t, false, 0ull);
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i < p.P) out[(size_t)c.r * p.P + i] = make_float4(t.f[k][0], t.f[k][1], t.f[k][2], 0.f);
+  }
+  if (c.err) atomicOr(&c.g.err[c.r], c.err);
+}
+
+// The sampling loop of perform_sampling (E.py:88-106), one launch for all samples.
+template <int ITEMS>
+__global__ void __launch_bounds__(1024, 1)
+k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevState g,
+              const __grid_constant__ cgpe_sample_params sp, uint32_t thr1, uint32_t thr2, double *obs,
+              float *qdist) {
+  Ctx c{p, g};
+  c.r = blockIdx.x;
+  chain_smem_layout(p, &c.s, smem_raw);
+  init_ctx(c);
+  Thr<ITEMS> t;
+  bool f_valid = g.f_valid[c.r] != 0, lists_valid = false;
+  unsigned long long counter = (unsigned long long)g.md_counter[c.r];
+  unsigned long long sample_ctr = (unsigned long long)g.samples_done[c.r];
+  unsigned long long trial_ctr[kMaxRx];
+  long long accepted[kMaxRx];
+  for (int m = 0; m < kMaxRx; ++m) {
+    trial_ctr[m] = m < p.n_rx ? (unsigned long long)g.trials[(size_t)c.r * p.n_rx + m] : 0ull;
+    accepted[m] = 0;
+  }
+  load_state(c, t, f_valid);
+  if (!sp.use_md) { build_lists(c, t); lists_valid = true; __syncthreads(); }
+  const double t0 = g.time[c.r];
+  long long steps = 0;
+  const uint32_t k0 = (uint32_t)sp.schedule_seed, k1 = (uint32_t)(p.replica_offset + c.r);
+  for (int s = 0; s < sp.n_samples; ++s) {
+    // every thread draws the same schedule numbers: cheaper than a broadcast + barrier
+    const uint4 o = philox4x32_10((uint32_t)sample_ctr, (uint32_t)(sample_ctr >> 32), 0u, kTagSchedule, k0, k1);
+    sample_ctr += 1;
+    if (sp.use_md) {
+      const int n = ((o.x >> 8) < thr1 ? sp.md_steps_per_burst : 0) +   // E.py:89-90
+                    ((o.y >> 8) < thr2 ? sp.md_steps_per_burst : 0);    // E.py:91-92
+      if (n > 0) {
+        if (!lists_valid) { build_lists(c, t); lists_valid = true; }
+        md_steps(c, t, n, counter, f_valid, lists_valid);
+        steps += n;
+        __syncthreads();  // list rows and positions visible to the MC warp
+      } else if (!lists_valid) {
+        build_lists(c, t); lists_valid = true;
+        __syncthreads();
+      }
+    }
+    for (int b = 0; b < sp.n_mc_blocks; ++b) {   // E.py:94-95
+      const int m = sp.mc_reaction[b];
+      mc_block(c, m, sp.mc_trials[b], trial_ctr[m], accepted[m], nullptr);
+      if (sp.mc_trials[b] > 0) f_valid = false;
+    }
+    double rg, ree;
+    chain_observables(c, t, &rg, &ree);   // E.py:100-101
+    if (c.tid == 0) {
+      double *o6 = obs + ((size_t)c.r * sp.n_samples + s) * CGPE_N_OBS;
+      int n_ion = 0;
+      for (int m = 0; m < p.n_rx; ++m) n_ion += c.s.cnt[m * 2 + 1];
+      o6[0] = p.n_rx > 0 ? c.s.cnt[1] : 0;   // E.py:97
+      o6[1] = p.n_rx > 1 ? c.s.cnt[3] : 0;   // E.py:98
+      o6[2] = n_ion;                          // E.py:99 (implicit ions: N_B = N_N + N_N2)
+      o6[3] = rg; o6[4] = ree;
+      o6[5] = t0 + (double)steps * p.dt_d;   // E.py:102
+    }
+    if (qdist && sp.q_snapshot_every > 0 && s % sp.q_snapshot_every == 0) {   // E.py:103-106
+      const int row = s / sp.q_snapshot_every;
+      if (row < sp.q_snapshot_rows)
+        for (int i = c.tid; i < p.N; i += c.nt)
+          qdist[((size_t)c.r * sp.q_snapshot_rows + row) * p.N + i] = c.s.pos[i].w;
+    }
+  }
+  store_state(c, t, true);
+  if (c.tid == 0) {
+    g.md_counter[c.r] = (long long)counter;
+    g.md_steps[c.r] += steps;
+    g.samples_done[c.r] = (long long)sample_ctr;
+    g.time[c.r] = t0 + (double)steps * p.dt_d;
+    g.f_valid[c.r] = f_valid ? 1 : 0;
+    for (int m = 0; m < p.n_rx; ++m) {
+      g.trials[(size_t)c.r * p.n_rx + m] = (long long)trial_ctr[m];
+      g.accepted[(size_t)c.r * p.n_rx + m] += accepted[m];
+    }
+  }
+}
+
+template <typename K>
+cudaError_t opt_in_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+ChainLaunch chain_launch_shape(const DevParams &p) {
+  ChainLaunch L{};
+  L.items = (p.P + 1023) / 1024;
+  if (L.items > 2) { L.items = 0; return L; }   // beyond the shared-memory engine
+  const int per = (p.P + L.items - 1) / L.items;
+  L.threads = ((per + 31) / 32) * 32;
+  if (L.threads < 32) L.threads = 32;
+  L.smem = chain_smem_bytes(p);
+  return L;
+}
+
+#define CGPE_DISPATCH(items, expr1, expr2) ((items) == 1 ? (expr1) : (expr2))
+
+cudaError_t launch_md_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int n_steps, cudaStream_t st) {
+  auto k = L.items == 1 ? k_md_run<1> : k_md_run<2>;
+  cudaError_t e = opt_in_smem(k, L.smem);
+  if (e != cudaSuccess) return e;
+  k<<<p.R, L.threads, L.smem, st>>>(p, g, n_steps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_steepest_descent(const DevParams &p, const DevState &g, const ChainLaunch &L, int n_steps,
+                                    float f_max, float gamma, float max_disp, cudaStream_t st) {
+  auto k = L.items == 1 ? k_steepest_descent<1> : k_steepest_descent<2>;
+  cudaError_t e = opt_in_smem(k, L.smem);
+  if (e != cudaSuccess) return e;
+  k<<<p.R, L.threads, L.smem, st>>>(p, g, n_steps, f_max, gamma, max_disp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mc_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int m, int n_trials,
+                          cgpe_trial_record *trace, cudaStream_t st) {
+  auto k = L.items == 1 ? k_mc_run<1> : k_mc_run<2>;
+  cudaError_t e = opt_in_smem(k, L.smem);
+  if (e != cudaSuccess) return e;
+  k<<<p.R, L.threads, L.smem, st>>>(p, g, m, n_trials, trace);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_md_forces(const DevParams &p, const DevState &g, const ChainLaunch &L, float4 *out, cudaStream_t st) {
+  auto k = L.items == 1 ? k_md_forces<1> : k_md_forces<2>;
+  cudaError_t e = opt_in_smem(k, L.smem);
+  if (e != cudaSuccess) return e;
+  k<<<p.R, L.threads, L.smem, st>>>(p, g, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample_loop(const DevParams &p, const DevState &g, const ChainLaunch &L,
+                               const cgpe_sample_params &sp, uint32_t thr1, uint32_t thr2, double *obs,
+                               float *qdist, cudaStream_t st) {
+  auto k = L.items == 1 ? k_sample_loop<1> : k_sample_loop<2>;
+  cudaError_t e = opt_in_smem(k, L.smem);
+  if (e != cudaSuccess) return e;
+  k<<<p.R, L.threads, L.smem, st>>>(p, g, sp, thr1, thr2, obs, qdist);
+  return cudaGetLastError();
+}
+
+}  // namespace cgpe

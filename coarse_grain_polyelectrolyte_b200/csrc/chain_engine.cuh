@@ -1,0 +1,51 @@
+// chain_engine.cuh — interface of the shared-memory replica engine (chain_engine.cu).
+#pragma once
+#include "cgpe_device.cuh"
+
+namespace cgpe {
+
+// pointers into the dynamic shared memory of one CTA (= one replica)
+struct ChainSmem {
+  float4 *pos;        // [P] x,y,z,q
+  float4 *tab;        // [(T+1)^2] WCA table
+  double *red;        // [32][4] block-reduction scratch
+  float *slot;        // [3 slots][3][NC] bonded hand-over slots
+  float *fd;          // [3][n_chg] Debye-Hueckel force per chargeable particle
+  int *cnt;           // [n_rx][2] n_prot, n_deprot
+  int *flag;          // [4]
+  uint16_t *wl;       // [cap_w][P] WCA Verlet list (column per particle)
+  uint16_t *dl;       // [cap_d][n_chg] Debye-Hueckel Verlet list (particle ids)
+  uint16_t *chg;      // [n_chg] chargeable particle ids
+  uint16_t *cidx;     // [P] particle id -> chargeable index (0xFFFF = none)
+  uint16_t *lp, *ld;  // [n_rx][n_chg] protonated / deprotonated bookkeeping lists
+  unsigned char *wn, *dn;   // list lengths
+  unsigned char *type;      // [P]
+};
+
+struct ChainLaunch {
+  int items;      // particles per thread (0 = system too large for this engine)
+  int threads;
+  size_t smem;
+};
+
+size_t chain_smem_bytes(const DevParams &p);
+ChainLaunch chain_launch_shape(const DevParams &p);
+
+cudaError_t launch_md_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int n_steps, cudaStream_t st);
+cudaError_t launch_steepest_descent(const DevParams &p, const DevState &g, const ChainLaunch &L, int n_steps,
+                                    float f_max, float gamma, float max_disp, cudaStream_t st);
+cudaError_t launch_mc_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int m, int n_trials,
+                          cgpe_trial_record *trace, cudaStream_t st);
+cudaError_t launch_md_forces(const DevParams &p, const DevState &g, const ChainLaunch &L, float4 *out, cudaStream_t st);
+cudaError_t launch_sample_loop(const DevParams &p, const DevState &g, const ChainLaunch &L,
+                               const cgpe_sample_params &sp, uint32_t thr1, uint32_t thr2, double *obs,
+                               float *qdist, cudaStream_t st);
+
+// all-pairs analysis kernels (diag_kernels.cu)
+cudaError_t launch_energy(const DevParams &p, const DevState &g, double *out /*[R][5]*/, cudaStream_t st);
+cudaError_t launch_forces(const DevParams &p, const DevState &g, float4 *out /*[R][P]*/, cudaStream_t st);
+cudaError_t launch_min_dist(const DevParams &p, const DevState &g, double *out /*[R]*/, cudaStream_t st);
+cudaError_t launch_observables(const DevParams &p, const DevState &g, double *rg, double *ree, int *counts,
+                               cudaStream_t st);
+
+}  // namespace cgpe

@@ -31,6 +31,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define CGPE_API __attribute__((visibility("default")))
+#else
+#define CGPE_API
+#endif
+
 #define CGPE_ABI_VERSION 3
 #define CGPE_MAX_TYPES 16     /* interacting particle types (the reference uses 8, M.py:58-76) */
 #define CGPE_MAX_REACTIONS 4  /* reaction objects (the reference uses 2, M.py:211-233)         */
@@ -136,80 +142,80 @@ typedef struct cgpe_trial_record {
 typedef struct cgpe_handle cgpe_handle;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
-int cgpe_abi_version(void);
+CGPE_API int cgpe_abi_version(void);
 /* espressomd.System(box_l=) + bonded_inter.add + non_bonded_inter[..].wca.set_params +
  * electrostatics.DH + ConstantpHEnsemble  (P.py:372-375, M.py:32-109,200-261) */
-int cgpe_create(const cgpe_config *cfg, cgpe_handle **out);
-void cgpe_destroy(cgpe_handle *h);
+CGPE_API int cgpe_create(const cgpe_config *cfg, cgpe_handle **out);
+CGPE_API void cgpe_destroy(cgpe_handle *h);
 /* message of the last failing call on h (or of the last failing cgpe_create if h == NULL) */
-const char *cgpe_last_error(const cgpe_handle *h);
+CGPE_API const char *cgpe_last_error(const cgpe_handle *h);
 /* SM count, compute capability and name of the device h lives on */
-int cgpe_device_info(const cgpe_handle *h, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,
+CGPE_API int cgpe_device_info(const cgpe_handle *h, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,
                      char *name, int32_t name_len);
 /* run on a caller-provided cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream);
  * NULL restores the handle's own stream */
-int cgpe_set_stream(cgpe_handle *h, void *cuda_stream);
-int cgpe_synchronize(cgpe_handle *h);
+CGPE_API int cgpe_set_stream(cgpe_handle *h, void *cuda_stream);
+CGPE_API int cgpe_synchronize(cgpe_handle *h);
 
 /* ---- state --------------------------------------------------------------------------------- */
 /* system.part.add(id,pos,type,q) (M.py:130-155,175-198).  xyzq [R][P][4] = x,y,z,q (positions
  * unfolded), vel [R][P][4] = vx,vy,vz,unused (NULL = zero), type [R][P].  Resets the reaction
  * bookkeeping lists to id order and invalidates cached forces. */
-int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const uint8_t *type);
+CGPE_API int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const uint8_t *type);
 /* system.part.by_ids(ids).q (E.py:105) and positions/velocities read-back; any pointer may be NULL */
-int cgpe_get_state(cgpe_handle *h, float *xyzq, float *vel, uint8_t *type);
+CGPE_API int cgpe_get_state(cgpe_handle *h, float *xyzq, float *vel, uint8_t *type);
 /* reactionX.constant_pH = pH (E.py:68-69), DH(kappa, r_cut) (M.py:105-106), thermostat kT/gamma
  * (E.py:35,57,61-63), per replica [R]; NULL leaves a parameter unchanged */
-int cgpe_set_replica_params(cgpe_handle *h, const double *pH, const double *kappa,
+CGPE_API int cgpe_set_replica_params(cgpe_handle *h, const double *pH, const double *kappa,
                             const double *r_cut, const double *kT, const double *gamma);
 /* non_bonded_inter[t1,t2].wca.set_params(epsilon=, sigma=) for the whole table (M.py:74-76) */
-int cgpe_set_wca(cgpe_handle *h, const double *eps, const double *sig);
+CGPE_API int cgpe_set_wca(cgpe_handle *h, const double *eps, const double *sig);
 /* thermostat.set_langevin(seed=) (E.py:35,62): negative seed keeps the current seed/counter */
-int cgpe_set_thermostat_seed(cgpe_handle *h, int32_t seed);
+CGPE_API int cgpe_set_thermostat_seed(cgpe_handle *h, int32_t seed);
 /* system.force_cap (E.py:32,48,51); 0 disables */
-int cgpe_set_force_cap(cgpe_handle *h, double cap);
+CGPE_API int cgpe_set_force_cap(cgpe_handle *h, double cap);
 /* system.time (E.py:30,77,102), per replica [R] */
-int cgpe_set_time(cgpe_handle *h, double t);
-int cgpe_get_time(cgpe_handle *h, double *t);
+CGPE_API int cgpe_set_time(cgpe_handle *h, double t);
+CGPE_API int cgpe_get_time(cgpe_handle *h, double *t);
 
 /* ---- hot path ------------------------------------------------------------------------------ */
 /* system.integrator.run(n) after set_vv() with the Langevin thermostat
  * (E.py:41,52,58,64,73,90,92): velocity Verlet, friction -gamma v, uniform noise,
  * harmonic/FENE + angle + dihedral + WCA + Debye-Hueckel forces */
-int cgpe_md_run(cgpe_handle *h, int32_t n_steps);
+CGPE_API int cgpe_md_run(cgpe_handle *h, int32_t n_steps);
 /* integrator.set_steepest_descent(f_max, gamma, max_displacement); integrator.run(n) (M.py:78-79) */
-int cgpe_steepest_descent(cgpe_handle *h, int32_t n_steps, double f_max, double gamma,
+CGPE_API int cgpe_steepest_descent(cgpe_handle *h, int32_t n_steps, double f_max, double gamma,
                           double max_displacement);
 /* reactionX.reaction(reaction_steps=n) (E.py:70-71,94-95).  trace may be NULL, else
  * [R][n_trials] records */
-int cgpe_mc_run(cgpe_handle *h, int32_t reaction_id, int32_t n_trials, cgpe_trial_record *trace);
+CGPE_API int cgpe_mc_run(cgpe_handle *h, int32_t reaction_id, int32_t n_trials, cgpe_trial_record *trace);
 /* the whole loop body of perform_sampling for n_samples samples (E.py:88-106), fused on device.
  * obs [R][n_samples][CGPE_N_OBS] = n_deprot(reaction 0), n_deprot(reaction 1), n_ion, Rg, Ree,
  * time (E.py:97-102); qdist [R][q_snapshot_rows][n_beads] charge snapshots (E.py:103-106) or NULL */
-int cgpe_sample_loop(cgpe_handle *h, const cgpe_sample_params *sp, double *obs, float *qdist);
+CGPE_API int cgpe_sample_loop(cgpe_handle *h, const cgpe_sample_params *sp, double *obs, float *qdist);
 /* same, leaving the results in device memory (read them later with cgpe_fetch_samples) */
-int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp);
-int cgpe_fetch_samples(cgpe_handle *h, double *obs, float *qdist);
+CGPE_API int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp);
+CGPE_API int cgpe_fetch_samples(cgpe_handle *h, double *obs, float *qdist);
 
 /* ---- analysis ------------------------------------------------------------------------------ */
 /* system.analysis.energy() (E.py:42): out [R][5] = total, kinetic, coulomb, bonded, non_bonded */
-int cgpe_energy(cgpe_handle *h, double *out);
+CGPE_API int cgpe_energy(cgpe_handle *h, double *out);
 /* interaction forces without thermostat, all-pairs evaluation: out [R][P][4] (w unused) */
-int cgpe_forces(cgpe_handle *h, float *out);
+CGPE_API int cgpe_forces(cgpe_handle *h, float *out);
 /* the same forces as the MD kernel computes them (Verlet lists, owner-computes bonded terms) */
-int cgpe_md_forces(cgpe_handle *h, float *out);
+CGPE_API int cgpe_md_forces(cgpe_handle *h, float *out);
 /* analysis.calc_rg / calc_re of chain 0 (E.py:100-101) and number_of_particles(type)
  * (E.py:97-99): rg [R], ree [R], counts [R][3] = n_deprot(reaction 0), n_deprot(reaction 1), n_ion */
-int cgpe_observables(cgpe_handle *h, double *rg, double *ree, int32_t *counts);
+CGPE_API int cgpe_observables(cgpe_handle *h, double *rg, double *ree, int32_t *counts);
 /* analysis.min_dist() (E.py:34,45): out [R] */
-int cgpe_min_dist(cgpe_handle *h, double *out);
+CGPE_API int cgpe_min_dist(cgpe_handle *h, double *out);
 /* bookkeeping totals per replica: md_steps [R], trials [R][n_reactions], accepted [R][n_reactions],
  * list_rebuilds [R]; any pointer may be NULL */
-int cgpe_get_counters(cgpe_handle *h, int64_t *md_steps, int64_t *trials, int64_t *accepted,
+CGPE_API int cgpe_get_counters(cgpe_handle *h, int64_t *md_steps, int64_t *trials, int64_t *accepted,
                       int64_t *list_rebuilds);
 /* device time of the last hot-path call in milliseconds (CUDA events on the handle's stream) and
  * the number of kernels it launched */
-int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches);
+CGPE_API int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches);
 
 #ifdef __cplusplus
 }

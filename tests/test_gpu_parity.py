@@ -1,0 +1,257 @@
+"""Parity of the CUDA hot path (through the C-ABI of libcgpe.so) with the FP64 CPU oracle on the
+same seeded inputs.
+
+Tolerances (BASELINE.json north_star): energies and forces within 1e-5 relative; integer
+charge-state bookkeeping bit-exact for identical proposal sequences.  Relative force error is
+measured against the largest force in the configuration (a per-component ratio is meaningless
+where a component passes through zero).
+"""
+import numpy as np
+import pytest
+
+from coarse_grain_polyelectrolyte_b200 import _abi
+from helpers import load, make_workload, random_state
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def Engine():
+    from coarse_grain_polyelectrolyte_b200.engine import Engine
+    return Engine
+
+
+def _pair(Engine, oracle_mod, w, state):
+    g = load(Engine(w.cfg), w, state)
+    o = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    return g, o
+
+
+@pytest.mark.parametrize("n_mon,flags", [
+    (50, None),
+    (100, None),
+    (100, {"USE_FENE": True}),
+    (100, {"USE_BENDING": False, "USE_DIHEDRAL_POT": False}),
+    (100, {"USE_ELECTROSTATICS": False}),
+    (1000, None),
+    (1500, None),
+])
+def test_energy_and_forces_match_oracle(Engine, oracle_mod, n_mon, flags):
+    w = make_workload(n_mon, pH=[6.0, 8.0, 10.0], flags=flags)
+    state = random_state(w, seed=n_mon, jitter=0.03)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    eg, eo = g.energy(), o.energy()
+    scale = np.maximum(np.abs(eo), 1e-3 * np.abs(eo).max(axis=1, keepdims=True))
+    assert np.max(np.abs(eg - eo) / scale) < REL_TOL, (eg, eo)
+    fo = o.forces_f64()
+    fmax = np.abs(fo).max()
+    for name, fg in (("all-pairs", g.forces()), ("md-lists", g.md_forces())):
+        err = np.abs(fg - fo).max() / fmax
+        assert err < REL_TOL, f"{name}: max |dF|/max|F| = {err:.3g}"
+    # analysis helpers
+    np.testing.assert_allclose(g.min_dist(), o.min_dist(), rtol=1e-6)
+    rg_g, ree_g, cnt_g = g.observables()
+    rg_o, ree_o, cnt_o = o.observables()
+    np.testing.assert_allclose(rg_g, rg_o, rtol=1e-6)
+    np.testing.assert_allclose(ree_g, ree_o, rtol=1e-6)
+    np.testing.assert_array_equal(cnt_g, cnt_o)
+
+
+@pytest.mark.parametrize("n_mon,n_trials", [(50, 4000), (100, 6000), (1000, 20000)])
+def test_mc_bookkeeping_bit_exact(Engine, oracle_mod, n_mon, n_trials):
+    """Same Philox proposal stream on both sides -> identical sites, directions, decisions,
+    types and charges; Delta-E within 1e-5 of the FP64 value.  A decision may differ only on a
+    near-tie |u - bf| <= 1e-4 bf, which the oracle then follows and the test counts."""
+    w = make_workload(n_mon, pH=[7.0, 8.18, 9.0, 10.5])
+    state = random_state(w, seed=7 + n_mon, jitter=0.03)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    for rx in (0, 1, 0):
+        tg = g.mc_run(rx, n_trials, trace=True)
+        to, ties = o.mc_run_follow(rx, tg, tie_tol=1e-4)
+        assert ties <= max(2, n_trials * w.R // 2000), f"{ties} near-ties"
+        np.testing.assert_array_equal(tg["particle"], to["particle"])
+        np.testing.assert_array_equal(tg["direction"], to["direction"])
+        np.testing.assert_array_equal(tg["accepted"], to["accepted"])
+        np.testing.assert_array_equal(tg["u"], to["u"])
+        tried = to["particle"] >= 0
+        # Delta-E enters the decision as exp(-dE/kT): what matters is its absolute error in kT
+        # (a WCA type swap is a difference of two O(1) terms, so |dE| itself can be tiny)
+        err = np.abs(tg["delta_e"][tried] - to["delta_e"][tried]) / np.maximum(np.abs(to["delta_e"][tried]), 1.0)
+        k = int(np.argmax(err))
+        assert err[k] < REL_TOL, (err[k], tg[tried][k], to[tried][k])
+        assert tg["accepted"].sum() > 0
+    xg, _, tyg = g.get_state()
+    xo, _, tyo = o.get_state()
+    np.testing.assert_array_equal(tyg, tyo)
+    np.testing.assert_array_equal(xg[..., 3], xo[..., 3])
+    cg, co = g.counters(), o.counters()
+    np.testing.assert_array_equal(cg["trials"], co["trials"])
+    np.testing.assert_array_equal(cg["accepted"], co["accepted"])
+    np.testing.assert_array_equal(g.observables()[2], o.observables()[2])
+
+
+@pytest.mark.parametrize("n_mon", [50, 100, 1000])
+def test_md_steps_match_oracle(Engine, oracle_mod, n_mon):
+    """One velocity-Verlet + Langevin step is a deterministic map given the Philox noise; FP32
+    vs FP64 differ by rounding only.  The gap then grows with the Lyapunov exponent."""
+    w = make_workload(n_mon, pH=[8.0, 9.0])
+    state = random_state(w, seed=3 + n_mon, jitter=0.02)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    x0 = state[0][..., :3].astype(np.float64)
+    ulp = float(np.spacing(np.float32(np.abs(x0).max())))   # FP32 grid of the stored coordinates
+    for n_steps, tol in ((1, 0.75 * ulp), (9, 8 * ulp), (40, 150 * ulp)):
+        g.md_run(n_steps)
+        o.md_run(n_steps)
+        xg, vg, _ = g.get_state()
+        xo, vo, _ = o.state_f64()[0], o.state_f64()[1], None
+        dx = np.abs(xg[..., :3] - xo).max()
+        dv = np.abs(vg[..., :3] - vo).max()
+        assert dx < tol and dv < tol * 1e3, f"after +{n_steps} steps: dx={dx:.3g} dv={dv:.3g}"
+    assert np.abs(xo - x0).max() > 1e-3     # the system actually moved
+    np.testing.assert_array_equal(g.counters()["md_steps"], o.counters()["md_steps"])
+    np.testing.assert_allclose(g.get_time(), o.get_time(), rtol=1e-12)
+
+
+def test_md_then_mc_then_md_reuses_state(Engine, oracle_mod):
+    """Interleaving as in equilibrate_pH / perform_sampling: forces are recomputed after a
+    reaction block, kept across back-to-back integrator calls."""
+    w = make_workload(100, pH=[8.5])
+    state = random_state(w, seed=99, jitter=0.02)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    for e in (g, o):
+        e.md_run(5)
+        e.md_run(5)
+        e.mc_run(0, 200)
+        e.mc_run(1, 20)
+        e.md_run(5)
+    xg, vg, tg = g.get_state()
+    xo, vo, _ = o.state_f64()
+    _, _, to = o.get_state()
+    np.testing.assert_array_equal(tg, to)
+    assert np.abs(xg[..., :3] - xo).max() < 5e-5
+    assert np.abs(vg[..., :3] - vo).max() < 5e-2
+
+
+def test_steepest_descent_matches_oracle(Engine, oracle_mod):
+    """integrator.set_steepest_descent (M.py:78-79).  With the reference's gamma=0.1 and
+    k_bond ~ 2.4e3 the clamped update is an expanding map (gamma*k >> 1), so FP32 and FP64 can
+    only be compared over a single step there; the contracting regime is compared over 40."""
+    w = make_workload(100, pH=[8.0, 9.0])
+    state = random_state(w, seed=5, jitter=0.1, vel_sigma=0.0)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    e0 = o.energy()[:, 0].copy()
+    for e in (g, o):
+        e.steepest_descent(40, f_max=0.0, gamma=1e-4, max_displacement=0.01)
+    xg = g.get_state()[0][..., :3]
+    xo = o.state_f64()[0]
+    # every clamped step adds the same rounding error of x += 0.01 on the FP32 grid (~2e-6 at x~36)
+    assert np.abs(xg - xo).max() < 1.5e-4
+    assert np.all(o.energy()[:, 0] < e0)
+    g1, o1 = _pair(Engine, oracle_mod, w, state)
+    for e in (g1, o1):
+        e.steepest_descent(1, f_max=0.0, gamma=0.1, max_displacement=0.1)
+    assert np.abs(g1.get_state()[0][..., :3] - o1.state_f64()[0]).max() < 1e-5
+    # f_max above every force: converged after the first displacement, no further motion
+    g2, o2 = _pair(Engine, oracle_mod, w, state)
+    for e in (g2, o2):
+        e.steepest_descent(25, f_max=1e9, gamma=1e-4, max_displacement=0.01)
+    assert np.abs(g2.get_state()[0][..., :3] - o2.state_f64()[0]).max() < 1e-5
+
+
+def test_force_cap_and_zero_temperature(Engine, oracle_mod):
+    """Warm-up mode (E.py:24-52): capped forces, kT = 0 thermostat."""
+    w = make_workload(50, pH=[8.0])
+    state = random_state(w, seed=11, jitter=0.2, vel_sigma=0.0)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    for e in (g, o):
+        e.set_force_cap(5.0)
+        e.set_replica_params(kT=0.0, gamma=1.0)
+        e.set_thermostat_seed(4)
+        e.md_run(12)
+    xg, vg, _ = g.get_state()
+    xo, vo, _ = o.state_f64()
+    assert np.abs(xg[..., :3] - xo).max() < 5e-5
+    assert np.abs(vg[..., :3] - vo).max() < 5e-3
+
+
+def test_sample_loop_matches_oracle(Engine, oracle_mod):
+    """The fused perform_sampling loop against the oracle's: integer columns identical, Rg/Ree
+    and time to rounding.  Short bursts keep the trajectories in the linear-error regime."""
+    w = make_workload(60, pH=[7.5, 8.5, 9.5])
+    state = random_state(w, seed=21, jitter=0.02)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    sp = g.sample_params(40, md_steps_per_burst=6, use_md=True, mc_blocks=((0, 31), (1, 11)),
+                         q_snapshot_every=15, q_snapshot_rows=3, schedule_seed=10, p_burst1=0.7, p_burst2=0.3)
+    og, qg = g.sample_loop(sp)
+    oo, qo = o.sample_loop(sp)
+    np.testing.assert_array_equal(og[..., :3], oo[..., :3])
+    np.testing.assert_allclose(og[..., 3:5], oo[..., 3:5], rtol=2e-4)
+    np.testing.assert_allclose(og[..., 5], oo[..., 5], rtol=1e-9)
+    np.testing.assert_array_equal(qg, qo)
+    assert og[..., 5].max() > 0 and len(np.unique(og[..., 0])) > 1
+    cg, co = g.counters(), o.counters()
+    for k in ("md_steps", "trials", "accepted"):
+        np.testing.assert_array_equal(cg[k], co[k])
+
+
+def test_results_do_not_depend_on_sharding(Engine):
+    """RNG streams are keyed on the global replica index: 8 replicas in one handle == 2 handles
+    of 4 with replica_offset 0 and 4, bit for bit."""
+    pH = np.linspace(6.0, 11.0, 8)
+    w_all = make_workload(100, pH=pH)
+    state = random_state(w_all, seed=31)
+    sp_kw = dict(md_steps_per_burst=25, use_md=True, mc_blocks=((0, 51), (1, 11)), schedule_seed=10,
+                 p_burst1=0.7, p_burst2=0.2)
+    g = load(Engine(w_all.cfg), w_all, state)
+    ref, _ = g.sample_loop(g.sample_params(30, **sp_kw))
+    parts = []
+    for lo in (0, 4):
+        w = make_workload(100, pH=pH[lo:lo + 4], replica_offset=lo)
+        sub = tuple(a[lo:lo + 4] for a in state)
+        e = load(Engine(w.cfg), w, sub)
+        parts.append(e.sample_loop(e.sample_params(30, **sp_kw))[0])
+    np.testing.assert_array_equal(ref, np.concatenate(parts, axis=0))
+
+
+def test_ideal_titration_curve(Engine):
+    """Interactions off: alpha(pH) must follow 1/(1+10^(pK-pH)) (utils.py:15-16 of the
+    reference) within statistical error."""
+    pH = np.linspace(6.0, 12.0, 16)
+    w = make_workload(100, pH=pH, flags={"USE_WCA": False, "USE_ELECTROSTATICS": False})
+    e = load(Engine(w.cfg), w, (np.broadcast_to(w.xyzq, (16, 100, 4)).copy(), None, np.broadcast_to(w.type, (16, 100)).copy()))
+    n1, n2 = w.n_sites
+    sp = e.sample_params(3000, use_md=False, mc_blocks=((0, 5 * n1 + 1), (1, 5 * n2 + 1)))
+    obs, _ = e.sample_loop(sp)
+    obs = obs[:, 200:]
+    for col, n, pK in ((0, n1, 8.18), (1, n2, 10.02)):
+        alpha = obs[..., col].mean(axis=1) / n
+        ideal = 1.0 / (1.0 + 10.0 ** (pK - pH))
+        sem = np.sqrt(ideal * (1 - ideal) / (n * obs.shape[1] / 4.0)) + 2e-3
+        assert np.all(np.abs(alpha - ideal) < 5 * sem), (alpha, ideal)
+    np.testing.assert_array_equal(obs[..., 2], obs[..., 0] + obs[..., 1])
+
+
+def test_capacity_overflow_is_reported(Engine):
+    w = make_workload(100, pH=[8.0], cap_wca=1)
+    e = load(Engine(w.cfg), w, random_state(w, seed=1))
+    with pytest.raises(_abi.CgpeError) as ei:
+        e.md_forces()
+    assert ei.value.status == _abi.ERR_CAPACITY
+
+
+def test_invalid_calls_fail_loudly(Engine):
+    w = make_workload(50, pH=[8.0])
+    e = Engine(w.cfg)
+    with pytest.raises(_abi.CgpeError) as ei:
+        e.md_run(1)
+    assert ei.value.status == _abi.ERR_STATE
+    load(e, w, random_state(w, seed=2))
+    with pytest.raises(_abi.CgpeError):
+        e.mc_run(5, 10)
+    with pytest.raises(_abi.CgpeError):
+        e.set_replica_params(r_cut=1e6)
+    w.cfg.abi_version = 1
+    with pytest.raises(_abi.CgpeError):
+        Engine(w.cfg)
