@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the hot path.
+
+A "step" is one pass of the reference's sampling-loop body (EnsembleDynamics.perform_sampling,
+E.py:88-106) over all replicas of this rank: the Bernoulli-scheduled bursts of 500 Langevin MD
+steps, the two blocks of constant-pH trial moves (5*n_nh+1, 5*n_nh2+1) and the observables.
+Workload at N GPUs: rank r holds 128 pH replicas of an N=1000 chain at one ionic strength
+(BASELINE.json configs[2] sharded, one ionic strength per GPU: weak scaling).
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement on the host cores
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from coarse_grain_polyelectrolyte_b200 import workloads  # noqa: E402
+
+METRIC = "md_bead_steps_per_s"
+UNIT = "bead-steps/s"
+SM_COUNT_B200 = 148
+FP32_LANES_PER_SM = 128
+MUFU_PER_SM = 16
+# algorithmic work per unit
+FLOP_PAIR_TEST, FLOP_PAIR_IN, FLOP_BEAD, FLOP_MC_TERM = 8.0, 24.0, 250.0, 14.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--n-mon", type=int, default=1000)
+    ap.add_argument("--replicas-per-gpu", type=int, default=128)
+    ap.add_argument("--equil-steps", type=int, default=4000, help="untimed MD steps before warm-up")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--skin", type=float, default=0.0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_flops(n_mon, md_steps, trials, stats):
+    """SURVEY §8d convention on the work the kernel's algorithm performs (unique listed pairs)."""
+    w_all, w_in, d_all, d_in = (float(x) / 2.0 for x in stats)   # directed -> unique
+    per_step = (w_all + d_all) * FLOP_PAIR_TEST + (w_in + d_in) * FLOP_PAIR_IN + n_mon * FLOP_BEAD
+    # a trial visits the site's two list rows (directed entries / particles that own a row)
+    return md_steps * per_step, per_step
+
+
+def run_cpu_sample(world_rank_workload, n_samples, threads, list_mode=True):
+    """Time the oracle on `threads` replicas (one per core) for n_samples samples."""
+    from oracle import oracle
+    oracle.build()
+    w = world_rank_workload
+    R = min(threads, w.R)
+    sub = workloads.Workload(w.params, pH=w.pH[:R], c_salt=None, replica_offset=int(w.cfg.replica_offset))
+    sub.kappa, sub.r_cut = w.kappa[:R], w.r_cut[:R]
+    oracle.set_threads(threads)
+    o = oracle.OracleEngine(sub.cfg)
+    sub.init_engine(o)
+    if list_mode:
+        o.set_list_mode(True, 0.8)
+    return o, sub, R
+
+
+def cpu_measure(w, threads, budget_s, warm_samples=2, list_mode=True):
+    o, sub, R = run_cpu_sample(w, 0, threads, list_mode)
+    o.md_run(200)                                    # leave the random-walk start
+    o.sample_loop(sub.sample_params(o, warm_samples))
+    # calibrate on a few samples, then spend the budget
+    t0 = time.perf_counter(); o.sample_loop(sub.sample_params(o, 3)); dt3 = time.perf_counter() - t0
+    n = int(max(3, min(2000, budget_s / max(dt3 / 3.0, 1e-6))))
+    c0 = o.counters()
+    t0 = time.perf_counter(); o.sample_loop(sub.sample_params(o, n)); dt = time.perf_counter() - t0
+    c1 = o.counters()
+    steps = int((c1["md_steps"] - c0["md_steps"]).sum())
+    trials = int((c1["trials"] - c0["trials"]).sum())
+    n_acid = sum(sub.n_sites)
+    return {
+        "value": steps * sub.cfg.n_beads / dt, "unit": UNIT, "cores": threads,
+        "kind": "port",
+        "sample": f"{R} replicas (one per host thread) x {n} samples of the same protocol, N={sub.cfg.n_beads}, "
+                  f"FP64 C oracle with Verlet lists (skin 0.8); {dt:.1f} s",
+        "mc_sweeps_per_s": trials / n_acid / dt, "samples_per_s": R * n / dt, "seconds": dt, "n_samples": n,
+    }, n
+
+
+def main_reference(args, rank, world):
+    """CPU arm: the restatement of the reference's path on the host cores (ESPResSo itself is not
+    installable here)."""
+    if rank != 0:
+        return
+    w = workloads.config_c3_shard(0, max(world, 1), n_ph=args.replicas_per_gpu, n_mon=args.n_mon)
+    threads = os.cpu_count() or 1
+    o, sub, R = run_cpu_sample(w, 0, threads)
+    o.md_run(200)
+    for _ in range(args.warmup):
+        o.sample_loop(sub.sample_params(o, 1))
+    # each step = one sample over the R replicas the host threads hold (bounded sample of the workload)
+    c0 = o.counters()
+    t0 = time.perf_counter()
+    o.sample_loop(sub.sample_params(o, args.steps))
+    dt = time.perf_counter() - t0
+    c1 = o.counters()
+    steps = int((c1["md_steps"] - c0["md_steps"]).sum())
+    trials = int((c1["trials"] - c0["trials"]).sum())
+    value = steps * sub.cfg.n_beads / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C3 shard on CPU: {R} of {w.R} pH replicas x N={args.n_mon} chain, "
+                               "perform_sampling loop body (MD bursts + constant-pH MC + observables)",
+                   "replicas": R, "n_mon": args.n_mon},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{R} replicas x {args.steps} samples, FP64 C oracle with Verlet lists"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mc_sweeps_per_s": trials / sum(sub.n_sites) / dt,
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return main_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from coarse_grain_polyelectrolyte_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = workloads.config_c3_shard(rank, world, n_ph=args.replicas_per_gpu, n_mon=args.n_mon, device=local_rank)
+    if args.skin > 0:
+        w.cfg.skin = args.skin
+    eng = Engine(w.cfg)
+    # a real (non-legacy) stream: torch's default stream has handle 0, which the C-ABI reads as
+    # "use the handle's own stream", and torch events would then bracket nothing
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    w.init_engine(eng)
+    info = eng.device_info()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # untimed: leave the synthetic random-walk start, then W warm-up steps of the protocol
+    eng.md_run(args.equil_steps)
+    eng.sample_loop_async(w.sample_params(eng, max(args.warmup, 3)))
+    eng.synchronize()
+    stats = eng.list_stats().mean(axis=0)
+
+    # L2 flush: the replicas live in shared memory; flush anyway so nothing is served from a warm L2
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    flush.fill_(1)
+    sampler = ClockSampler(local_rank)
+    c0 = eng.counters()
+    sp = w.sample_params(eng, args.steps)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    eng.sample_loop_async(sp)          # ONE launch of k_sample_loop: K steps for all replicas
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    kernel_ms, launches = eng.last_call_ms()
+    c1 = eng.counters()
+    obs, _ = eng.fetch_samples()
+    md_steps = int((c1["md_steps"] - c0["md_steps"]).sum())
+    trials = int((c1["trials"] - c0["trials"]).sum())
+    rebuilds = int((c1["list_rebuilds"] - c0["list_rebuilds"]).sum())
+    n_acid = sum(w.n_sites)
+
+    # end to end through the public call with HOST buffers: upload the state, run K steps,
+    # read the observables and the final state back; copies inside the timed region
+    xyzq, vel, typ = eng.get_state()
+    pin = [torch.from_numpy(a).pin_memory().numpy() for a in (xyzq, vel, typ)]
+    barrier()
+    t0 = time.perf_counter()
+    eng.set_state(*pin)
+    eng.set_replica_params(pH=w.pH, kappa=w.kappa, r_cut=w.r_cut)
+    obs2, _ = eng.sample_loop(sp)
+    out_state = eng.get_state()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    ce = eng.counters()
+    md_steps_e2e = int((ce["md_steps"] - c1["md_steps"]).sum())
+    h2d = sum(a.nbytes for a in pin) + 3 * 8 * w.R
+    d2h = obs2.nbytes + sum(a.nbytes for a in out_state)
+
+    # max over ranks of the device time; sums over ranks of the work
+    t_ms, t_e2e = ms, e2e_s
+    tot = torch.tensor([md_steps, trials, md_steps_e2e, rebuilds], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        t_ms, t_e2e = float(tt[0]), float(tt[1])
+    md_all, tr_all, md_e2e_all, reb_all = (float(x) for x in tot.tolist())
+    n_mon = args.n_mon
+    value = md_all * n_mon / (t_ms * 1e-3)
+    e2e_value = md_e2e_all * n_mon / t_e2e
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        sm_count = info["sm_count"] or SM_COUNT_B200
+        fp32_peak = sm_count * FP32_LANES_PER_SM * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12      # TFLOP/s
+        md_flops, per_step = algorithmic_flops(n_mon, md_steps, trials, stats)
+        terms_per_trial = (stats[0] / n_mon + stats[2] / max(n_acid, 1))                      # rows visited by a trial
+        mc_flops = trials * terms_per_trial * FLOP_MC_TERM
+        achieved = (md_flops + mc_flops) / (ms * 1e-3) / 1e12
+        # the same step count charged as the SURVEY's all-pairs algorithm would be (context only)
+        allpairs_equiv = md_steps * (n_mon * (n_mon - 1) / 2 * FLOP_PAIR_TEST + (stats[1] + stats[3]) / 2 * FLOP_PAIR_IN
+                                     + n_mon * FLOP_BEAD) / (ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"BASELINE configs[2] shard: {w.R} pH replicas per GPU x N={n_mon} chain, one ionic strength "
+                            "per GPU; step = perform_sampling loop body (Bernoulli bursts of 500 Langevin MD steps + "
+                            f"{w.sample_kwargs['mc_blocks'][0][1]}+{w.sample_kwargs['mc_blocks'][1][1]} constant-pH trials + Rg/Ree/counts)",
+                "replicas_per_gpu": w.R, "n_mon": n_mon, "n_titratable": n_acid, "ion_model": "implicit (Debye-Hueckel)",
+                "l2": "replica state is shared-memory resident inside one launch; 256 MiB L2 flush before the timed region",
+                "equil_md_steps": args.equil_steps, "skin": float(w.cfg.skin) or 0.8,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(args.steps, 1),
+                    "d2h_bytes_per_step": d2h / max(args.steps, 1), "seconds": t_e2e,
+                    "call": "Engine.set_state + set_replica_params + sample_loop + get_state on host (pinned) buffers"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "mc_sweeps_per_s": tr_all / n_acid / (t_ms * 1e-3),
+            "samples_per_s": w.R * world * args.steps / (t_ms * 1e-3),
+            "md_steps_per_replica_sample": md_all / (w.R * world * max(args.steps, 1)),
+            "list_rebuilds_per_1k_md_steps": 1e3 * reb_all / max(md_all, 1.0),
+            "ph_sweep_wall_s_projected": w.num_samples * t_ms * 1e-3 / max(args.steps, 1),
+            "kernel_ms_cgpe_events": kernel_ms,
+            "roofline": {
+                "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                "traffic": None, "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_kind} clock; no FP32 entry in MEASURED_PEAKS.json)",
+                "kernel": "k_sample_loop",
+                "algorithmic_flop_per_md_step": per_step, "unique_listed_pairs": [float(s) / 2 for s in stats],
+                "note": "Verlet-list algorithm: work counted on the pairs the lists hold (SURVEY 8d formula); the kernel is "
+                        "barrier/latency-bound at one CTA per replica, not pipe-bound",
+                "allpairs_equivalent_tflops": allpairs_equiv,
+            },
+            "observables_check": {"alpha_mean": float(obs[..., 0].mean() / max(w.n_sites[0], 1)),
+                                  "rg_mean": float(obs[..., 3].mean()), "ree_mean": float(obs[..., 4].mean())},
+            "device": info["name"],
+        }
+        if not args.no_cpu_baseline:
+            try:
+                cpu, _ = cpu_measure(w, os.cpu_count() or 1, args.cpu_seconds)
+                line["cpu_baseline"] = cpu
+            except Exception as exc:  # the GPU line must still print
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {exc!r}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

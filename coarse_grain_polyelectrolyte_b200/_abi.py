@@ -111,6 +111,7 @@ SIGNATURES = {
     "observables": (C.c_int, [_p, _p, _p, _p]),
     "min_dist": (C.c_int, [_p, _p]),
     "get_counters": (C.c_int, [_p, _p, _p, _p, _p]),
+    "list_stats": (C.c_int, [_p, _p]),
     "last_call_ms": (C.c_int, [_p, _fp, _i32p]),
 }
 
@@ -339,6 +340,12 @@ class EngineBase:
         rb = np.zeros(self.R, np.int64)
         self._check(self._b.get_counters(self._h, _ptr(md), _ptr(tr), _ptr(ac), _ptr(rb)), "get_counters")
         return {"md_steps": md, "trials": tr, "accepted": ac, "list_rebuilds": rb}
+
+    def list_stats(self):
+        """[R][4]: directed WCA list entries, in-cutoff ones, directed DH entries, charged in-cutoff ones."""
+        out = np.empty((self.R, 4), np.float64)
+        self._check(self._b.list_stats(self._h, _ptr(out)), "list_stats")
+        return out
 
     def last_call_ms(self):
         ms, n = C.c_float(), C.c_int32()

@@ -120,20 +120,13 @@ int upload_wca(cgpe_handle *h) {
   return CGPE_OK;
 }
 
-// Row capacities of the two Verlet lists.  cap_dh follows the list radius (sites sit >= 3 bonds
-// apart along the backbone; room is left for coiled states); cap_wca takes what is left of the
-// 227 KB shared-memory budget, up to 64 entries.  Explicit values in the config win.
+// List shapes.  The Debye-Hueckel list is a bit matrix over the chargeable particles (fixed size);
+// the WCA row capacity takes what is left of the 227 KB shared-memory budget, up to 64 entries,
+// unless the config gives one.
 int choose_capacities(cgpe_handle *h) {
   DevParams &p = h->p;
   const int n_chg = p.n_chg;
-  if (h->cfg.cap_dh > 0) p.cap_d = h->cfg.cap_dh;
-  else {
-    int cap = (int)(24 + 3.0 * (h->cfg.r_cut + p.skin));
-    cap = (cap + 7) / 8 * 8;
-    if (cap > 248) cap = 248;
-    p.cap_d = cap;
-  }
-  if (p.cap_d > (n_chg > 1 ? n_chg - 1 : 1)) p.cap_d = n_chg > 1 ? n_chg - 1 : 1;
+  p.dw = ((n_chg + 31) / 32) | 1;   // odd row stride: thread-per-row reads hit distinct banks
   if (h->cfg.cap_wca > 0) p.cap_w = h->cfg.cap_wca;
   else {
     cudaDeviceProp prop;
@@ -161,9 +154,7 @@ int check_device_errors(cgpe_handle *h) {
   CU(cudaMemsetAsync(h->g.err, 0, sizeof(int) * h->p.R, h->stream));
   if (any & kErrNonFinite) return fail(h, CGPE_ERR_NUMERIC, "non-finite coordinate or velocity (first replica %d)", first);
   if (any & kErrFene) return fail(h, CGPE_ERR_NUMERIC, "FENE bond stretched beyond d_r_max (first replica %d)", first);
-  if (any & kErrWcaCap)
-    return fail(h, CGPE_ERR_CAPACITY, "WCA neighbour list overflow (cap_wca=%d, first replica %d): raise cap_wca", h->p.cap_w, first);
-  return fail(h, CGPE_ERR_CAPACITY, "Debye-Hueckel neighbour list overflow (cap_dh=%d, first replica %d): raise cap_dh", h->p.cap_d, first);
+  return fail(h, CGPE_ERR_CAPACITY, "WCA neighbour list overflow (cap_wca=%d, first replica %d): raise cap_wca or lower skin", h->p.cap_w, first);
 }
 
 int require_engine(cgpe_handle *h) {
@@ -245,8 +236,8 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   }
   // chargeable particles are fixed at set_state; size the lists for "every third bead" + ions
   p.n_chg = 0;
-  p.cap_w = cfg->cap_wca; p.cap_d = cfg->cap_dh;   // 0: chosen at set_state (choose_capacities)
-  if (p.cap_w > 255 || p.cap_d > 255 || p.cap_w < 0 || p.cap_d < 0) { delete h; return fail(nullptr, CGPE_ERR_INVALID, "list capacities must be <= 255"); }
+  p.cap_w = cfg->cap_wca;   // 0: chosen at set_state (choose_capacities)
+  if (p.cap_w > 255 || p.cap_w < 0) { delete h; return fail(nullptr, CGPE_ERR_INVALID, "list capacities must be <= 255"); }
 
   auto bail = [&](cudaError_t e, const char *what) {
     fail(nullptr, CGPE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -679,6 +670,18 @@ int cgpe_get_counters(cgpe_handle *h, int64_t *md_steps, int64_t *trials, int64_
   if (list_rebuilds) CU(cudaMemcpyAsync(list_rebuilds, h->g.rebuilds, sizeof(int64_t) * R, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return CGPE_OK;
+}
+
+int cgpe_list_stats(cgpe_handle *h, double *out) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!out) return fail(h, CGPE_ERR_INVALID, "out is NULL");
+  int rc = require_engine(h);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  CU(launch_list_stats(h->p, h->g, h->launch, h->d_tmp_d, h->stream));
+  CU(cudaMemcpyAsync(out, h->d_tmp_d, sizeof(double) * h->p.R * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return check_device_errors(h);
 }
 
 int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches) {

@@ -15,7 +15,7 @@ constexpr int kMaxRx = CGPE_MAX_REACTIONS;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // error bits raised by kernels into DevState::err[r]
-enum : int { kErrWcaCap = 1, kErrDhCap = 2, kErrNonFinite = 4, kErrFene = 8 };
+enum : int { kErrWcaCap = 1, kErrNonFinite = 4, kErrFene = 8 };
 
 struct DevReaction {
   int type_prot, type_deprot, type_ion;
@@ -31,7 +31,8 @@ struct DevParams {
   int n_chg;                    // chargeable particles per replica (sites [+ ions])
   int n_rx;
   int bond_kind, use_angle, use_dih, dih_mult, use_wca, use_dh;
-  int cap_w, cap_d;
+  int cap_w;                    // WCA list row capacity
+  int dw;                       // words per row of the Debye-Hueckel bit list (odd: conflict-free)
   int replica_offset;
   uint32_t thermostat_seed;
   float bond_k, bond_r0, fene_drmax2;

@@ -40,13 +40,13 @@ __host__ __device__ size_t chain_smem_layout(const DevParams &p, ChainSmem *s, u
   size_t a_cnt = take(sizeof(int) * kMaxRx * 2, 4);
   size_t a_flag = take(sizeof(int) * 4, 4);
   size_t a_wl = take(sizeof(uint16_t) * (size_t)p.cap_w * p.P, 4);
-  size_t a_dl = take(sizeof(uint16_t) * (size_t)p.cap_d * (p.n_chg > 0 ? p.n_chg : 1), 4);
+  size_t a_db = take(sizeof(uint32_t) * (size_t)p.dw * (p.n_chg > 0 ? p.n_chg : 1), 4);
+  size_t a_qm = take(sizeof(uint32_t) * (size_t)(p.dw > 0 ? p.dw : 1), 4);
   size_t a_chg = take(sizeof(uint16_t) * (p.n_chg > 0 ? p.n_chg : 1), 2);
   size_t a_cidx = take(sizeof(uint16_t) * p.P, 2);
   size_t a_lp = take(sizeof(uint16_t) * (size_t)(p.n_rx > 0 ? p.n_rx : 1) * (p.n_chg > 0 ? p.n_chg : 1), 2);
   size_t a_ld = take(sizeof(uint16_t) * (size_t)(p.n_rx > 0 ? p.n_rx : 1) * (p.n_chg > 0 ? p.n_chg : 1), 2);
   size_t a_wn = take((size_t)p.P, 1);
-  size_t a_dn = take((size_t)(p.n_chg > 0 ? p.n_chg : 1), 1);
   size_t a_type = take((size_t)p.P, 1);
   if (s) {
     s->pos = reinterpret_cast<float4 *>(base + a_pos);
@@ -57,13 +57,13 @@ __host__ __device__ size_t chain_smem_layout(const DevParams &p, ChainSmem *s, u
     s->cnt = reinterpret_cast<int *>(base + a_cnt);
     s->flag = reinterpret_cast<int *>(base + a_flag);
     s->wl = reinterpret_cast<uint16_t *>(base + a_wl);
-    s->dl = reinterpret_cast<uint16_t *>(base + a_dl);
+    s->dbits = reinterpret_cast<uint32_t *>(base + a_db);
+    s->qmask = reinterpret_cast<uint32_t *>(base + a_qm);
     s->chg = reinterpret_cast<uint16_t *>(base + a_chg);
     s->cidx = reinterpret_cast<uint16_t *>(base + a_cidx);
     s->lp = reinterpret_cast<uint16_t *>(base + a_lp);
     s->ld = reinterpret_cast<uint16_t *>(base + a_ld);
     s->wn = base + a_wn;
-    s->dn = base + a_dn;
     s->type = base + a_type;
   }
   return align_up(o, 16);
@@ -122,7 +122,6 @@ __device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
   for (int i = c.tid; i < (p.T + 1) * (p.T + 1); i += c.nt) c.s.tab[i] = c.g.wca_tab[i];
   for (int i = c.tid; i < p.n_chg; i += c.nt) {
     c.s.chg[i] = (uint16_t)c.g.chg[(size_t)c.r * p.n_chg + i];
-    c.s.dn[i] = 0;
     c.s.fd[i] = c.s.fd[p.n_chg + i] = c.s.fd[2 * p.n_chg + i] = 0.0f;
   }
   for (int m = 0; m < p.n_rx; ++m) {
@@ -135,6 +134,15 @@ __device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
   }
   __syncthreads();
   for (int i = c.tid; i < p.n_chg; i += c.nt) c.s.cidx[c.s.chg[i]] = (uint16_t)i;
+  // live mask of the chargeable particles that carry charge right now (the MC warp keeps it current)
+  for (int w = c.tid; w < p.dw; w += c.nt) {
+    uint32_t m = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int cj = w * 32 + b;
+      if (cj < p.n_chg && c.s.pos[c.s.chg[cj]].w != 0.0f) m |= 1u << b;
+    }
+    c.s.qmask[w] = m;
+  }
   __syncthreads();
 }
 
@@ -197,21 +205,21 @@ __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
     }
   }
   if (p.use_dh) {
+    // one bit per (chargeable, chargeable) pair inside r_cut + skin: fixed size, cannot overflow
     for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
-      const int i = c.s.chg[ci];
-      const float4 pi = c.s.pos[i];
-      int n = 0;
-      for (int cj = 0; cj < p.n_chg; ++cj) {
-        const int j = c.s.chg[cj];
-        V3 d;
-        const float r2 = dist2(c, pi, c.s.pos[j], &d);
-        if (r2 < c.rlist_d2 && cj != ci) {
-          if (n < p.cap_d) c.s.dl[(size_t)n * p.n_chg + ci] = (uint16_t)j;
-          ++n;
+      const float4 pi = c.s.pos[c.s.chg[ci]];
+      const int nw = (p.n_chg + 31) >> 5;
+      for (int w = 0; w < nw; ++w) {
+        uint32_t m = 0;
+        const int hi = min(32, p.n_chg - w * 32);
+        for (int b = 0; b < hi; ++b) {
+          V3 d;
+          const float r2 = dist2(c, pi, c.s.pos[c.s.chg[w * 32 + b]], &d);
+          if (r2 < c.rlist_d2) m |= 1u << b;
         }
+        if ((ci >> 5) == w) m &= ~(1u << (ci & 31));   // not its own partner
+        c.s.dbits[(size_t)ci * p.dw + w] = m;
       }
-      if (n > p.cap_d) { c.err |= kErrDhCap; n = p.cap_d; }
-      c.s.dn[ci] = (unsigned char)n;
     }
   }
   c.rebuilds += 1;
@@ -282,21 +290,24 @@ __device__ void compute_forces(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsigned 
     t.f[k][0] = f.x; t.f[k][1] = f.y; t.f[k][2] = f.z;
   }
   if (p.use_dh) {
+    const int nw = (p.n_chg + 31) >> 5;
     for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
-      const int i = c.s.chg[ci];
-      const float4 pi4 = c.s.pos[i];
+      const float4 pi4 = c.s.pos[c.s.chg[ci]];
       V3 f = {0.f, 0.f, 0.f};
       if (pi4.w != 0.0f) {
-        const int n = c.s.dn[ci];
-        for (int e = 0; e < n; ++e) {
-          const int j = c.s.dl[(size_t)e * p.n_chg + ci];
-          const float4 pj4 = c.s.pos[j];
-          V3 d;
-          const float r2 = dist2(c, pi4, pj4, &d);
-          if (pj4.w != 0.0f && r2 < c.rc2) {
-            float fr;
-            dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr);
-            f = f + (p.dh_pref * pi4.w * pj4.w * fr) * d;
+        for (int w = 0; w < nw; ++w) {
+          uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w];   // listed AND charged
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const float4 pj4 = c.s.pos[c.s.chg[w * 32 + b]];
+            V3 d;
+            const float r2 = dist2(c, pi4, pj4, &d);
+            if (r2 < c.rc2) {
+              float fr;
+              dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr);
+              f = f + (p.dh_pref * pi4.w * pj4.w * fr) * d;
+            }
           }
         }
       }
@@ -425,17 +436,21 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
           }
         }
         if (p.use_dh && dq != 0.f) {
+          // lane b looks at bit b of every word of the site's row: balanced for any list density
           const int ci = c.s.cidx[i];
-          const int n = c.s.dn[ci];
+          const int nw = (p.n_chg + 31) >> 5;
           float sum = 0.f;
-          for (int e = c.lane; e < n; e += 32) {
-            const int j = c.s.dl[(size_t)e * p.n_chg + ci];
-            const float4 pj4 = c.s.pos[j];
-            V3 d;
-            const float r2 = dist2(c, pi4, pj4, &d);
-            if (pj4.w != 0.f && r2 < c.rc2) {
-              float fr;
-              sum = fmaf(pj4.w, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), sum);
+          for (int w = 0; w < nw; ++w) {
+            const uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w];
+            if (m == 0u) continue;   // warp-uniform
+            if ((m >> c.lane) & 1u) {
+              const float4 pj4 = c.s.pos[c.s.chg[w * 32 + c.lane]];
+              V3 d;
+              const float r2 = dist2(c, pi4, pj4, &d);
+              if (r2 < c.rc2) {
+                float fr;
+                sum = fmaf(pj4.w, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), sum);
+              }
             }
           }
           de = fmaf(p.dh_pref * dq, sum, de);
@@ -453,6 +468,11 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
           if (c.lane == 0) {
             c.s.type[i] = (unsigned char)t_new;
             c.s.pos[i].w = q_new;
+            if (p.use_dh) {
+              const int ci = c.s.cidx[i];
+              if (q_new != 0.f) c.s.qmask[ci >> 5] |= 1u << (ci & 31);
+              else c.s.qmask[ci >> 5] &= ~(1u << (ci & 31));
+            }
             src[k] = src[n_src - 1];
             dst[n_dst] = (uint16_t)i;
           }
@@ -625,6 +645,60 @@ k_md_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
   if (c.err) atomicOr(&c.g.err[c.r], c.err);
 }
 
+// census of the Verlet lists for the current configuration (roofline arithmetic)
+template <int ITEMS>
+__global__ void __launch_bounds__(1024, 1)
+k_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, double *out) {
+  Ctx c{p, g};
+  c.r = blockIdx.x;
+  chain_smem_layout(p, &c.s, smem_raw);
+  init_ctx(c);
+  Thr<ITEMS> t;
+  load_state(c, t, false);
+  build_lists(c, t);
+  double nw = 0, nw_in = 0, nd = 0, nd_in = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i < p.P && p.use_wca) {
+      const int ti = c.s.type[i];
+      const float4 pi4 = c.s.pos[i];
+      for (int e = 0; e < c.s.wn[i]; ++e) {
+        const int j = c.s.wl[(size_t)e * p.P + i];
+        V3 d;
+        const float r2 = dist2(c, pi4, c.s.pos[j], &d);
+        nw += 1;
+        if (ti < p.T && r2 < c.s.tab[ti * (p.T + 1) + c.s.type[j]].z) nw_in += 1;
+      }
+    }
+  }
+  if (p.use_dh)
+    for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
+      const float4 pi4 = c.s.pos[c.s.chg[ci]];
+      for (int w = 0; w < (p.n_chg + 31) >> 5; ++w) {
+        uint32_t m = c.s.dbits[(size_t)ci * p.dw + w];
+        nd += __popc(m);
+        m &= c.s.qmask[w];
+        while (m && pi4.w != 0.f) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          V3 d;
+          if (dist2(c, pi4, c.s.pos[c.s.chg[w * 32 + b]], &d) < c.rc2) nd_in += 1;
+        }
+      }
+    }
+  nw = warp_sum(nw); nw_in = warp_sum(nw_in); nd = warp_sum(nd); nd_in = warp_sum(nd_in);
+  __syncthreads();
+  if (c.lane == 0) { c.s.red[c.warp * 4] = nw; c.s.red[c.warp * 4 + 1] = nw_in; c.s.red[c.warp * 4 + 2] = nd; c.s.red[c.warp * 4 + 3] = nd_in; }
+  __syncthreads();
+  if (c.tid == 0) {
+    double a[4] = {0, 0, 0, 0};
+    for (int w = 0; w < (c.nt + 31) / 32; ++w) for (int q = 0; q < 4; ++q) a[q] += c.s.red[w * 4 + q];
+    for (int q = 0; q < 4; ++q) out[c.r * 4 + q] = a[q];
+  }
+  if (c.err) atomicOr(&c.g.err[c.r], c.err);
+}
+
 // The sampling loop of perform_sampling (E.py:88-106), one launch for all samples.
 template <int ITEMS>
 __global__ void __launch_bounds__(1024, 1)
@@ -756,6 +830,14 @@ cudaError_t launch_mc_run(const DevParams &p, const DevState &g, const ChainLaun
 
 cudaError_t launch_md_forces(const DevParams &p, const DevState &g, const ChainLaunch &L, float4 *out, cudaStream_t st) {
   auto k = L.items == 1 ? k_md_forces<1> : k_md_forces<2>;
+  cudaError_t e = opt_in_smem(k, L.smem);
+  if (e != cudaSuccess) return e;
+  k<<<p.R, L.threads, L.smem, st>>>(p, g, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_list_stats(const DevParams &p, const DevState &g, const ChainLaunch &L, double *out, cudaStream_t st) {
+  auto k = L.items == 1 ? k_list_stats<1> : k_list_stats<2>;
   cudaError_t e = opt_in_smem(k, L.smem);
   if (e != cudaSuccess) return e;
   k<<<p.R, L.threads, L.smem, st>>>(p, g, out);

@@ -14,11 +14,12 @@ struct ChainSmem {
   int *cnt;           // [n_rx][2] n_prot, n_deprot
   int *flag;          // [4]
   uint16_t *wl;       // [cap_w][P] WCA Verlet list (column per particle)
-  uint16_t *dl;       // [cap_d][n_chg] Debye-Hueckel Verlet list (particle ids)
+  uint32_t *dbits;    // [n_chg][dw] Debye-Hueckel Verlet list, one bit per chargeable partner
+  uint32_t *qmask;    // [dw] chargeable particles that carry charge right now
   uint16_t *chg;      // [n_chg] chargeable particle ids
   uint16_t *cidx;     // [P] particle id -> chargeable index (0xFFFF = none)
   uint16_t *lp, *ld;  // [n_rx][n_chg] protonated / deprotonated bookkeeping lists
-  unsigned char *wn, *dn;   // list lengths
+  unsigned char *wn;        // WCA list lengths
   unsigned char *type;      // [P]
 };
 
@@ -37,6 +38,7 @@ cudaError_t launch_steepest_descent(const DevParams &p, const DevState &g, const
 cudaError_t launch_mc_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int m, int n_trials,
                           cgpe_trial_record *trace, cudaStream_t st);
 cudaError_t launch_md_forces(const DevParams &p, const DevState &g, const ChainLaunch &L, float4 *out, cudaStream_t st);
+cudaError_t launch_list_stats(const DevParams &p, const DevState &g, const ChainLaunch &L, double *out, cudaStream_t st);
 cudaError_t launch_sample_loop(const DevParams &p, const DevState &g, const ChainLaunch &L,
                                const cgpe_sample_params &sp, uint32_t thr1, uint32_t thr2, double *obs,
                                float *qdist, cudaStream_t st);

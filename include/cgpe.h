@@ -90,8 +90,8 @@ typedef struct cgpe_config {
   int32_t use_wca;        /* M.py:57                                                           */
   int32_t use_dh;         /* electrostatics.DH (M.py:97-107)                                   */
   int32_t n_reactions;
-  int32_t cap_wca;        /* neighbour-list row capacity, 0 = library default                  */
-  int32_t cap_dh;
+  int32_t cap_wca;        /* WCA neighbour-list row capacity, 0 = library default              */
+  int32_t cap_dh;         /* unused (the Debye-Hueckel list is a fixed-size bit matrix)        */
   int32_t device;         /* CUDA ordinal, -1 = current device                                 */
   int32_t reserved0;
   double bond_k, bond_r0, fene_drmax;   /* M.py:35-39                                          */
@@ -213,6 +213,10 @@ CGPE_API int cgpe_min_dist(cgpe_handle *h, double *out);
  * list_rebuilds [R]; any pointer may be NULL */
 CGPE_API int cgpe_get_counters(cgpe_handle *h, int64_t *md_steps, int64_t *trials, int64_t *accepted,
                       int64_t *list_rebuilds);
+/* Verlet-list census of the current configuration, out [R][4] = directed WCA list entries,
+ * those inside their cutoff, directed Debye-Hueckel list entries, those between two charged
+ * particles inside r_cut.  (Unique pairs = directed / 2.)  Feeds the roofline arithmetic. */
+CGPE_API int cgpe_list_stats(cgpe_handle *h, double *out);
 /* device time of the last hot-path call in milliseconds (CUDA events on the handle's stream) and
  * the number of kernels it launched */
 CGPE_API int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches);

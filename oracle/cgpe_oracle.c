@@ -89,6 +89,15 @@ struct orc_handle {
   double force_cap;
   int have_state;
   double *last_obs; float *last_qdist; int last_ns, last_qrows;
+  /* optional Verlet lists (performance mode for the CPU baseline; results are identical up to
+     summation order).  Full rows: wl row i holds every j within rc_wca_max+skin, dl row i (only
+     chargeable i) every chargeable j within r_cut+skin. */
+  int use_lists; double skin;
+  int *wl, *wn, *dl, *dn; int cap_wl, cap_dl;   /* [R][P][cap], [R][P] */
+  double *ref;                                  /* [R][P][3] positions at the last build */
+  int *lists_valid;                             /* [R] */
+  uint8_t *chargeable;                          /* [R][P] */
+  int64_t *rebuilds;                            /* [R] */
   char err[512];
 };
 typedef struct orc_handle orc_handle;
@@ -243,6 +252,8 @@ static double dihedral_energy_force(const cgpe_config *c, const double *p1, cons
 /* Full interaction energy / forces of replica r, all pairs (R3, R4)                            */
 /* f may be NULL.  e[0..2] = coulomb, bonded, non_bonded                                        */
 /* ------------------------------------------------------------------------------------------- */
+static void nonbonded_listed(orc_handle *h, int r, double *f, double e[3]);
+
 static void interactions(const orc_handle *h, int r, double *f, double e[3]) {
   const cgpe_config *c = &h->cfg;
   const int P = h->P, T = h->T;
@@ -280,6 +291,7 @@ static void interactions(const orc_handle *h, int r, double *f, double e[3]) {
   }
   /* non-bonded: every pair, bonded neighbours included (the reference sets no exclusions) */
   if (!c->use_wca && !c->use_dh) return;
+  if (h->use_lists) { nonbonded_listed((orc_handle *)h, r, f, e); return; }
   for (int i = 0; i < P; ++i) {
     if (ty[i] >= T) continue; /* non-interacting type */
     const double *xi = X(h, r, i);
@@ -298,6 +310,97 @@ static void interactions(const orc_handle *h, int r, double *f, double e[3]) {
       }
       if (f && fr != 0.0) for (int k = 0; k < 3; ++k) { f[i * 3 + k] += fr * d[k]; f[j * 3 + k] -= fr * d[k]; }
     }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Verlet-list mode: the same sums as interactions(), restricted to listed pairs                 */
+/* ------------------------------------------------------------------------------------------- */
+static double wca_rc_max(const orc_handle *h) {
+  double m = 0.0;
+  for (int a = 0; a < h->T; ++a) for (int b = 0; b < h->T; ++b) {
+    double e = h->cfg.wca_eps[a * CGPE_MAX_TYPES + b], s = h->cfg.wca_sig[a * CGPE_MAX_TYPES + b];
+    if (e != 0.0 && s != 0.0 && 1.122462048309373 * s > m) m = 1.122462048309373 * s;
+  }
+  return m;
+}
+
+static void build_lists(orc_handle *h, int r) {
+  const int P = h->P;
+  const double L = h->cfg.box_l;
+  const double rw = wca_rc_max(h) + h->skin, rw2 = rw * rw;
+  const double rd = h->rcut[r] + h->skin, rd2 = rd * rd;
+  int *wl = h->wl + (size_t)r * P * h->cap_wl, *wn = h->wn + (size_t)r * P;
+  int *dl = h->dl + (size_t)r * P * h->cap_dl, *dn = h->dn + (size_t)r * P;
+  const uint8_t *chg = h->chargeable + (size_t)r * P;
+  memset(wn, 0, sizeof(int) * P);
+  memset(dn, 0, sizeof(int) * P);
+  for (int i = 0; i < P; ++i) {
+    const double *xi = X(h, r, i);
+    for (int j = i + 1; j < P; ++j) {
+      const double *xj = X(h, r, j);
+      double d0 = min_image(xi[0] - xj[0], L), d1 = min_image(xi[1] - xj[1], L), d2 = min_image(xi[2] - xj[2], L);
+      double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+      if (h->cfg.use_wca && r2 < rw2) {
+        if (wn[i] >= h->cap_wl || wn[j] >= h->cap_wl) { fprintf(stderr, "oracle: WCA list overflow\n"); abort(); }
+        wl[(size_t)i * h->cap_wl + wn[i]++] = j;
+        wl[(size_t)j * h->cap_wl + wn[j]++] = i;
+      }
+      if (h->cfg.use_dh && chg[i] && chg[j] && r2 < rd2) {
+        if (dn[i] >= h->cap_dl || dn[j] >= h->cap_dl) { fprintf(stderr, "oracle: DH list overflow\n"); abort(); }
+        dl[(size_t)i * h->cap_dl + dn[i]++] = j;
+        dl[(size_t)j * h->cap_dl + dn[j]++] = i;
+      }
+    }
+  }
+  memcpy(h->ref + (size_t)r * P * 3, h->x + (size_t)r * P * 3, sizeof(double) * 3 * P);
+  h->lists_valid[r] = 1;
+  h->rebuilds[r] += 1;
+}
+
+static void ensure_lists(orc_handle *h, int r) {
+  if (!h->lists_valid[r]) { build_lists(h, r); return; }
+  const double *x = h->x + (size_t)r * h->P * 3, *ref = h->ref + (size_t)r * h->P * 3;
+  const double lim = 0.25 * h->skin * h->skin;
+  for (int i = 0; i < h->P; ++i) {
+    double a = x[i * 3] - ref[i * 3], b = x[i * 3 + 1] - ref[i * 3 + 1], c = x[i * 3 + 2] - ref[i * 3 + 2];
+    if (!(a * a + b * b + c * c <= lim)) { build_lists(h, r); return; }
+  }
+}
+
+/* non-bonded part over listed pairs (each unique pair once: j > i) */
+static void nonbonded_listed(orc_handle *h, int r, double *f, double e[3]) {
+  const cgpe_config *c = &h->cfg;
+  const int P = h->P, T = h->T;
+  const uint8_t *ty = h->type + (size_t)r * P;
+  const double *q = h->q + (size_t)r * P;
+  const double L = c->box_l;
+  ensure_lists(h, r);
+  const int *wl = h->wl + (size_t)r * P * h->cap_wl, *wn = h->wn + (size_t)r * P;
+  const int *dl = h->dl + (size_t)r * P * h->cap_dl, *dn = h->dn + (size_t)r * P;
+  for (int i = 0; i < P; ++i) {
+    if (ty[i] >= T) continue;
+    const double *xi = X(h, r, i);
+    if (c->use_wca)
+      for (int k = 0; k < wn[i]; ++k) {
+        const int j = wl[(size_t)i * h->cap_wl + k];
+        if (j < i || ty[j] >= T) continue;
+        const double *xj = X(h, r, j);
+        double d[3] = {min_image(xi[0] - xj[0], L), min_image(xi[1] - xj[1], L), min_image(xi[2] - xj[2], L)};
+        double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], fr;
+        e[2] += wca(c->wca_eps[ty[i] * CGPE_MAX_TYPES + ty[j]], c->wca_sig[ty[i] * CGPE_MAX_TYPES + ty[j]], r2, &fr);
+        if (f && fr != 0.0) for (int a = 0; a < 3; ++a) { f[i * 3 + a] += fr * d[a]; f[j * 3 + a] -= fr * d[a]; }
+      }
+    if (c->use_dh && q[i] != 0.0)
+      for (int k = 0; k < dn[i]; ++k) {
+        const int j = dl[(size_t)i * h->cap_dl + k];
+        if (j < i || ty[j] >= T || q[j] == 0.0) continue;
+        const double *xj = X(h, r, j);
+        double d[3] = {min_image(xi[0] - xj[0], L), min_image(xi[1] - xj[1], L), min_image(xi[2] - xj[2], L)};
+        double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], fr;
+        e[0] += dh(c->dh_prefactor * q[i] * q[j], h->kappa[r], h->rcut[r], r2, &fr);
+        if (f && fr != 0.0) for (int a = 0; a < 3; ++a) { f[i * 3 + a] += fr * d[a]; f[j * 3 + a] -= fr * d[a]; }
+      }
   }
 }
 
@@ -347,6 +450,10 @@ int orc_create(const cgpe_config *cfg, orc_handle **out) {
     h->kT[r] = cfg->kT; h->gamma[r] = cfg->gamma;
   }
   h->thermostat_seed = 0;
+  h->use_lists = 0; h->skin = 0.8; h->cap_wl = 96; h->cap_dl = 256;
+  h->lists_valid = calloc(h->R, sizeof(int));
+  h->rebuilds = calloc(h->R, sizeof(int64_t));
+  h->chargeable = calloc(RP, 1);
   *out = h;
   return CGPE_OK;
 }
@@ -359,6 +466,7 @@ void orc_destroy(orc_handle *h) {
   free(h->pH); free(h->kappa); free(h->rcut); free(h->kT); free(h->gamma); free(h->time);
   free(h->md_counter); free(h->md_steps); free(h->samples_done); free(h->f_valid);
   free(h->trials); free(h->accepted); free(h->last_obs); free(h->last_qdist);
+  free(h->wl); free(h->wn); free(h->dl); free(h->dn); free(h->ref); free(h->lists_valid); free(h->rebuilds); free(h->chargeable);
   free(h);
 }
 
@@ -401,7 +509,13 @@ int orc_set_state(orc_handle *h, const float *xyzq, const float *vel, const uint
     h->type[k] = type[k];
   }
   rebuild_lists(h);
-  for (int r = 0; r < h->R; ++r) h->f_valid[r] = 0;
+  {
+    unsigned reactive = 0;
+    for (int m = 0; m < h->cfg.n_reactions; ++m) reactive |= (1u << h->cfg.reactions[m].type_prot) | (1u << h->cfg.reactions[m].type_deprot);
+    for (size_t k = 0; k < RP; ++k)
+      h->chargeable[k] = (h->q[k] != 0.0) || ((reactive >> h->type[k]) & 1u) || ((int)(k % h->P) >= h->NC);
+  }
+  for (int r = 0; r < h->R; ++r) { h->f_valid[r] = 0; h->lists_valid[r] = 0; }
   h->have_state = 1;
   return CGPE_OK;
 }
@@ -428,7 +542,21 @@ int orc_get_state_f64(orc_handle *h, double *x, double *v, double *q) {
 /* double-precision position upload for finite-difference tests */
 int orc_set_positions_f64(orc_handle *h, const double *x) {
   memcpy(h->x, x, sizeof(double) * 3 * (size_t)h->R * h->P);
-  for (int r = 0; r < h->R; ++r) h->f_valid[r] = 0;
+  for (int r = 0; r < h->R; ++r) { h->f_valid[r] = 0; h->lists_valid[r] = 0; }
+  return CGPE_OK;
+}
+
+/* Verlet-list mode on/off (performance only; used for the CPU baseline timing) */
+int orc_set_list_mode(orc_handle *h, int32_t on, double skin) {
+  h->use_lists = on != 0;
+  if (skin > 0.0) h->skin = skin;
+  if (on && !h->wl) {
+    size_t RP = (size_t)h->R * h->P;
+    h->wl = malloc(sizeof(int) * RP * h->cap_wl); h->wn = calloc(RP, sizeof(int));
+    h->dl = malloc(sizeof(int) * RP * h->cap_dl); h->dn = calloc(RP, sizeof(int));
+    h->ref = calloc(RP * 3, sizeof(double));
+  }
+  for (int r = 0; r < h->R; ++r) h->lists_valid[r] = 0;
   return CGPE_OK;
 }
 
@@ -444,6 +572,7 @@ int orc_set_replica_params(orc_handle *h, const double *pH, const double *kappa,
     if (kT) h->kT[r] = kT[r];
     if (gamma) h->gamma[r] = gamma[r];
     if (kappa || rcut || kT || gamma) h->f_valid[r] = 0;
+    if (rcut) h->lists_valid[r] = 0;
   }
   return CGPE_OK;
 }
@@ -451,7 +580,7 @@ int orc_set_replica_params(orc_handle *h, const double *pH, const double *kappa,
 int orc_set_wca(orc_handle *h, const double *eps, const double *sig) {
   memcpy(h->cfg.wca_eps, eps, sizeof(h->cfg.wca_eps));
   memcpy(h->cfg.wca_sig, sig, sizeof(h->cfg.wca_sig));
-  for (int r = 0; r < h->R; ++r) h->f_valid[r] = 0;
+  for (int r = 0; r < h->R; ++r) { h->f_valid[r] = 0; h->lists_valid[r] = 0; }
   return CGPE_OK;
 }
 
@@ -568,6 +697,31 @@ static double site_delta_e(const orc_handle *h, int r, int i, int t_old, int t_n
   const double *q = h->q + (size_t)r * h->P;
   const double *xi = X(h, r, i);
   double de_w = 0.0, de_c = 0.0, fr;
+  if (h->use_lists) {
+    orc_handle *hm = (orc_handle *)h;
+    ensure_lists(hm, r);
+    const int *wl = h->wl + ((size_t)r * h->P + i) * h->cap_wl, *dl = h->dl + ((size_t)r * h->P + i) * h->cap_dl;
+    const int nw = h->wn[(size_t)r * h->P + i], nd = h->dn[(size_t)r * h->P + i];
+    if (c->use_wca)
+      for (int k = 0; k < nw; ++k) {
+        const int j = wl[k];
+        if (ty[j] >= h->T) continue;
+        const double *xj = X(h, r, j);
+        double d0 = min_image(xi[0] - xj[0], c->box_l), d1 = min_image(xi[1] - xj[1], c->box_l), d2 = min_image(xi[2] - xj[2], c->box_l);
+        double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+        if (t_new < h->T) de_w += wca(c->wca_eps[t_new * CGPE_MAX_TYPES + ty[j]], c->wca_sig[t_new * CGPE_MAX_TYPES + ty[j]], r2, &fr);
+        if (t_old < h->T) de_w -= wca(c->wca_eps[t_old * CGPE_MAX_TYPES + ty[j]], c->wca_sig[t_old * CGPE_MAX_TYPES + ty[j]], r2, &fr);
+      }
+    if (c->use_dh)
+      for (int k = 0; k < nd; ++k) {
+        const int j = dl[k];
+        if (ty[j] >= h->T || q[j] == 0.0) continue;
+        const double *xj = X(h, r, j);
+        double d0 = min_image(xi[0] - xj[0], c->box_l), d1 = min_image(xi[1] - xj[1], c->box_l), d2 = min_image(xi[2] - xj[2], c->box_l);
+        de_c += dh(c->dh_prefactor * (q_new - q_old) * q[j], h->kappa[r], h->rcut[r], d0 * d0 + d1 * d1 + d2 * d2, &fr);
+      }
+    return de_w + de_c;
+  }
   for (int j = 0; j < h->P; ++j) {
     if (j == i || ty[j] >= h->T) continue;
     const double *xj = X(h, r, j);
@@ -755,7 +909,41 @@ int orc_get_counters(orc_handle *h, int64_t *md_steps, int64_t *trials, int64_t 
   if (md_steps) memcpy(md_steps, h->md_steps, sizeof(int64_t) * h->R);
   if (trials) memcpy(trials, h->trials, sizeof(int64_t) * h->R * h->cfg.n_reactions);
   if (accepted) memcpy(accepted, h->accepted, sizeof(int64_t) * h->R * h->cfg.n_reactions);
-  if (rebuilds) memset(rebuilds, 0, sizeof(int64_t) * h->R);
+  if (rebuilds) memcpy(rebuilds, h->rebuilds, sizeof(int64_t) * h->R);
+  return CGPE_OK;
+}
+
+int orc_list_stats(orc_handle *h, double *out) {
+  if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
+  const int was = h->use_lists;
+  if (!was) orc_set_list_mode(h, 1, 0.0);
+  const cgpe_config *c = &h->cfg;
+  for (int r = 0; r < h->R; ++r) {
+    build_lists(h, r);
+    double a[4] = {0, 0, 0, 0};
+    const uint8_t *ty = h->type + (size_t)r * h->P;
+    const double *q = h->q + (size_t)r * h->P;
+    for (int i = 0; i < h->P; ++i) {
+      const double *xi = X(h, r, i);
+      for (int k = 0; k < h->wn[(size_t)r * h->P + i]; ++k) {
+        const int j = h->wl[((size_t)r * h->P + i) * h->cap_wl + k];
+        const double *xj = X(h, r, j);
+        double d0 = min_image(xi[0] - xj[0], c->box_l), d1 = min_image(xi[1] - xj[1], c->box_l), d2 = min_image(xi[2] - xj[2], c->box_l);
+        double s = ty[i] < h->T && ty[j] < h->T ? c->wca_sig[ty[i] * CGPE_MAX_TYPES + ty[j]] : 0.0;
+        a[0] += 1;
+        if (d0 * d0 + d1 * d1 + d2 * d2 < 1.2599210498948731648 * s * s) a[1] += 1;
+      }
+      for (int k = 0; k < h->dn[(size_t)r * h->P + i]; ++k) {
+        const int j = h->dl[((size_t)r * h->P + i) * h->cap_dl + k];
+        const double *xj = X(h, r, j);
+        double d0 = min_image(xi[0] - xj[0], c->box_l), d1 = min_image(xi[1] - xj[1], c->box_l), d2 = min_image(xi[2] - xj[2], c->box_l);
+        a[2] += 1;
+        if (q[i] != 0.0 && q[j] != 0.0 && d0 * d0 + d1 * d1 + d2 * d2 < h->rcut[r] * h->rcut[r]) a[3] += 1;
+      }
+    }
+    memcpy(out + 4 * r, a, sizeof(a));
+  }
+  if (!was) { h->use_lists = 0; }
   return CGPE_OK;
 }
 

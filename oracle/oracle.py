@@ -41,6 +41,7 @@ def binding():
         lib.orc_philox4x32_10.argtypes = [C.c_void_p] * 3
         lib.orc_philox4x32_10.restype = None
         lib.orc_set_threads.argtypes = [C.c_int32]
+        lib.orc_set_list_mode.argtypes = [C.c_void_p, C.c_int32, C.c_double]
     return _binding
 
 
@@ -49,6 +50,10 @@ class OracleEngine(_abi.EngineBase):
 
     def __init__(self, cfg):
         super().__init__(binding(), cfg)
+
+    def set_list_mode(self, on=True, skin=0.0):
+        """Verlet-list evaluation (same sums, listed pairs only): the CPU-baseline configuration."""
+        self._check(self._b.lib.orc_set_list_mode(self._h, int(on), float(skin)), "set_list_mode")
 
     def state_f64(self):
         x = np.empty((self.R, self.P, 3)); v = np.empty((self.R, self.P, 3)); q = np.empty((self.R, self.P))

@@ -152,7 +152,8 @@ def test_steepest_descent_matches_oracle(Engine, oracle_mod):
     g1, o1 = _pair(Engine, oracle_mod, w, state)
     for e in (g1, o1):
         e.steepest_descent(1, f_max=0.0, gamma=0.1, max_displacement=0.1)
-    assert np.abs(g1.get_state()[0][..., :3] - o1.state_f64()[0]).max() < 1e-5
+    # unclamped components move by gamma*f: FP32 force error 3e-7*|F|max ~ 1e-4 -> 1e-5 in x
+    assert np.abs(g1.get_state()[0][..., :3] - o1.state_f64()[0]).max() < 5e-5
     # f_max above every force: converged after the first displacement, no further motion
     g2, o2 = _pair(Engine, oracle_mod, w, state)
     for e in (g2, o2):
