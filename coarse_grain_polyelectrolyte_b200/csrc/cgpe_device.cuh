@@ -33,6 +33,7 @@ struct DevParams {
   int bond_kind, use_angle, use_dih, dih_mult, use_wca, use_dh;
   int cap_w;                    // WCA list row capacity
   int dw;                       // words per row of the Debye-Hueckel bit list (odd: conflict-free)
+  int dh_group;                 // sub-threads sharing one Debye-Hueckel row (1..4)
   int replica_offset;
   uint32_t thermostat_seed;
   float bond_k, bond_r0, fene_drmax2;
@@ -120,16 +121,23 @@ __device__ __forceinline__ V3 xyz(float4 p) { return {p.x, p.y, p.z}; }
 // ------------------------------------------------------------------------------------------------
 // pair terms
 // ------------------------------------------------------------------------------------------------
+// MUFU.RCP, ~1 ulp; the IEEE-rounded __frcp_rn costs a Newton step and a fix-up path on top
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // WCA (M.py:74-76).  tab = {24 eps, sigma^2, rc^2, eps}.  Returns F/r; r2 must be < tab.z.
 __device__ __forceinline__ float wca_force_over_r(float4 tab, float r2) {
-  const float inv_r2 = __frcp_rn(r2);
+  const float inv_r2 = fast_rcp(r2);
   const float s2 = tab.y * inv_r2, s6 = s2 * s2 * s2;
   return tab.x * s6 * fmaf(2.0f, s6, -1.0f) * inv_r2;
 }
 // energy 4 eps [s^12 - s^6 + 1/4]
 __device__ __forceinline__ float wca_energy(float4 tab, float r2) {
   if (r2 >= tab.z) return 0.0f;
-  const float s2 = tab.y * __frcp_rn(r2), s6 = s2 * s2 * s2;
+  const float s2 = tab.y * fast_rcp(r2), s6 = s2 * s2 * s2;
   return 4.0f * tab.w * (fmaf(s6, s6, -s6) + 0.25f);
 }
 // Debye-Hueckel (M.py:97-107): e = exp(-kappa r)/r ; F/r = e (1 + kappa r)/r^2 ; both without the

@@ -36,7 +36,7 @@ __host__ __device__ size_t chain_smem_layout(const DevParams &p, ChainSmem *s, u
   size_t a_tab = take(sizeof(float4) * TT, 16);
   size_t a_red = take(sizeof(double) * 32 * 4, 8);
   size_t a_slot = take(sizeof(float) * 9 * p.NC, 4);
-  size_t a_fd = take(sizeof(float) * 3 * (p.n_chg > 0 ? p.n_chg : 1), 4);
+  size_t a_fd = take(sizeof(float) * 3 * (size_t)(p.dh_group > 0 ? p.dh_group : 1) * (p.n_chg > 0 ? p.n_chg : 1), 4);
   size_t a_cnt = take(sizeof(int) * kMaxRx * 2, 4);
   size_t a_flag = take(sizeof(int) * 4, 4);
   size_t a_wl = take(sizeof(uint16_t) * (size_t)p.cap_w * p.P, 4);
@@ -77,6 +77,7 @@ namespace {
 template <int ITEMS>
 struct Thr {
   float x[ITEMS][3], v[ITEMS][3], f[ITEMS][3], ref[ITEMS][3];
+  int l[ITEMS];   // index within its chain, -1 for particles that are not chain beads
 };
 
 struct Ctx {
@@ -85,15 +86,21 @@ struct Ctx {
   ChainSmem s;
   int r;              // replica (local)
   int tid, nt, lane, warp;
-  float kappa, rc2, neg_kappa_log2e, rlist_d2, gamma, noise_pref;
+  float kappa, rc2, neg_kappa_log2e, rlist_d2, rlist_max, gamma, noise_pref;
+  bool wrap;          // false: every listed pair is closer directly than through any periodic image
   int err;            // thread-local error bits, merged at exit
   long long rebuilds; // uniform
 };
 
+template <bool WRAP>
 __device__ __forceinline__ float dist2(const Ctx &c, float4 a, float4 b, V3 *d) {
-  d->x = min_image(a.x - b.x, c.p.box_l, c.p.inv_box_l);
-  d->y = min_image(a.y - b.y, c.p.box_l, c.p.inv_box_l);
-  d->z = min_image(a.z - b.z, c.p.box_l, c.p.inv_box_l);
+  if (WRAP) {
+    d->x = min_image(a.x - b.x, c.p.box_l, c.p.inv_box_l);
+    d->y = min_image(a.y - b.y, c.p.box_l, c.p.inv_box_l);
+    d->z = min_image(a.z - b.z, c.p.box_l, c.p.inv_box_l);
+  } else {
+    d->x = a.x - b.x; d->y = a.y - b.y; d->z = a.z - b.z;
+  }
   return fmaf(d->x, d->x, fmaf(d->y, d->y, d->z * d->z));
 }
 
@@ -117,12 +124,13 @@ __device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
       c.s.cidx[i] = 0xFFFFu;
       c.s.wn[i] = 0;
     }
+    t.l[k] = (i < p.NC) ? (p.NC == p.N ? i : i % p.N) : -1;
   }
   for (int i = c.tid; i < 9 * p.NC; i += c.nt) c.s.slot[i] = 0.0f;
   for (int i = c.tid; i < (p.T + 1) * (p.T + 1); i += c.nt) c.s.tab[i] = c.g.wca_tab[i];
   for (int i = c.tid; i < p.n_chg; i += c.nt) {
     c.s.chg[i] = (uint16_t)c.g.chg[(size_t)c.r * p.n_chg + i];
-    c.s.fd[i] = c.s.fd[p.n_chg + i] = c.s.fd[2 * p.n_chg + i] = 0.0f;
+    for (int gsub = 0; gsub < 3 * p.dh_group; ++gsub) c.s.fd[gsub * p.n_chg + i] = 0.0f;
   }
   for (int m = 0; m < p.n_rx; ++m) {
     const int *gp = c.g.lst_prot + ((size_t)c.r * p.n_rx + m) * p.P;
@@ -178,10 +186,14 @@ __device__ void store_state(Ctx &c, Thr<ITEMS> &t, bool store_forces) {
 }
 
 // ---- Verlet lists ------------------------------------------------------------------------------
-// Requires s.pos current and visible (barrier before).  Rows are written and later read by the
-// same thread, so the MD loop needs no barrier after this; the MC warp gets one anyway.
-template <int ITEMS>
-__device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
+// WCA rows hold every partner inside (max WCA cutoff + skin) EXCEPT the same-chain neighbours
+// i+-1, i+-2, which the bonded owner evaluates directly (compute_forces).  The Debye-Hueckel list is
+// one bit per (chargeable, chargeable) pair inside r_cut + skin: fixed size, cannot overflow.
+// Requires s.pos current and visible.  Contains block barriers (bounding-box reduction that
+// decides whether minimum-image arithmetic can be skipped until the next rebuild, and a trailing
+// one that publishes the rows: the Debye-Hueckel rows are read by other threads).
+template <int ITEMS, bool WRAP>
+__device__ void build_rows(Ctx &c, Thr<ITEMS> &t) {
   const DevParams &p = c.p;
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
@@ -190,11 +202,14 @@ __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
       t.ref[k][0] = t.x[k][0]; t.ref[k][1] = t.x[k][1]; t.ref[k][2] = t.x[k][2];
       if (p.use_wca) {
         const float4 pi = c.s.pos[i];
+        // same-chain partners handled by the bonded owner (also excludes j == i)
+        int ex_lo = i, ex_hi = i;
+        if (t.l[k] >= 0) { ex_lo = i - min(2, t.l[k]); ex_hi = i + min(2, p.N - 1 - t.l[k]); }
         int n = 0;
         for (int j = 0; j < p.P; ++j) {
           V3 d;
-          const float r2 = dist2(c, pi, c.s.pos[j], &d);
-          if (r2 < p.rlist_w2 && j != i) {
+          const float r2 = dist2<WRAP>(c, pi, c.s.pos[j], &d);
+          if (r2 < p.rlist_w2 && (j < ex_lo || j > ex_hi)) {
             if (n < p.cap_w) c.s.wl[(size_t)n * p.P + i] = (uint16_t)j;
             ++n;
           }
@@ -205,16 +220,15 @@ __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
     }
   }
   if (p.use_dh) {
-    // one bit per (chargeable, chargeable) pair inside r_cut + skin: fixed size, cannot overflow
+    const int nw = (p.n_chg + 31) >> 5;
     for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
       const float4 pi = c.s.pos[c.s.chg[ci]];
-      const int nw = (p.n_chg + 31) >> 5;
       for (int w = 0; w < nw; ++w) {
         uint32_t m = 0;
         const int hi = min(32, p.n_chg - w * 32);
         for (int b = 0; b < hi; ++b) {
           V3 d;
-          const float r2 = dist2(c, pi, c.s.pos[c.s.chg[w * 32 + b]], &d);
+          const float r2 = dist2<WRAP>(c, pi, c.s.pos[c.s.chg[w * 32 + b]], &d);
           if (r2 < c.rlist_d2) m |= 1u << b;
         }
         if ((ci >> 5) == w) m &= ~(1u << (ci & 31));   // not its own partner
@@ -222,16 +236,58 @@ __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
       }
     }
   }
+}
+
+template <int ITEMS>
+__device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
+  const DevParams &p = c.p;
+  // bounding box of the replica: if extent + list radius + skin < L no listed pair can be closer
+  // through a periodic image than directly, and it stays so until the next rebuild
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i < p.P)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], t.x[k][a]); hi[a] = fmaxf(hi[a], t.x[k][a]); }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+  float *scr = reinterpret_cast<float *>(c.s.red);   // 32 warps x 6 floats fit in the scratch
+  __syncthreads();
+  if (c.lane == 0)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { scr[c.warp * 6 + a] = lo[a]; scr[c.warp * 6 + 3 + a] = hi[a]; }
+  __syncthreads();
+  float ext = 0.f;
+  {
+    const int nwarps = (c.nt + 31) >> 5;
+    for (int a = 0; a < 3; ++a) {
+      float l_ = 3.0e38f, h_ = -3.0e38f;
+      for (int w = 0; w < nwarps; ++w) { l_ = fminf(l_, scr[w * 6 + a]); h_ = fmaxf(h_, scr[w * 6 + 3 + a]); }
+      ext = fmaxf(ext, h_ - l_);
+    }
+  }
+  c.wrap = !(ext + c.rlist_max + p.skin < p.box_l);   // NaN-safe: wraps
+  if (c.wrap) build_rows<ITEMS, true>(c, t); else build_rows<ITEMS, false>(c, t);
+  __syncthreads();   // Debye-Hueckel rows are read by other threads (sub-thread split, MC warp)
   c.rebuilds += 1;
 }
 
 // ---- forces ------------------------------------------------------------------------------------
 // Phase 1 reads s.pos (must be visible), phase 2 gathers the slots.  thermostat: add
 // -gamma v + sqrt(24 gamma kT/dt)(U-1/2) with U from Philox(counter, particle) (E.py:61-63).
-template <int ITEMS>
-__device__ void compute_forces(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsigned long long counter) {
+// Owner-computes scheme for everything that is local to the chain: bead i evaluates bond (i-1,i),
+// angle (i-1,i,i+1), dihedral (i-1,i,i+1,i+2) and the WCA pairs (i-1,i) and (i-1,i+1) once, keeps
+// its own share and hands the partners' shares over through slots A (i-1), B (i+1), C (i+2).
+template <int ITEMS, bool WRAP>
+__device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsigned long long counter) {
   const DevParams &p = c.p;
-  const int NC = p.NC;
+  const int NC = p.NC, S = p.T + 1;
   float *sa = c.s.slot, *sb = c.s.slot + 3 * NC, *sc = c.s.slot + 6 * NC;
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
@@ -240,78 +296,104 @@ __device__ void compute_forces(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsigned 
     if (i < p.P) {
       const float4 pi4 = c.s.pos[i];
       const V3 pi = xyz(pi4);
-      if (i < NC) {
-        const int l = i % p.N;  // index within the chain
-        if (l >= 1) {
-          const V3 pm1 = xyz(c.s.pos[i - 1]);
-          V3 to_prev = {0.f, 0.f, 0.f}, to_next = {0.f, 0.f, 0.f};
-          if (p.bond_kind != CGPE_BOND_NONE) {  // bond (i-1,i): M.py:159-160
-            V3 fb;
-            bond_term(p, pi, pm1, &fb, &c.err);
-            f = f + fb;
-            to_prev = to_prev - fb;
-          }
-          const bool has_angle = p.use_angle && l <= p.N - 2;  // M.py:161-165
-          const bool has_dih = p.use_dih && l <= p.N - 3;      // M.py:166-170
-          if (has_angle || has_dih) {
-            const V3 pp1 = xyz(c.s.pos[i + 1]);
-            if (has_angle) {
-              V3 fl, fm, fr;
-              angle_term(p, pm1, pi, pp1, &fl, &fm, &fr);
-              to_prev = to_prev + fl; f = f + fm; to_next = to_next + fr;
-            }
-            if (has_dih) {
-              const V3 pp2 = xyz(c.s.pos[i + 2]);
-              V3 f1, f2, f3, f4;
-              dihedral_term(p, pm1, pi, pp1, pp2, &f1, &f2, &f3, &f4);
-              to_prev = to_prev + f1; f = f + f2; to_next = to_next + f3;
-              sc[i + 2] = f4.x; sc[NC + i + 2] = f4.y; sc[2 * NC + i + 2] = f4.z;
-            }
-            sb[i + 1] = to_next.x; sb[NC + i + 1] = to_next.y; sb[2 * NC + i + 1] = to_next.z;
-          }
-          sa[i - 1] = to_prev.x; sa[NC + i - 1] = to_prev.y; sa[2 * NC + i - 1] = to_prev.z;
+      const int ti = c.s.type[i];
+      const float4 *tab_i = c.s.tab + ti * S;
+      const int l = t.l[k];
+      if (l >= 1) {
+        const V3 pm1 = xyz(c.s.pos[i - 1]);
+        const int tm1 = c.s.type[i - 1];
+        V3 to_prev = {0.f, 0.f, 0.f}, to_next = {0.f, 0.f, 0.f};
+        const V3 d01 = pi - pm1;
+        if (p.bond_kind != CGPE_BOND_NONE) {  // bond (i-1,i): M.py:159-160
+          V3 fb;
+          bond_term(p, pi, pm1, &fb, &c.err);
+          f = f + fb;
+          to_prev = to_prev - fb;
         }
-      }
-      if (p.use_wca) {
-        const int ti = c.s.type[i];
-        if (ti < p.T) {
-          const int n = c.s.wn[i];
-          for (int e = 0; e < n; ++e) {
-            const int j = c.s.wl[(size_t)e * p.P + i];
-            const int tj = c.s.type[j];
-            V3 d;
-            const float r2 = dist2(c, pi4, c.s.pos[j], &d);
-            const float4 tab = c.s.tab[ti * (p.T + 1) + tj];
-            if (r2 < tab.z) f = f + wca_force_over_r(tab, r2) * d;
+        if (p.use_wca) {                      // WCA of the bonded pair (no exclusions in the reference)
+          const float4 tab = tab_i[tm1];
+          const float r2 = dot(d01, d01);
+          if (r2 < tab.z) {
+            const V3 fw = wca_force_over_r(tab, r2) * d01;
+            f = f + fw;
+            to_prev = to_prev - fw;
           }
+        }
+        const bool has_angle = p.use_angle && l <= p.N - 2;  // M.py:161-165
+        const bool has_dih = p.use_dih && l <= p.N - 3;      // M.py:166-170
+        if (l <= p.N - 2 && (p.use_angle || p.use_dih || p.use_wca)) {
+          const V3 pp1 = xyz(c.s.pos[i + 1]);
+          if (p.use_wca) {                    // WCA of the next-nearest pair (i-1,i+1)
+            const float4 tab = c.s.tab[tm1 * S + c.s.type[i + 1]];
+            const V3 d = pp1 - pm1;
+            const float r2 = dot(d, d);
+            if (r2 < tab.z) {
+              const V3 fw = wca_force_over_r(tab, r2) * d;
+              to_next = to_next + fw;
+              to_prev = to_prev - fw;
+            }
+          }
+          if (has_angle) {
+            V3 fl, fm, fr;
+            angle_term(p, pm1, pi, pp1, &fl, &fm, &fr);
+            to_prev = to_prev + fl; f = f + fm; to_next = to_next + fr;
+          }
+          if (has_dih) {
+            const V3 pp2 = xyz(c.s.pos[i + 2]);
+            V3 f1, f2, f3, f4;
+            dihedral_term(p, pm1, pi, pp1, pp2, &f1, &f2, &f3, &f4);
+            to_prev = to_prev + f1; f = f + f2; to_next = to_next + f3;
+            sc[i + 2] = f4.x; sc[NC + i + 2] = f4.y; sc[2 * NC + i + 2] = f4.z;
+          }
+          sb[i + 1] = to_next.x; sb[NC + i + 1] = to_next.y; sb[2 * NC + i + 1] = to_next.z;
+        }
+        sa[i - 1] = to_prev.x; sa[NC + i - 1] = to_prev.y; sa[2 * NC + i - 1] = to_prev.z;
+      }
+      if (p.use_wca && ti < p.T) {
+        const int n = c.s.wn[i];
+        for (int e = 0; e < n; ++e) {
+          const int j = c.s.wl[(size_t)e * p.P + i];
+          const float4 pj4 = c.s.pos[j];
+          const float4 tab = tab_i[c.s.type[j]];
+          V3 d;
+          const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
+          if (r2 < tab.z) f = f + wca_force_over_r(tab, r2) * d;
         }
       }
     }
     t.f[k][0] = f.x; t.f[k][1] = f.y; t.f[k][2] = f.z;
   }
   if (p.use_dh) {
-    const int nw = (p.n_chg + 31) >> 5;
-    for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
+    // Debye-Hueckel rows: G sub-threads per row, sub-thread g takes the bits b = g (mod G) of every
+    // word, so the backbone neighbours ci+-1, ci+-2, ... of a site land on different sub-threads;
+    // each writes its partial force into its own slot plane (summed in phase 2)
+    const int nw = (p.n_chg + 31) >> 5, G = p.dh_group;
+    for (int idx = c.tid; idx < G * p.n_chg; idx += c.nt) {
+      const int g = idx / p.n_chg, ci = idx - g * p.n_chg;
+      const uint32_t sel = G == 1 ? 0xFFFFFFFFu : G == 2 ? (0x55555555u << g) : G == 3 ? (0x49249249u << g) : (0x11111111u << g);
       const float4 pi4 = c.s.pos[c.s.chg[ci]];
       V3 f = {0.f, 0.f, 0.f};
       if (pi4.w != 0.0f) {
+        const float qi = p.dh_pref * pi4.w;
         for (int w = 0; w < nw; ++w) {
-          uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w];   // listed AND charged
+          uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w] & sel;   // listed AND charged AND mine
           while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
             const float4 pj4 = c.s.pos[c.s.chg[w * 32 + b]];
             V3 d;
-            const float r2 = dist2(c, pi4, pj4, &d);
+            const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
             if (r2 < c.rc2) {
               float fr;
               dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr);
-              f = f + (p.dh_pref * pi4.w * pj4.w * fr) * d;
+              fr *= qi * pj4.w;
+              f.x = fmaf(fr, d.x, f.x); f.y = fmaf(fr, d.y, f.y); f.z = fmaf(fr, d.z, f.z);
             }
           }
         }
       }
-      c.s.fd[ci] = f.x; c.s.fd[p.n_chg + ci] = f.y; c.s.fd[2 * p.n_chg + ci] = f.z;
+      float *fdg = c.s.fd + (size_t)g * 3 * p.n_chg;
+      fdg[ci] = f.x; fdg[p.n_chg + ci] = f.y; fdg[2 * p.n_chg + ci] = f.z;
     }
   }
   __syncthreads();
@@ -321,14 +403,18 @@ __device__ void compute_forces(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsigned 
     const int i = c.tid + k * c.nt;
     if (i < p.P) {
       float fx = t.f[k][0], fy = t.f[k][1], fz = t.f[k][2];
-      if (i < NC) {
+      if (t.l[k] >= 0) {
         fx += sa[i] + sb[i] + sc[i];
         fy += sa[NC + i] + sb[NC + i] + sc[NC + i];
         fz += sa[2 * NC + i] + sb[2 * NC + i] + sc[2 * NC + i];
       }
       if (p.use_dh) {
         const int ci = c.s.cidx[i];
-        if (ci != 0xFFFF) { fx += c.s.fd[ci]; fy += c.s.fd[p.n_chg + ci]; fz += c.s.fd[2 * p.n_chg + ci]; }
+        if (ci != 0xFFFF)
+          for (int g = 0; g < p.dh_group; ++g) {
+            const float *fdg = c.s.fd + (size_t)g * 3 * p.n_chg;
+            fx += fdg[ci]; fy += fdg[p.n_chg + ci]; fz += fdg[2 * p.n_chg + ci];
+          }
       }
       if (thermostat && c.s.type[i] < p.T) {
         const uint4 o = philox4x32_10((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)i, kTagLangevin, k0, k1);
@@ -346,6 +432,12 @@ __device__ void compute_forces(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsigned 
       t.f[k][0] = fx; t.f[k][1] = fy; t.f[k][2] = fz;
     }
   }
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void compute_forces(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsigned long long counter) {
+  if (c.wrap) compute_forces_impl<ITEMS, true>(c, t, thermostat, counter);
+  else compute_forces_impl<ITEMS, false>(c, t, thermostat, counter);
 }
 
 // ---- velocity Verlet + Langevin (R2) ------------------------------------------------------------
@@ -386,15 +478,23 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
 }
 
 // ---- constant-pH trial moves (R1), warp 0 -------------------------------------------------------
+// One trial = pick direction and site from the Philox draw, Delta-E over the site's rows as a
+// warp reduction, Metropolis decision, O(1) swap-remove bookkeeping.  Lanes 0-3 take the chain
+// neighbours i-2..i+2 (they are not in the WCA rows), lanes 4.. the WCA row; for the Debye-Hueckel
+// part lane w first fetches word w of the site's bit row, a ballot finds the non-empty words and
+// lane b then evaluates bit b of each of those: balanced for any list density.
 __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_ctr, long long &accepted,
                          cgpe_trial_record *trace) {
   const DevParams &p = c.p;
   if (c.warp == 0 && n_trials > 0) {
     const DevReaction rx = p.rx[m];
+    const int S = p.T + 1;
     uint16_t *lp = c.s.lp + (size_t)m * p.n_chg, *ld = c.s.ld + (size_t)m * p.n_chg;
     int n_p = c.s.cnt[m * 2], n_d = c.s.cnt[m * 2 + 1];
-    const float arg_fwd = (float)(2.302585092994045684 * (c.g.pH[c.r] - rx.pK));
+    const float arg_fwd = (float)(2.302585092994045684 * (c.g.pH[c.r] - rx.pK)) * kLog2e;
+    const float neg_beta_log2e = -rx.inv_kT * kLog2e;
     const uint32_t k0 = rx.seed, k1 = (uint32_t)(p.replica_offset + c.r);
+    const int nw = (p.n_chg + 31) >> 5;
     long long acc = 0;
     for (int base = 0; base < n_trials; base += 32) {
       const unsigned long long cnt = trial_ctr + (unsigned long long)(base + c.lane);
@@ -417,36 +517,48 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
         const int k = (int)__umulhi(a1, (uint32_t)n_src);
         const int i = src[k];
         const int t_old = fwd ? rx.type_prot : rx.type_deprot, t_new = fwd ? rx.type_deprot : rx.type_prot;
+        // everything that depends only on i is fetched up front
         const float4 pi4 = c.s.pos[i];
+        const int ci = c.s.cidx[i];
+        const int n_w = p.use_wca ? (int)c.s.wn[i] : 0;
+        const bool dh_on = p.use_dh && ci != 0xFFFF;
+        uint32_t row = 0;
+        if (dh_on && c.lane < nw) row = c.s.dbits[(size_t)ci * p.dw + c.lane] & c.s.qmask[c.lane];
         const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = q_new - pi4.w;
         float de = 0.f;
         if (p.use_wca) {
-          const int n = c.s.wn[i];
-          for (int e = c.lane; e < n; e += 32) {
-            const int j = c.s.wl[(size_t)e * p.P + i];
-            const int tj = c.s.type[j];
-            if (tj < p.T) {
+          // partner of this lane: chain neighbours first, then the list row (loop if the row is long)
+          const int l = (p.NC == p.N) ? i : (i < p.NC ? i % p.N : -1);
+          for (int e = c.lane; e < n_w + 4; e += 32) {
+            int j = -1;
+            if (e < 4) {
+              const int off = e < 2 ? e - 2 : e - 1;            // -2,-1,+1,+2
+              if (l >= 0 && l + off >= 0 && l + off < p.N) j = i + off;
+            } else {
+              j = c.s.wl[(size_t)(e - 4) * p.P + i];
+            }
+            if (j >= 0) {
+              const int tj = c.s.type[j];
               V3 d;
-              const float r2 = dist2(c, pi4, c.s.pos[j], &d);
-              float en = 0.f;
-              if (t_new < p.T) en += wca_energy(c.s.tab[t_new * (p.T + 1) + tj], r2);
-              if (t_old < p.T) en -= wca_energy(c.s.tab[t_old * (p.T + 1) + tj], r2);
-              de += en;
+              const float r2 = dist2<true>(c, pi4, c.s.pos[j], &d);
+              if (tj < p.T) {
+                if (t_new < p.T) de += wca_energy(c.s.tab[t_new * S + tj], r2);
+                if (t_old < p.T) de -= wca_energy(c.s.tab[t_old * S + tj], r2);
+              }
             }
           }
         }
-        if (p.use_dh && dq != 0.f) {
-          // lane b looks at bit b of every word of the site's row: balanced for any list density
-          const int ci = c.s.cidx[i];
-          const int nw = (p.n_chg + 31) >> 5;
+        if (dh_on && dq != 0.f) {
+          uint32_t live = __ballot_sync(0xffffffffu, row != 0u);   // non-empty words of the row
           float sum = 0.f;
-          for (int w = 0; w < nw; ++w) {
-            const uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w];
-            if (m == 0u) continue;   // warp-uniform
-            if ((m >> c.lane) & 1u) {
+          while (live) {
+            const int w = __ffs(live) - 1;
+            live &= live - 1;
+            const uint32_t mw = __shfl_sync(0xffffffffu, row, w);
+            if ((mw >> c.lane) & 1u) {
               const float4 pj4 = c.s.pos[c.s.chg[w * 32 + c.lane]];
               V3 d;
-              const float r2 = dist2(c, pi4, pj4, &d);
+              const float r2 = dist2<true>(c, pi4, pj4, &d);
               if (r2 < c.rc2) {
                 float fr;
                 sum = fmaf(pj4.w, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), sum);
@@ -457,8 +569,8 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
         }
         de = warp_sum(de);
         // bf = N_react/(N_prod+1) exp(-dE/kT + nu ln10 (pH-pK))   
-        const float arg = (fwd ? arg_fwd : -arg_fwd) - rx.inv_kT * de;
-        const float bf = ((float)n_src / (float)(n_dst + 1)) * exp2f(arg * kLog2e);
+        const float bf = __fdividef((float)n_src, (float)(n_dst + 1)) *
+                         exp2f(fmaf(neg_beta_log2e, de, fwd ? arg_fwd : -arg_fwd));
         const bool accept = u < bf;
         if (trace && c.lane == 0) {
           cgpe_trial_record rec = {i, -1, (int8_t)(fwd ? 1 : -1), (int8_t)accept, 0, 0, de, bf, u};
@@ -468,8 +580,7 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
           if (c.lane == 0) {
             c.s.type[i] = (unsigned char)t_new;
             c.s.pos[i].w = q_new;
-            if (p.use_dh) {
-              const int ci = c.s.cidx[i];
+            if (dh_on) {
               if (q_new != 0.f) c.s.qmask[ci >> 5] |= 1u << (ci & 31);
               else c.s.qmask[ci >> 5] &= ~(1u << (ci & 31));
             }
@@ -528,6 +639,8 @@ __device__ void init_ctx(Ctx &c) {
   c.rc2 = rc * rc;
   c.neg_kappa_log2e = -c.kappa * kLog2e;
   c.rlist_d2 = (rc + p.skin) * (rc + p.skin);
+  c.rlist_max = fmaxf(p.use_dh ? rc + p.skin : 0.f, p.use_wca ? sqrtf(p.rlist_w2) : 0.f);
+  c.wrap = true;
   c.gamma = c.g.gamma[c.r];
   c.noise_pref = sqrtf(24.0f * c.gamma * c.g.kT[c.r] / p.dt);
   c.err = 0;
@@ -663,10 +776,17 @@ k_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevSta
     if (i < p.P && p.use_wca) {
       const int ti = c.s.type[i];
       const float4 pi4 = c.s.pos[i];
-      for (int e = 0; e < c.s.wn[i]; ++e) {
-        const int j = c.s.wl[(size_t)e * p.P + i];
+      for (int e = -4; e < (int)c.s.wn[i]; ++e) {
+        int j = -1;
+        if (e < 0) {   // the chain neighbours the bonded owner evaluates (directed count, like the rows)
+          const int off = e < -2 ? e + 2 : e + 3;   // -2,-1,+1,+2
+          if (t.l[k] >= 0 && t.l[k] + off >= 0 && t.l[k] + off < p.N) j = i + off;
+        } else {
+          j = c.s.wl[(size_t)e * p.P + i];
+        }
+        if (j < 0) continue;
         V3 d;
-        const float r2 = dist2(c, pi4, c.s.pos[j], &d);
+        const float r2 = dist2<true>(c, pi4, c.s.pos[j], &d);
         nw += 1;
         if (ti < p.T && r2 < c.s.tab[ti * (p.T + 1) + c.s.type[j]].z) nw_in += 1;
       }
@@ -683,7 +803,7 @@ k_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevSta
           const int b = __ffs(m) - 1;
           m &= m - 1;
           V3 d;
-          if (dist2(c, pi4, c.s.pos[c.s.chg[w * 32 + b]], &d) < c.rc2) nd_in += 1;
+          if (dist2<true>(c, pi4, c.s.pos[c.s.chg[w * 32 + b]], &d) < c.rc2) nd_in += 1;
         }
       }
     }

@@ -10,7 +10,7 @@ struct ChainSmem {
   float4 *tab;        // [(T+1)^2] WCA table
   double *red;        // [32][4] block-reduction scratch
   float *slot;        // [3 slots][3][NC] bonded hand-over slots
-  float *fd;          // [3][n_chg] Debye-Hueckel force per chargeable particle
+  float *fd;          // [dh_group][3][n_chg] partial Debye-Hueckel forces per chargeable particle
   int *cnt;           // [n_rx][2] n_prot, n_deprot
   int *flag;          // [4]
   uint16_t *wl;       // [cap_w][P] WCA Verlet list (column per particle)
