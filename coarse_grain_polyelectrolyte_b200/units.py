@@ -69,8 +69,12 @@ def reduce_parameters(temperature, c_acid, c_salt, n_poly, n_mon, n_nh, n_nh2, b
     # box volume so that n_poly*n_mon monomers give c_acid (P.py:271-279)
     box_volume_nm3 = n_poly * n_mon / (AVOGADRO * c_acid) * LITRE_IN_NM3
     box_length_nm = box_volume_nm3 ** (1.0 / 3.0)
-    # P.py:280 truncates with int(), it does not round
-    n_salt = int(c_salt * (box_volume_nm3 / LITRE_IN_NM3) * AVOGADRO)
+    # P.py:280 truncates with int(), it does not round.  The exact value is c_salt/c_acid*n_mon,
+    # often an integer; depending on the order of the unit factors the float lands a few ulp
+    # below it (199.99999999999997) and truncation would then lose an ion pair, so values within
+    # 1e-9 of an integer are snapped to it first.
+    n_salt_float = c_salt * (box_volume_nm3 / LITRE_IN_NM3) * AVOGADRO
+    n_salt = int(n_salt_float * (1.0 + 1e-9))
     kappa_nm = kappa_per_nm(c_salt)
     ru = ReducedUnits(
         kT_joule=kT,

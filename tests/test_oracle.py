@@ -1,0 +1,202 @@
+"""Pins the CPU oracle: Philox known answers, closed-form few-body energies and forces, finite
+differences, the ideal titration curve, list-mode == all-pairs, and the committed golden vectors.
+
+The reference holds no golden vector for this path (its arithmetic is ESPResSo's); these are the
+anchors SURVEY.md §8c lists.  PARITY UNPINNED against ESPResSo itself.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from coarse_grain_polyelectrolyte_b200 import _abi
+from helpers import load, make_workload, random_state
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def few_body_cfg(n, p, **kw):
+    eps, sig, pref, kappa, rc, L = p[:6]
+    base = dict(n_replicas=1, n_beads=n, n_types=1, box_l=L, time_step=1e-3, kappa=kappa, r_cut=rc,
+                dh_prefactor=pref, wca_eps=[[eps]], wca_sig=[[sig]])
+    base.update(kw)
+    return _abi.make_config(**base)
+
+
+def test_philox_known_answers(oracle_mod):
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in kat:
+        assert [int(x) for x in oracle_mod.philox4x32_10(ctr, key)] == want
+
+
+def test_pair_closed_form(oracle_mod):
+    g = np.load(os.path.join(GOLD, "few_body.npz"))
+    p = g["pair_params"]
+    for key in ("pair_x", "pair_pbc_x"):
+        cfg = few_body_cfg(2, p, use_wca=1, use_dh=1, bond_kind=_abi.BOND_HARMONIC, bond_k=p[6], bond_r0=p[7])
+        o = oracle_mod.OracleEngine(cfg)
+        x = g[key].copy()
+        if key == "pair_pbc_x":      # bonds use unfolded coordinates: unfold the partner first
+            cfg2 = few_body_cfg(2, p, use_wca=1, use_dh=1)
+            o = oracle_mod.OracleEngine(cfg2)
+            o.set_state(x.astype(np.float32), None, np.zeros(2, np.uint8))
+            o.set_positions_f64(x[None, :, :3])
+            e = o.energy()[0]
+            np.testing.assert_allclose(e[2], g["pair_energy"][2], rtol=2e-6)
+            np.testing.assert_allclose(e[4], g["pair_energy"][4], rtol=2e-5)
+            continue
+        o.set_state(x.astype(np.float32), None, np.zeros(2, np.uint8))
+        o.set_positions_f64(x[None, :, :3])      # exact coordinates (set_state takes float32)
+        np.testing.assert_allclose(o.energy()[0], g["pair_energy"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(o.forces_f64()[0], g["pair_force"], rtol=1e-5, atol=1e-7)
+
+
+def test_angle_and_dihedral_closed_form(oracle_mod):
+    g = np.load(os.path.join(GOLD, "few_body.npz"))
+    kb, phi0 = g["angle_params"]
+    cfg = _abi.make_config(n_replicas=1, n_beads=3, n_types=1, box_l=40.0, time_step=1e-3, use_angle=1,
+                           angle_k=kb, angle_phi0=phi0)
+    o = oracle_mod.OracleEngine(cfg)
+    o.set_state(g["angle_x"].astype(np.float32), None, np.zeros(3, np.uint8))
+    o.set_positions_f64(g["angle_x"][None, :, :3])
+    np.testing.assert_allclose(o.energy()[0, 3], g["angle_energy"], rtol=1e-6)
+    np.testing.assert_allclose(o.forces_f64()[0], g["angle_force"], rtol=1e-6, atol=1e-9)
+    kd, mult, phase = g["dih_params"]
+    cfg = _abi.make_config(n_replicas=1, n_beads=4, n_types=1, box_l=40.0, time_step=1e-3, use_dihedral=1,
+                           dihedral_k=kd, dihedral_mult=int(mult), dihedral_phase=phase)
+    for key, want in zip(("dih_cis_x", "dih_trans_x", "dih_gauche_x"), g["dih_energy"]):
+        o = oracle_mod.OracleEngine(cfg)
+        o.set_state(g[key].astype(np.float32), None, np.zeros(4, np.uint8))
+        o.set_positions_f64(g[key][None, :, :3])
+        np.testing.assert_allclose(o.energy()[0, 3], want, atol=1e-6)
+        f = o.forces_f64()[0]
+        np.testing.assert_allclose(f.sum(axis=0), 0.0, atol=1e-9)     # momentum
+        np.testing.assert_allclose(f, 0.0, atol=1e-5)                 # cis/trans/gauche are stationary for mult=3, phase=pi
+
+
+@pytest.mark.parametrize("flags", [None, {"USE_FENE": True}, {"USE_DIHEDRAL_POT": False}])
+def test_forces_are_minus_grad_energy(oracle_mod, flags):
+    w = make_workload(40, pH=[8.0], flags=flags)
+    state = random_state(w, seed=4, jitter=0.03)
+    o = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    x0 = o.state_f64()[0][0].copy()
+    F = o.forces_f64()[0]
+    h, worst = 1e-5, 0.0
+    for i in range(0, 40, 3):
+        for k in range(3):
+            xp, xm = x0.copy(), x0.copy()
+            xp[i, k] += h
+            xm[i, k] -= h
+            o.set_positions_f64(xp[None]); ep = o.energy()[0, 0]
+            o.set_positions_f64(xm[None]); em = o.energy()[0, 0]
+            worst = max(worst, abs(-(ep - em) / (2 * h) - F[i, k]) / max(1.0, abs(F[i, k])))
+    assert worst < 1e-6
+    assert np.abs(F.sum(axis=0)).max() < 1e-9 * np.abs(F).max() * 40
+
+
+@pytest.mark.parametrize("name", ["chain_n52.npz", "chain_n100.npz"])
+def test_golden_chain(oracle_mod, name):
+    g = np.load(os.path.join(GOLD, name))
+    w = make_workload(int(g["n_mon"]), pH=[8.0])
+    o = load(oracle_mod.OracleEngine(w.cfg), w, (g["xyzq"], g["vel"], g["type"]))
+    np.testing.assert_allclose(o.energy(), g["energy"], rtol=1e-12)
+    np.testing.assert_allclose(o.forces_f64(), g["forces"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(o.min_dist(), g["min_dist"], rtol=1e-12)
+    rg, ree, _ = o.observables()
+    np.testing.assert_allclose(rg, g["rg"], rtol=1e-12)
+    np.testing.assert_allclose(ree, g["ree"], rtol=1e-12)
+
+
+def test_golden_trial_log(oracle_mod):
+    g = np.load(os.path.join(GOLD, "trials_n100.npz"))
+    w = make_workload(int(g["n_mon"]), pH=[float(g["pH"])])
+    o = load(oracle_mod.OracleEngine(w.cfg), w, (g["xyzq"], g["vel"], g["type"]))
+    rec = o.mc_run(0, g["trace"].shape[1], trace=True)
+    for f in ("particle", "direction", "accepted", "u"):
+        np.testing.assert_array_equal(rec[f], g["trace"][f])
+    np.testing.assert_allclose(rec["delta_e"], g["trace"]["delta_e"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(o.get_state()[2], g["final_type"])
+    assert 0.05 < rec["accepted"].mean() < 0.95
+
+
+def test_ideal_titration_curve(oracle_mod):
+    """Interactions off -> alpha(pH) = 1/(1+10^(pK-pH)), the only closed form the reference
+    carries (utils.py:15-16)."""
+    g = np.load(os.path.join(GOLD, "titration.npz"))
+    pH = g["pH"][::4]
+    w = make_workload(100, pH=pH, flags={"USE_WCA": False, "USE_ELECTROSTATICS": False})
+    o = w.init_engine(oracle_mod.OracleEngine(w.cfg))
+    n1, n2 = w.n_sites
+    sp = o.sample_params(1500, use_md=False, mc_blocks=((0, 5 * n1 + 1), (1, 5 * n2 + 1)))
+    obs, _ = o.sample_loop(sp)
+    obs = obs[:, 100:]
+    alpha = obs[..., 0].mean(axis=1) / n1
+    ideal = g["alpha_pK1"][::4]
+    sem = np.sqrt(ideal * (1 - ideal) / (n1 * obs.shape[1] / 4.0)) + 2e-3
+    assert np.all(np.abs(alpha - ideal) < 5 * sem), (alpha, ideal)
+    np.testing.assert_array_equal(obs[..., 2], obs[..., 0] + obs[..., 1])
+
+
+def test_list_mode_equals_all_pairs(oracle_mod):
+    w = make_workload(120, pH=[7.5, 9.0])
+    state = random_state(w, seed=8, jitter=0.02)
+    a = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    b = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    b.set_list_mode(True, 0.6)
+    np.testing.assert_allclose(a.energy(), b.energy(), rtol=1e-12)
+    np.testing.assert_allclose(a.forces_f64(), b.forces_f64(), rtol=1e-10, atol=1e-10)
+    sp = a.sample_params(15, md_steps_per_burst=40, use_md=True, mc_blocks=((0, 61), (1, 11)), p_burst1=0.7, p_burst2=0.3)
+    oa, _ = a.sample_loop(sp)
+    ob, _ = b.sample_loop(sp)
+    np.testing.assert_array_equal(oa[..., :3], ob[..., :3])
+    np.testing.assert_allclose(oa[..., 3:], ob[..., 3:], rtol=1e-9)
+    assert b.counters()["list_rebuilds"].min() >= 1
+    sa, sb = a.list_stats(), b.list_stats()
+    np.testing.assert_array_equal(sa[:, [1, 3]], sb[:, [1, 3]])   # in-cutoff counts do not depend on the skin
+    assert np.all(sb[:, 0] <= sa[:, 0])                          # skin 0.6 lists are shorter than skin 0.8 ones
+
+
+def test_langevin_thermostat_temperature(oracle_mod):
+    """<T> = 2 E_kin / (3 N) -> kT = 1 (the notebook's T_inst check, NB:234-248)."""
+    w = make_workload(60, pH=[12.0], flags={"USE_ELECTROSTATICS": False})
+    o = w.init_engine(oracle_mod.OracleEngine(w.cfg))
+    o.set_list_mode(True, 0.8)
+    o.md_run(3000)
+    temps = []
+    for _ in range(60):
+        o.md_run(100)
+        temps.append(2.0 * o.energy()[0, 1] / (3 * 60))
+    assert abs(np.mean(temps) - 1.0) < 0.06, np.mean(temps)
+
+
+def test_energy_conservation_without_thermostat(oracle_mod):
+    w = make_workload(40, pH=[12.0])
+    state = random_state(w, seed=2, jitter=0.01, vel_sigma=0.5)
+    o = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    o.set_replica_params(kT=0.0, gamma=0.0)
+    o.md_run(200)                     # let the jitter relax into the stiff bonds first
+    e0 = o.energy()[0, 0]
+    o.md_run(2000)
+    e1 = o.energy()[0, 0]
+    assert abs(e1 - e0) < 2e-3 * abs(e0)
+
+
+def test_sharding_invariance(oracle_mod):
+    pH = np.linspace(6.0, 11.0, 6)
+    w_all = make_workload(50, pH=pH)
+    state = random_state(w_all, seed=31)
+    kw = dict(md_steps_per_burst=10, use_md=True, mc_blocks=((0, 41), (1, 11)), p_burst1=0.7, p_burst2=0.2)
+    e = load(oracle_mod.OracleEngine(w_all.cfg), w_all, state)
+    ref, _ = e.sample_loop(e.sample_params(12, **kw))
+    parts = []
+    for lo in (0, 3):
+        w = make_workload(50, pH=pH[lo:lo + 3], replica_offset=lo)
+        s = load(oracle_mod.OracleEngine(w.cfg), w, tuple(a[lo:lo + 3] for a in state))
+        parts.append(s.sample_loop(s.sample_params(12, **kw))[0])
+    np.testing.assert_array_equal(ref, np.concatenate(parts, axis=0))
