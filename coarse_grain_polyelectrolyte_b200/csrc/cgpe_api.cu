@@ -117,6 +117,7 @@ int upload_wca(cgpe_handle *h) {
   const double rl = rc_max + h->p.skin;
   if (h->cfg.use_wca && rl > 0.5 * h->cfg.box_l) return fail(h, CGPE_ERR_INVALID, "WCA cutoff + skin exceeds box_l/2");
   h->p.rlist_w2 = (float)(rl * rl);
+  h->p.rc_w_max2 = (float)(rc_max * rc_max * (1.0 + 1e-6));
   return CGPE_OK;
 }
 
@@ -146,6 +147,7 @@ int choose_capacities(cgpe_handle *h) {
     p.cap_w = (int)cap;
   }
   if (p.cap_w > (p.P > 1 ? p.P - 1 : 1)) p.cap_w = p.P > 1 ? p.P - 1 : 1;
+  chain_smem_bytes(p);   // final layout -> p.off
   h->launch = chain_launch_shape(p);
   return CGPE_OK;
 }
@@ -336,6 +338,17 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     if (type[k] > p.T) return fail(h, CGPE_ERR_INVALID, "type index %d out of range at particle %zu", (int)type[k], k);
     if (!std::isfinite(xyzq[4 * k]) || !std::isfinite(xyzq[4 * k + 1]) || !std::isfinite(xyzq[4 * k + 2]))
       return fail(h, CGPE_ERR_INVALID, "non-finite coordinate at particle %zu", k);
+  }
+  // the trial moves swap a site between its two default charges (M.py:239-243): a titratable
+  // particle must carry the default charge of its current type
+  for (int m = 0; m < p.n_rx; ++m) {
+    const cgpe_reaction &rx = h->cfg.reactions[m];
+    for (size_t k = 0; k < RP; ++k) {
+      const float want = type[k] == rx.type_prot ? (float)rx.q_prot : type[k] == rx.type_deprot ? (float)rx.q_deprot : xyzq[4 * k + 3];
+      if (xyzq[4 * k + 3] != want)
+        return fail(h, CGPE_ERR_INVALID, "particle %zu of titratable type %d carries charge %g, default_charges says %g",
+                    k % p.P, (int)type[k], xyzq[4 * k + 3], want);
+    }
   }
   // particles that can carry charge: charged now, or of a type a reaction can charge
   unsigned reactive = 0;

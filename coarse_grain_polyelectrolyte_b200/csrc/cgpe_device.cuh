@@ -25,6 +25,12 @@ struct DevReaction {
   double pK;
 };
 
+// Byte offsets of the shared-memory arrays of the replica engine (chain_engine.cu).  They live in
+// the kernel-parameter constant bank, so an address is one add away and no pointer stays in a register.
+struct SmemOff {
+  int pos, tab, red, slot, fd, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, cpos, wrange, wflag, ratio, total;
+};
+
 // Uniform (replica-independent) parameters, passed to kernels by value.
 struct DevParams {
   int R, P, NC, N, T;           // replicas, particles, chain beads (n_chains*N), beads per chain, types
@@ -45,7 +51,9 @@ struct DevParams {
   double dt_d;                  // time step in double for the clock (system.time)
   float skin, half_skin2;       // Verlet skin, (skin/2)^2
   float rlist_w2;               // (max WCA cutoff + skin)^2
+  float rc_w_max2;              // (max WCA cutoff)^2
   float force_cap;              // 0 = off
+  SmemOff off;
   DevReaction rx[kMaxRx];
 };
 
@@ -128,6 +136,12 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return y;
 }
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // WCA (M.py:74-76).  tab = {24 eps, sigma^2, rc^2, eps}.  Returns F/r; r2 must be < tab.z.
 __device__ __forceinline__ float wca_force_over_r(float4 tab, float r2) {
   const float inv_r2 = fast_rcp(r2);
@@ -144,7 +158,7 @@ __device__ __forceinline__ float wca_energy(float4 tab, float r2) {
 // pref*qi*qj factor.  neg_kappa_log2e = -kappa*log2(e).
 __device__ __forceinline__ float dh_energy_unit(float r2, float kappa, float neg_kappa_log2e, float *f_over_r) {
   const float rinv = rsqrtf(r2), r = r2 * rinv;
-  const float e = exp2f(neg_kappa_log2e * r) * rinv;
+  const float e = fast_ex2(neg_kappa_log2e * r) * rinv;
   *f_over_r = e * fmaf(kappa, r, 1.0f) * rinv * rinv;
   return e;
 }

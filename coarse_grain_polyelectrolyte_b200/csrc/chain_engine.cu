@@ -26,50 +26,41 @@ namespace cgpe {
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up (same function on host, for the size, and on device, for the pointers)
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ size_t chain_smem_layout(const DevParams &p, ChainSmem *s, unsigned char *base) {
+// Host: lay the arrays out for the shapes in p and record the offsets in p.off.
+size_t chain_smem_bytes(DevParams &p) {
   size_t o = 0;
   const int TT = (p.T + 1) * (p.T + 1);
-  auto take = [&](size_t bytes, size_t align) { o = align_up(o, align); size_t at = o; o += bytes; return at; };
-  size_t a_pos = take(sizeof(float4) * p.P, 16);
-  size_t a_tab = take(sizeof(float4) * TT, 16);
-  size_t a_red = take(sizeof(double) * 32 * 4, 8);
-  size_t a_slot = take(sizeof(float) * 9 * p.NC, 4);
-  size_t a_fd = take(sizeof(float) * 3 * (size_t)(p.dh_group > 0 ? p.dh_group : 1) * (p.n_chg > 0 ? p.n_chg : 1), 4);
-  size_t a_cnt = take(sizeof(int) * kMaxRx * 2, 4);
-  size_t a_flag = take(sizeof(int) * 4, 4);
-  size_t a_wl = take(sizeof(uint16_t) * (size_t)p.cap_w * p.P, 4);
-  size_t a_db = take(sizeof(uint32_t) * (size_t)p.dw * (p.n_chg > 0 ? p.n_chg : 1), 4);
-  size_t a_qm = take(sizeof(uint32_t) * (size_t)(p.dw > 0 ? p.dw : 1), 4);
-  size_t a_chg = take(sizeof(uint16_t) * (p.n_chg > 0 ? p.n_chg : 1), 2);
-  size_t a_cidx = take(sizeof(uint16_t) * p.P, 2);
-  size_t a_lp = take(sizeof(uint16_t) * (size_t)(p.n_rx > 0 ? p.n_rx : 1) * (p.n_chg > 0 ? p.n_chg : 1), 2);
-  size_t a_ld = take(sizeof(uint16_t) * (size_t)(p.n_rx > 0 ? p.n_rx : 1) * (p.n_chg > 0 ? p.n_chg : 1), 2);
-  size_t a_wn = take((size_t)p.P, 1);
-  size_t a_type = take((size_t)p.P, 1);
-  if (s) {
-    s->pos = reinterpret_cast<float4 *>(base + a_pos);
-    s->tab = reinterpret_cast<float4 *>(base + a_tab);
-    s->red = reinterpret_cast<double *>(base + a_red);
-    s->slot = reinterpret_cast<float *>(base + a_slot);
-    s->fd = reinterpret_cast<float *>(base + a_fd);
-    s->cnt = reinterpret_cast<int *>(base + a_cnt);
-    s->flag = reinterpret_cast<int *>(base + a_flag);
-    s->wl = reinterpret_cast<uint16_t *>(base + a_wl);
-    s->dbits = reinterpret_cast<uint32_t *>(base + a_db);
-    s->qmask = reinterpret_cast<uint32_t *>(base + a_qm);
-    s->chg = reinterpret_cast<uint16_t *>(base + a_chg);
-    s->cidx = reinterpret_cast<uint16_t *>(base + a_cidx);
-    s->lp = reinterpret_cast<uint16_t *>(base + a_lp);
-    s->ld = reinterpret_cast<uint16_t *>(base + a_ld);
-    s->wn = base + a_wn;
-    s->type = base + a_type;
-  }
-  return align_up(o, 16);
+  const size_t n_chg = p.n_chg > 0 ? p.n_chg : 1, n_rx = p.n_rx > 0 ? p.n_rx : 1, grp = p.dh_group > 0 ? p.dh_group : 1;
+  auto take = [&](size_t bytes, size_t align) { o = align_up(o, align); size_t at = o; o += bytes; return (int)at; };
+  SmemOff &f = p.off;
+  f.pos = take(sizeof(float4) * p.P, 16);
+  f.tab = take(sizeof(float4) * TT, 16);
+  f.red = take(sizeof(double) * 32 * 4, 8);
+  f.slot = take(sizeof(float) * 9 * p.NC, 4);
+  f.fd = take(sizeof(float) * 3 * grp * n_chg, 4);
+  f.cnt = take(sizeof(int) * kMaxRx * 2, 4);
+  f.flag = take(sizeof(int) * 4, 4);
+  f.wl = take(sizeof(uint16_t) * (size_t)p.cap_w * p.P, 4);
+  f.db = take(sizeof(uint32_t) * (size_t)(p.dw > 0 ? p.dw : 1) * n_chg, 4);
+  f.qm = take(sizeof(uint32_t) * (size_t)(p.dw > 0 ? p.dw : 1), 4);
+  f.chg = take(sizeof(uint16_t) * n_chg, 2);
+  f.cidx = take(sizeof(uint16_t) * p.P, 2);
+  f.lp = take(sizeof(uint16_t) * n_rx * n_chg, 2);
+  f.ld = take(sizeof(uint16_t) * n_rx * n_chg, 2);
+  f.wn = take((size_t)p.P, 1);
+  f.type = take((size_t)p.P, 1);
+  f.phi = take(sizeof(float) * n_chg, 4);
+  f.wc = take(sizeof(float) * n_chg, 4);
+  f.rxof = take(n_chg, 1);
+  f.cpos = take(sizeof(float4) * n_chg, 16);
+  f.wrange = take(2 * n_chg, 1);
+  f.wflag = take(n_chg, 1);
+  f.ratio = take(sizeof(float) * n_rx * (n_chg + 1), 4);
+  f.total = (int)align_up(o, 16);
+  return (size_t)f.total;
 }
-
-size_t chain_smem_bytes(const DevParams &p) { return chain_smem_layout(p, nullptr, nullptr); }
 
 namespace {
 
@@ -78,6 +69,7 @@ template <int ITEMS>
 struct Thr {
   float x[ITEMS][3], v[ITEMS][3], f[ITEMS][3], ref[ITEMS][3];
   int l[ITEMS];   // index within its chain, -1 for particles that are not chain beads
+  int ci[ITEMS];  // index among the chargeable particles, -1 if the particle can never carry charge
 };
 
 struct Ctx {
@@ -141,7 +133,11 @@ __device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
     if (c.tid == 0) { c.s.cnt[m * 2] = np; c.s.cnt[m * 2 + 1] = nd; }
   }
   __syncthreads();
-  for (int i = c.tid; i < p.n_chg; i += c.nt) c.s.cidx[c.s.chg[i]] = (uint16_t)i;
+  for (int i = c.tid; i < p.n_chg; i += c.nt) {
+    c.s.cidx[c.s.chg[i]] = (uint16_t)i;
+    c.s.cpos[i] = c.s.pos[c.s.chg[i]];
+    c.s.wrange[2 * i] = 0; c.s.wrange[2 * i + 1] = 0;
+  }
   // live mask of the chargeable particles that carry charge right now (the MC warp keeps it current)
   for (int w = c.tid; w < p.dw; w += c.nt) {
     uint32_t m = 0;
@@ -152,6 +148,11 @@ __device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
     c.s.qmask[w] = m;
   }
   __syncthreads();
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    t.ci[k] = (i < p.P && c.s.cidx[i] != 0xFFFF) ? (int)c.s.cidx[i] : -1;
+  }
 }
 
 template <int ITEMS>
@@ -222,18 +223,22 @@ __device__ void build_rows(Ctx &c, Thr<ITEMS> &t) {
   if (p.use_dh) {
     const int nw = (p.n_chg + 31) >> 5;
     for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
-      const float4 pi = c.s.pos[c.s.chg[ci]];
+      const float4 pi = c.s.cpos[ci];
+      int w_lo = nw, w_hi = 0;
       for (int w = 0; w < nw; ++w) {
         uint32_t m = 0;
         const int hi = min(32, p.n_chg - w * 32);
         for (int b = 0; b < hi; ++b) {
           V3 d;
-          const float r2 = dist2<WRAP>(c, pi, c.s.pos[c.s.chg[w * 32 + b]], &d);
+          const float r2 = dist2<WRAP>(c, pi, c.s.cpos[w * 32 + b], &d);
           if (r2 < c.rlist_d2) m |= 1u << b;
         }
         if ((ci >> 5) == w) m &= ~(1u << (ci & 31));   // not its own partner
         c.s.dbits[(size_t)ci * p.dw + w] = m;
+        if (m) { w_lo = min(w_lo, w); w_hi = w + 1; }
       }
+      c.s.wrange[2 * ci] = (unsigned char)min(w_lo, w_hi);   // backbone neighbours cluster in a few words
+      c.s.wrange[2 * ci + 1] = (unsigned char)w_hi;
     }
   }
 }
@@ -367,20 +372,21 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
     // Debye-Hueckel rows: G sub-threads per row, sub-thread g takes the bits b = g (mod G) of every
     // word, so the backbone neighbours ci+-1, ci+-2, ... of a site land on different sub-threads;
     // each writes its partial force into its own slot plane (summed in phase 2)
-    const int nw = (p.n_chg + 31) >> 5, G = p.dh_group;
+    const int G = p.dh_group;
     for (int idx = c.tid; idx < G * p.n_chg; idx += c.nt) {
       const int g = idx / p.n_chg, ci = idx - g * p.n_chg;
       const uint32_t sel = G == 1 ? 0xFFFFFFFFu : G == 2 ? (0x55555555u << g) : G == 3 ? (0x49249249u << g) : (0x11111111u << g);
-      const float4 pi4 = c.s.pos[c.s.chg[ci]];
+      const float4 pi4 = c.s.cpos[ci];
       V3 f = {0.f, 0.f, 0.f};
       if (pi4.w != 0.0f) {
         const float qi = p.dh_pref * pi4.w;
-        for (int w = 0; w < nw; ++w) {
+        const int w_end = c.s.wrange[2 * ci + 1];
+        for (int w = c.s.wrange[2 * ci]; w < w_end; ++w) {
           uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w] & sel;   // listed AND charged AND mine
           while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            const float4 pj4 = c.s.pos[c.s.chg[w * 32 + b]];
+            const float4 pj4 = c.s.cpos[w * 32 + b];
             V3 d;
             const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
             if (r2 < c.rc2) {
@@ -464,6 +470,7 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
         }
         float4 *sp = &c.s.pos[i];
         sp->x = t.x[k][0]; sp->y = t.x[k][1]; sp->z = t.x[k][2];
+        if (t.ci[k] >= 0) { float4 *cp = &c.s.cpos[t.ci[k]]; cp->x = t.x[k][0]; cp->y = t.x[k][1]; cp->z = t.x[k][2]; }
         moved |= !(d2 <= p.half_skin2);  // also true for NaN
       }
     }
@@ -477,24 +484,116 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
   }
 }
 
-// ---- constant-pH trial moves (R1), warp 0 -------------------------------------------------------
-// One trial = pick direction and site from the Philox draw, Delta-E over the site's rows as a
-// warp reduction, Metropolis decision, O(1) swap-remove bookkeeping.  Lanes 0-3 take the chain
-// neighbours i-2..i+2 (they are not in the WCA rows), lanes 4.. the WCA row; for the Debye-Hueckel
-// part lane w first fetches word w of the site's bit row, a ballot finds the non-empty words and
-// lane b then evaluates bit b of each of those: balanced for any list density.
+// ---- constant-pH trial moves (R1) ----------------------------------------------------------------
+// Positions do not move inside a reaction block, so everything a trial needs is cached per
+// chargeable particle by ALL threads (mc_prepare):
+//   phi[ci]    = sum_j q_j exp(-kappa r_ij)/r_ij over the listed, charged partners inside r_cut
+//   wcache[ci] = sum_j WCA(t_deprot, t_j, r_ij) - WCA(t_prot, t_j, r_ij) over chain neighbours + row
+// A trial (warp 0) is then: direction and site from the Philox draw, Delta-E = +-wcache + pref dq phi,
+// Metropolis decision, O(1) swap-remove bookkeeping: a handful of dependent loads.  Only an ACCEPTED
+// flip does lane-parallel work: it adds dq e(r) to phi of every listed partner of the flipped site
+// and refreshes wcache of partners that are themselves titratable.
+
+// WCA type-swap energy of chargeable particle ci (serial over its partners)
+__device__ float wca_swap_energy(const Ctx &c, int ci, bool *titratable_partner = nullptr) {
+  const DevParams &p = c.p;
+  const int m = c.s.rxof[ci];
+  if (titratable_partner) *titratable_partner = false;
+  if (m == 255 || !p.use_wca) return 0.f;
+  const int S = p.T + 1, i = c.s.chg[ci];
+  const int tp = p.rx[m].type_prot, td = p.rx[m].type_deprot;
+  const float4 pi4 = c.s.pos[i];
+  const int l = (p.NC == p.N) ? (i < p.NC ? i : -1) : (i < p.NC ? i % p.N : -1);
+  const int n_w = c.s.wn[i];
+  float e = 0.f;
+  for (int k = 0; k < n_w + 4; ++k) {
+    int j = -1;
+    if (k < 4) {
+      const int off = k < 2 ? k - 2 : k - 1;   // -2,-1,+1,+2: the chain neighbours are not in the rows
+      if (l >= 0 && l + off >= 0 && l + off < p.N) j = i + off;
+    } else {
+      j = c.s.wl[(size_t)(k - 4) * p.P + i];
+    }
+    if (j < 0) continue;
+    const int tj = c.s.type[j];
+    if (tj >= p.T) continue;
+    V3 d;
+    const float r2 = dist2<true>(c, pi4, c.s.pos[j], &d);
+    // a titratable partner inside the largest WCA cutoff: its own cache depends on this particle's type
+    if (titratable_partner && r2 < p.rc_w_max2 && c.s.cidx[j] != 0xFFFF && c.s.rxof[c.s.cidx[j]] != 255)
+      *titratable_partner = true;
+    e += wca_energy(c.s.tab[td * S + tj], r2) - wca_energy(c.s.tab[tp * S + tj], r2);
+  }
+  return e;
+}
+
+// all threads; needs positions, types, rows and qmask current; ends with a barrier
+__device__ void mc_prepare(Ctx &c) {
+  const DevParams &p = c.p;
+  const int G = p.dh_group;
+  if (p.use_dh) {
+    for (int idx = c.tid; idx < G * p.n_chg; idx += c.nt) {
+      const int g = idx / p.n_chg, ci = idx - g * p.n_chg;
+      const uint32_t sel = G == 1 ? 0xFFFFFFFFu : G == 2 ? (0x55555555u << g) : G == 3 ? (0x49249249u << g) : (0x11111111u << g);
+      const float4 pi4 = c.s.cpos[ci];
+      float sum = 0.f;
+      const int w_end = c.s.wrange[2 * ci + 1];
+      for (int w = c.s.wrange[2 * ci]; w < w_end; ++w) {
+        uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w] & sel;
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const float4 pj4 = c.s.cpos[w * 32 + b];
+          V3 d;
+          const float r2 = c.wrap ? dist2<true>(c, pi4, pj4, &d) : dist2<false>(c, pi4, pj4, &d);
+          if (r2 < c.rc2) {
+            float fr;
+            sum = fmaf(pj4.w, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), sum);
+          }
+        }
+      }
+      c.s.fd[(size_t)g * 3 * p.n_chg + ci] = sum;   // the x plane of the force slots doubles as scratch
+    }
+  }
+  for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
+    const int t = c.s.type[c.s.chg[ci]];
+    int m = 255;
+    for (int k = 0; k < p.n_rx; ++k)
+      if (t == p.rx[k].type_prot || t == p.rx[k].type_deprot) m = k;
+    c.s.rxof[ci] = (unsigned char)m;
+  }
+  // N/(N_sites - N + 1) for N = 0..N_sites: the N_react/(N_prod+1) factor without a division per trial
+  for (int m = 0; m < p.n_rx; ++m) {
+    const int n_sites = c.s.cnt[m * 2] + c.s.cnt[m * 2 + 1];
+    for (int n = c.tid; n <= n_sites; n += c.nt)
+      c.s.ratio[(size_t)m * (p.n_chg + 1) + n] = (float)n / (float)(n_sites - n + 1);
+  }
+  __syncthreads();
+  for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
+    float ph = 0.f;
+    if (p.use_dh)
+      for (int g = 0; g < G; ++g) ph += c.s.fd[(size_t)g * 3 * p.n_chg + ci];
+    c.s.phi[ci] = ph;
+    bool flag;
+    c.s.wcache[ci] = wca_swap_energy(c, ci, &flag);
+    c.s.wflag[ci] = flag ? 1 : 0;
+  }
+  __syncthreads();
+}
+
 __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_ctr, long long &accepted,
                          cgpe_trial_record *trace) {
   const DevParams &p = c.p;
   if (c.warp == 0 && n_trials > 0) {
     const DevReaction rx = p.rx[m];
-    const int S = p.T + 1;
     uint16_t *lp = c.s.lp + (size_t)m * p.n_chg, *ld = c.s.ld + (size_t)m * p.n_chg;
     int n_p = c.s.cnt[m * 2], n_d = c.s.cnt[m * 2 + 1];
     const float arg_fwd = (float)(2.302585092994045684 * (c.g.pH[c.r] - rx.pK)) * kLog2e;
     const float neg_beta_log2e = -rx.inv_kT * kLog2e;
+    const float dq_fwd = rx.q_deprot - rx.q_prot, coul_fwd = p.dh_pref * dq_fwd;
     const uint32_t k0 = rx.seed, k1 = (uint32_t)(p.replica_offset + c.r);
     const int nw = (p.n_chg + 31) >> 5;
+    const float *ratio = c.s.ratio + (size_t)m * (p.n_chg + 1);
     long long acc = 0;
     for (int base = 0; base < n_trials; base += 32) {
       const unsigned long long cnt = trial_ctr + (unsigned long long)(base + c.lane);
@@ -516,80 +615,76 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
         }
         const int k = (int)__umulhi(a1, (uint32_t)n_src);
         const int i = src[k];
-        const int t_old = fwd ? rx.type_prot : rx.type_deprot, t_new = fwd ? rx.type_deprot : rx.type_prot;
-        // everything that depends only on i is fetched up front
-        const float4 pi4 = c.s.pos[i];
         const int ci = c.s.cidx[i];
-        const int n_w = p.use_wca ? (int)c.s.wn[i] : 0;
-        const bool dh_on = p.use_dh && ci != 0xFFFF;
-        uint32_t row = 0;
-        if (dh_on && c.lane < nw) row = c.s.dbits[(size_t)ci * p.dw + c.lane] & c.s.qmask[c.lane];
-        const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = q_new - pi4.w;
-        float de = 0.f;
-        if (p.use_wca) {
-          // partner of this lane: chain neighbours first, then the list row (loop if the row is long)
-          const int l = (p.NC == p.N) ? i : (i < p.NC ? i % p.N : -1);
-          for (int e = c.lane; e < n_w + 4; e += 32) {
-            int j = -1;
-            if (e < 4) {
-              const int off = e < 2 ? e - 2 : e - 1;            // -2,-1,+1,+2
-              if (l >= 0 && l + off >= 0 && l + off < p.N) j = i + off;
-            } else {
-              j = c.s.wl[(size_t)(e - 4) * p.P + i];
-            }
-            if (j >= 0) {
-              const int tj = c.s.type[j];
-              V3 d;
-              const float r2 = dist2<true>(c, pi4, c.s.pos[j], &d);
-              if (tj < p.T) {
-                if (t_new < p.T) de += wca_energy(c.s.tab[t_new * S + tj], r2);
-                if (t_old < p.T) de -= wca_energy(c.s.tab[t_old * S + tj], r2);
-              }
-            }
-          }
-        }
-        if (dh_on && dq != 0.f) {
-          uint32_t live = __ballot_sync(0xffffffffu, row != 0u);   // non-empty words of the row
-          float sum = 0.f;
-          while (live) {
-            const int w = __ffs(live) - 1;
-            live &= live - 1;
-            const uint32_t mw = __shfl_sync(0xffffffffu, row, w);
-            if ((mw >> c.lane) & 1u) {
-              const float4 pj4 = c.s.pos[c.s.chg[w * 32 + c.lane]];
-              V3 d;
-              const float r2 = dist2<true>(c, pi4, pj4, &d);
-              if (r2 < c.rc2) {
-                float fr;
-                sum = fmaf(pj4.w, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), sum);
-              }
-            }
-          }
-          de = fmaf(p.dh_pref * dq, sum, de);
-        }
-        de = warp_sum(de);
+        // E_new - E_old of the type/charge swap of site i from the per-site caches
+        float de = c.s.wcache[ci];
+        if (p.use_dh) de = fmaf(coul_fwd, c.s.phi[ci], de);
+        if (!fwd) de = -de;
         // bf = N_react/(N_prod+1) exp(-dE/kT + nu ln10 (pH-pK))   
-        const float bf = __fdividef((float)n_src, (float)(n_dst + 1)) *
-                         exp2f(fmaf(neg_beta_log2e, de, fwd ? arg_fwd : -arg_fwd));
+        const float bf = ratio[n_src] * exp2f(fmaf(neg_beta_log2e, de, fwd ? arg_fwd : -arg_fwd));
         const bool accept = u < bf;
         if (trace && c.lane == 0) {
           cgpe_trial_record rec = {i, -1, (int8_t)(fwd ? 1 : -1), (int8_t)accept, 0, 0, de, bf, u};
           trace[base + tt] = rec;
         }
         if (accept) {
+          const int t_new = fwd ? rx.type_deprot : rx.type_prot;
+          const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = fwd ? dq_fwd : -dq_fwd;
+          const float4 pi4 = c.s.cpos[ci];
+          // the flipped site's row: lane w fetches word w (before the bookkeeping stores)
+          const uint32_t row = (p.use_dh && c.lane < nw) ? c.s.dbits[(size_t)ci * p.dw + c.lane] : 0u;
+          const bool refresh = p.use_wca && c.s.wflag[ci] != 0;
           if (c.lane == 0) {
             c.s.type[i] = (unsigned char)t_new;
             c.s.pos[i].w = q_new;
-            if (dh_on) {
-              if (q_new != 0.f) c.s.qmask[ci >> 5] |= 1u << (ci & 31);
-              else c.s.qmask[ci >> 5] &= ~(1u << (ci & 31));
-            }
+            c.s.cpos[ci].w = q_new;
+            if (q_new != 0.f) c.s.qmask[ci >> 5] |= 1u << (ci & 31);
+            else c.s.qmask[ci >> 5] &= ~(1u << (ci & 31));
             src[k] = src[n_src - 1];
             dst[n_dst] = (uint16_t)i;
           }
           if (fwd) { n_p -= 1; n_d += 1; } else { n_d -= 1; n_p += 1; }
           acc += 1;
+          if (p.use_dh && dq != 0.f) {
+            // phi of every listed partner inside r_cut changes by dq e(r): lane b handles bit b of
+            // each non-empty word
+            uint32_t live = __ballot_sync(0xffffffffu, row != 0u);
+            while (live) {
+              const int w = __ffs(live) - 1;
+              live &= live - 1;
+              const uint32_t mw = __shfl_sync(0xffffffffu, row, w);
+              if ((mw >> c.lane) & 1u) {
+                const int ck = w * 32 + c.lane;
+                V3 d;
+                const float4 pk4 = c.s.cpos[ck];
+                const float r2 = c.wrap ? dist2<true>(c, pi4, pk4, &d) : dist2<false>(c, pi4, pk4, &d);
+                if (r2 < c.rc2) {
+                  float fr;
+                  c.s.phi[ck] = fmaf(dq, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), c.s.phi[ck]);
+                }
+              }
+            }
+          }
           __syncwarp();
+          if (refresh) {
+            // partners of i that are titratable themselves see a new neighbour type: refresh their cache
+            const int l = (p.NC == p.N) ? (i < p.NC ? i : -1) : (i < p.NC ? i % p.N : -1);
+            const int n_w = c.s.wn[i];
+            for (int e = c.lane; e < n_w + 4; e += 32) {
+              int j = -1;
+              if (e < 4) {
+                const int off = e < 2 ? e - 2 : e - 1;
+                if (l >= 0 && l + off >= 0 && l + off < p.N) j = i + off;
+              } else {
+                j = c.s.wl[(size_t)(e - 4) * p.P + i];
+              }
+              if (j >= 0) {
+                const int cj = c.s.cidx[j];
+                if (cj != 0xFFFF && c.s.rxof[cj] != 255) c.s.wcache[cj] = wca_swap_energy(c, cj);
+              }
+            }
+            __syncwarp();
+          }
         }
       }
     }
@@ -649,13 +744,40 @@ __device__ void init_ctx(Ctx &c) {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+__device__ __forceinline__ void bind_smem(const DevParams &p, ChainSmem *s) {
+  const SmemOff &f = p.off;
+  s->pos = reinterpret_cast<float4 *>(smem_raw + f.pos);
+  s->tab = reinterpret_cast<float4 *>(smem_raw + f.tab);
+  s->red = reinterpret_cast<double *>(smem_raw + f.red);
+  s->slot = reinterpret_cast<float *>(smem_raw + f.slot);
+  s->fd = reinterpret_cast<float *>(smem_raw + f.fd);
+  s->cnt = reinterpret_cast<int *>(smem_raw + f.cnt);
+  s->flag = reinterpret_cast<int *>(smem_raw + f.flag);
+  s->wl = reinterpret_cast<uint16_t *>(smem_raw + f.wl);
+  s->dbits = reinterpret_cast<uint32_t *>(smem_raw + f.db);
+  s->qmask = reinterpret_cast<uint32_t *>(smem_raw + f.qm);
+  s->chg = reinterpret_cast<uint16_t *>(smem_raw + f.chg);
+  s->cidx = reinterpret_cast<uint16_t *>(smem_raw + f.cidx);
+  s->lp = reinterpret_cast<uint16_t *>(smem_raw + f.lp);
+  s->ld = reinterpret_cast<uint16_t *>(smem_raw + f.ld);
+  s->wn = smem_raw + f.wn;
+  s->type = smem_raw + f.type;
+  s->phi = reinterpret_cast<float *>(smem_raw + f.phi);
+  s->wcache = reinterpret_cast<float *>(smem_raw + f.wc);
+  s->rxof = smem_raw + f.rxof;
+  s->cpos = reinterpret_cast<float4 *>(smem_raw + f.cpos);
+  s->wrange = smem_raw + f.wrange;
+  s->wflag = smem_raw + f.wflag;
+  s->ratio = reinterpret_cast<float *>(smem_raw + f.ratio);
+}
+
 // ---- kernels -----------------------------------------------------------------------------------
 template <int ITEMS>
 __global__ void __launch_bounds__(1024, 1)
 k_md_run(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, int n_steps) {
   Ctx c{p, g};
   c.r = blockIdx.x;
-  chain_smem_layout(p, &c.s, smem_raw);
+  bind_smem(p, &c.s);
   init_ctx(c);
   Thr<ITEMS> t;
   bool f_valid = g.f_valid[c.r] != 0, lists_valid = false;
@@ -678,7 +800,7 @@ k_steepest_descent(const __grid_constant__ DevParams p, const __grid_constant__ 
                    float f_max, float sd_gamma, float max_disp) {
   Ctx c{p, g};
   c.r = blockIdx.x;
-  chain_smem_layout(p, &c.s, smem_raw);
+  bind_smem(p, &c.s);
   init_ctx(c);
   Thr<ITEMS> t;
   load_state(c, t, false);
@@ -701,6 +823,7 @@ k_steepest_descent(const __grid_constant__ DevParams p, const __grid_constant__ 
         }
         float4 *sp = &c.s.pos[i];
         sp->x = t.x[k][0]; sp->y = t.x[k][1]; sp->z = t.x[k][2];
+        if (t.ci[k] >= 0) { float4 *cp = &c.s.cpos[t.ci[k]]; cp->x = t.x[k][0]; cp->y = t.x[k][1]; cp->z = t.x[k][2]; }
         moved |= !(d2 <= p.half_skin2);
         big |= !(n2 < f_max * f_max);
       }
@@ -721,12 +844,12 @@ k_mc_run(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
          cgpe_trial_record *trace) {
   Ctx c{p, g};
   c.r = blockIdx.x;
-  chain_smem_layout(p, &c.s, smem_raw);
+  bind_smem(p, &c.s);
   init_ctx(c);
   Thr<ITEMS> t;
   load_state(c, t, true);
   build_lists(c, t);
-  __syncthreads();
+  mc_prepare(c);
   unsigned long long trial_ctr = (unsigned long long)g.trials[(size_t)c.r * p.n_rx + m];
   long long accepted = 0;
   mc_block(c, m, n_trials, trial_ctr, accepted, trace ? trace + (size_t)c.r * n_trials : nullptr);
@@ -744,7 +867,7 @@ __global__ void __launch_bounds__(1024, 1)
 k_md_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, float4 *out) {
   Ctx c{p, g};
   c.r = blockIdx.x;
-  chain_smem_layout(p, &c.s, smem_raw);
+  bind_smem(p, &c.s);
   init_ctx(c);
   Thr<ITEMS> t;
   load_state(c, t, false);
@@ -764,7 +887,7 @@ __global__ void __launch_bounds__(1024, 1)
 k_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, double *out) {
   Ctx c{p, g};
   c.r = blockIdx.x;
-  chain_smem_layout(p, &c.s, smem_raw);
+  bind_smem(p, &c.s);
   init_ctx(c);
   Thr<ITEMS> t;
   load_state(c, t, false);
@@ -827,7 +950,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
               float *qdist) {
   Ctx c{p, g};
   c.r = blockIdx.x;
-  chain_smem_layout(p, &c.s, smem_raw);
+  bind_smem(p, &c.s);
   init_ctx(c);
   Thr<ITEMS> t;
   bool f_valid = g.f_valid[c.r] != 0, lists_valid = false;
@@ -861,6 +984,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
         __syncthreads();
       }
     }
+    if (sp.n_mc_blocks > 0) mc_prepare(c);      // per-site caches for this sample's trial moves
     for (int b = 0; b < sp.n_mc_blocks; ++b) {   // E.py:94-95
       const int m = sp.mc_reaction[b];
       mc_block(c, m, sp.mc_trials[b], trial_ctr[m], accepted[m], nullptr);
@@ -916,7 +1040,7 @@ ChainLaunch chain_launch_shape(const DevParams &p) {
   const int per = (p.P + L.items - 1) / L.items;
   L.threads = ((per + 31) / 32) * 32;
   if (L.threads < 32) L.threads = 32;
-  L.smem = chain_smem_bytes(p);
+  L.smem = (size_t)p.off.total;
   return L;
 }
 

@@ -21,6 +21,13 @@ struct ChainSmem {
   uint16_t *lp, *ld;  // [n_rx][n_chg] protonated / deprotonated bookkeeping lists
   unsigned char *wn;        // WCA list lengths
   unsigned char *type;      // [P]
+  float *phi;               // [n_chg] Debye-Hueckel potential sum_j q_j exp(-kappa r)/r at each chargeable particle
+  float *wcache;            // [n_chg] WCA energy change of the type swap prot -> deprot
+  unsigned char *rxof;      // [n_chg] reaction the particle belongs to (255 = none)
+  float4 *cpos;             // [n_chg] x,y,z,q of the chargeable particles, compact (no id indirection)
+  unsigned char *wrange;    // [n_chg][2] first / one-past-last non-empty word of the Debye-Hueckel row
+  unsigned char *wflag;     // [n_chg] 1 if a WCA partner of the particle is titratable itself
+  float *ratio;             // [n_rx][n_chg+1] N/(N_sites - N + 1): the factorial factor of the acceptance
 };
 
 struct ChainLaunch {
@@ -29,7 +36,7 @@ struct ChainLaunch {
   size_t smem;
 };
 
-size_t chain_smem_bytes(const DevParams &p);
+size_t chain_smem_bytes(DevParams &p);   // lays the arrays out, fills p.off, returns the size
 ChainLaunch chain_launch_shape(const DevParams &p);
 
 cudaError_t launch_md_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int n_steps, cudaStream_t st);
