@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_TYPES = 16
 MAX_REACTIONS = 4
 MAX_MC_BLOCKS = 4
@@ -45,7 +45,7 @@ class Config(C.Structure):
         ("dh_prefactor", C.c_double), ("box_l", C.c_double), ("time_step", C.c_double),
         ("skin", C.c_double),
         ("pH", C.c_double), ("kappa", C.c_double), ("r_cut", C.c_double), ("kT", C.c_double),
-        ("gamma", C.c_double),
+        ("gamma", C.c_double), ("dihedral_sin_min", C.c_double),
         ("wca_eps", C.c_double * (MAX_TYPES * MAX_TYPES)),
         ("wca_sig", C.c_double * (MAX_TYPES * MAX_TYPES)),
         ("reactions", Reaction * MAX_REACTIONS),

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -163,6 +164,8 @@ int check_device_errors(cgpe_handle *h) {
   CU(cudaMemsetAsync(h->g.err, 0, sizeof(int) * h->p.R, h->stream));
   if (any & kErrNonFinite) return fail(h, CGPE_ERR_NUMERIC, "non-finite coordinate or velocity (first replica %d)", first);
   if (any & kErrFene) return fail(h, CGPE_ERR_NUMERIC, "FENE bond stretched beyond d_r_max (first replica %d)", first);
+  if (any & kErrDiverged)
+    return fail(h, CGPE_ERR_NUMERIC, "replica %d diverged (a velocity exceeds 1000 sqrt(kT/m)): the integration is unstable, reduce the time step", first);
   return fail(h, CGPE_ERR_CAPACITY, "WCA neighbour list overflow (cap_wca=%d, first replica %d): raise cap_wca or lower skin", h->p.cap_w, first);
 }
 
@@ -228,6 +231,10 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   p.angle_k = (float)cfg->angle_k; p.angle_phi0 = (float)cfg->angle_phi0;
   p.dih_k = (float)cfg->dihedral_k;
   p.dih_cos_phase = (float)std::cos(cfg->dihedral_phase); p.dih_sin_phase = (float)std::sin(cfg->dihedral_phase);
+  {
+    const double smin = cfg->dihedral_sin_min == 0.0 ? 0.02 : (cfg->dihedral_sin_min < 0.0 ? 0.0 : cfg->dihedral_sin_min);
+    p.dih_sin_min2 = (float)(smin * smin);
+  }
   p.dh_pref = (float)cfg->dh_prefactor;
   p.box_l = (float)cfg->box_l; p.inv_box_l = (float)(1.0 / cfg->box_l);
   p.dt = (float)cfg->time_step; p.half_dt = (float)(0.5 * cfg->time_step); p.dt_d = cfg->time_step;
@@ -235,6 +242,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   p.skin = (float)skin; p.half_skin2 = (float)(0.25 * skin * skin);
   p.force_cap = 0.f;
   p.thermostat_seed = 0u;
+  if (const char *dp = std::getenv("CGPE_DENSE_POLICY")) p.dense_policy = std::atoi(dp);   // diagnostics only
   for (int m = 0; m < p.n_rx; ++m) {
     const cgpe_reaction &r = cfg->reactions[m];
     DevReaction &d = p.rx[m];

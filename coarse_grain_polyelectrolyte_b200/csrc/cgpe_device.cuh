@@ -15,7 +15,7 @@ constexpr int kMaxRx = CGPE_MAX_REACTIONS;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // error bits raised by kernels into DevState::err[r]
-enum : int { kErrWcaCap = 1, kErrNonFinite = 4, kErrFene = 8 };
+enum : int { kErrWcaCap = 1, kErrNonFinite = 4, kErrFene = 8, kErrDiverged = 16 };
 
 struct DevReaction {
   int type_prot, type_deprot, type_ion;
@@ -28,7 +28,7 @@ struct DevReaction {
 // Byte offsets of the shared-memory arrays of the replica engine (chain_engine.cu).  They live in
 // the kernel-parameter constant bank, so an address is one add away and no pointer stays in a register.
 struct SmemOff {
-  int pos, tab, red, slot, fd, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, cpos, wrange, wflag, ratio, total;
+  int pos, tab, red, slot, fd, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, cpos, wrange, wflag, ratio, qlist, total;
 };
 
 // Uniform (replica-independent) parameters, passed to kernels by value.
@@ -40,11 +40,12 @@ struct DevParams {
   int cap_w;                    // WCA list row capacity
   int dw;                       // words per row of the Debye-Hueckel bit list (odd: conflict-free)
   int dh_group;                 // sub-threads sharing one Debye-Hueckel row (1..4)
+  int dense_policy;             // 0 = choose per rebuild, 1 = never dense, 2 = always dense (diagnostics)
   int replica_offset;
   uint32_t thermostat_seed;
   float bond_k, bond_r0, fene_drmax2;
   float angle_k, angle_phi0;
-  float dih_k, dih_cos_phase, dih_sin_phase;
+  float dih_k, dih_cos_phase, dih_sin_phase, dih_sin_min2;
   float dh_pref;
   float box_l, inv_box_l;
   float dt, half_dt;
@@ -206,10 +207,12 @@ __device__ __forceinline__ float dihedral_term(const DevParams &p, V3 p1, V3 p2,
   const V3 b1 = p2 - p1, b2 = p3 - p2, b3 = p4 - p3;
   const V3 m = cross(b1, b2), n = cross(b2, b3);
   const float m2 = dot(m, m), n2 = dot(n, n), l2sq = dot(b2, b2);
-  if (m2 < 1e-20f || n2 < 1e-20f) {
+  if (m2 <= 1e-8f || n2 <= 1e-8f) {   // |b1 x b2| <= 1e-4: torsion undefined (ESPResSo's guard)
     *f1 = *f2 = *f3 = *f4 = V3{0.f, 0.f, 0.f};
     return 0.0f;
   }
+  // gradient evaluated with sin(bond angle) >= dihedral_sin_min (see cgpe.h)
+  const float m2g = fmaxf(m2, p.dih_sin_min2 * dot(b1, b1) * l2sq), n2g = fmaxf(n2, p.dih_sin_min2 * dot(b3, b3) * l2sq);
   const float l2 = sqrtf(l2sq), inv_mn = rsqrtf(m2 * n2);
   const float c1 = dot(m, n) * inv_mn, s1 = l2 * dot(b1, n) * inv_mn;   // cos phi, sin phi
   float cm = 1.0f, sm = 0.0f;                                            // cos/sin(mult phi)
@@ -221,8 +224,8 @@ __device__ __forceinline__ float dihedral_term(const DevParams &p, V3 p1, V3 p2,
   const float cos_arg = fmaf(cm, p.dih_cos_phase, sm * p.dih_sin_phase);
   const float sin_arg = fmaf(sm, p.dih_cos_phase, -cm * p.dih_sin_phase);
   const float dedphi = p.dih_k * (float)p.dih_mult * sin_arg;
-  const V3 g1 = (-l2 / m2) * m, g4 = (l2 / n2) * n;   // dphi/dp1, dphi/dp4
-  const float s12 = dot(b1, b2) / l2sq, s32 = dot(b3, b2) / l2sq;
+  const V3 g1 = (-l2 * fast_rcp(m2g)) * m, g4 = (l2 * fast_rcp(n2g)) * n;   // dphi/dp1, dphi/dp4
+  const float inv_l2sq = fast_rcp(l2sq), s12 = dot(b1, b2) * inv_l2sq, s32 = dot(b3, b2) * inv_l2sq;
   const V3 g2 = (-1.0f - s12) * g1 + s32 * g4;
   const V3 g3 = s12 * g1 + (-1.0f - s32) * g4;
   *f1 = (-dedphi) * g1; *f2 = (-dedphi) * g2; *f3 = (-dedphi) * g3; *f4 = (-dedphi) * g4;

@@ -58,6 +58,7 @@ size_t chain_smem_bytes(DevParams &p) {
   f.wrange = take(2 * n_chg, 1);
   f.wflag = take(n_chg, 1);
   f.ratio = take(sizeof(float) * n_rx * (n_chg + 1), 4);
+  f.qlist = take(sizeof(uint16_t) * n_chg, 2);
   f.total = (int)align_up(o, 16);
   return (size_t)f.total;
 }
@@ -80,6 +81,8 @@ struct Ctx {
   int tid, nt, lane, warp;
   float kappa, rc2, neg_kappa_log2e, rlist_d2, rlist_max, gamma, noise_pref;
   bool wrap;          // false: every listed pair is closer directly than through any periodic image
+  bool dense;         // Debye-Hueckel list radius ~ replica extent: loop over all charged particles instead of the bit rows
+  int dh_g0, dh_ci0;  // this thread's first (sub-thread, row) work item of the Debye-Hueckel phase
   int err;            // thread-local error bits, merged at exit
   long long rebuilds; // uniform
 };
@@ -171,9 +174,11 @@ __device__ void store_state(Ctx &c, Thr<ITEMS> &t, bool store_forces) {
       if (store_forces) c.g.frc[base + i] = make_float4(t.f[k][0], t.f[k][1], t.f[k][2], 0.f);
       c.g.type[base + i] = c.s.type[i];
       if (!isfinite(t.x[k][0] + t.x[k][1] + t.x[k][2] + t.v[k][0] + t.v[k][1] + t.v[k][2])) bad = 1;
+      if (t.v[k][0] * t.v[k][0] + t.v[k][1] * t.v[k][1] + t.v[k][2] * t.v[k][2] > 1.0e6f * fmaxf(c.g.kT[c.r], 1.0f)) bad |= 2;
     }
   }
-  if (bad) c.err |= kErrNonFinite;
+  if (bad & 1) c.err |= kErrNonFinite;
+  if (bad & 2) c.err |= kErrDiverged;
   for (int m = 0; m < p.n_rx; ++m) {
     int *gp = c.g.lst_prot + ((size_t)c.r * p.n_rx + m) * p.P;
     int *gd = c.g.lst_deprot + ((size_t)c.r * p.n_rx + m) * p.P;
@@ -278,9 +283,26 @@ __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
     }
   }
   c.wrap = !(ext + c.rlist_max + p.skin < p.box_l);   // NaN-safe: wraps
+  c.dense = p.use_dh && (p.dense_policy == 2 || (p.dense_policy == 0 && c.rlist_d2 >= 0.16f * ext * ext));   // list radius >= 0.4 extent: the rows prune little
   if (c.wrap) build_rows<ITEMS, true>(c, t); else build_rows<ITEMS, false>(c, t);
   __syncthreads();   // Debye-Hueckel rows are read by other threads (sub-thread split, MC warp)
   c.rebuilds += 1;
+}
+
+// Compact list of the chargeable particles that carry charge right now (warp 0; callers put a
+// barrier behind it).  Order = chargeable index, so results do not depend on who built it.
+__device__ void build_qlist(Ctx &c) {
+  const DevParams &p = c.p;
+  if (c.warp == 0) {
+    const int nw = (p.n_chg + 31) >> 5;
+    int base = 0;
+    for (int w = 0; w < nw; ++w) {
+      const uint32_t m = c.s.qmask[w];
+      if ((m >> c.lane) & 1u) c.s.qlist[base + __popc(m & ((1u << c.lane) - 1u))] = (uint16_t)(w * 32 + c.lane);
+      base += __popc(m);
+    }
+    if (c.lane == 0) c.s.flag[0] = base;
+  }
 }
 
 // ---- forces ------------------------------------------------------------------------------------
@@ -374,11 +396,27 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
     // each writes its partial force into its own slot plane (summed in phase 2)
     const int G = p.dh_group;
     for (int idx = c.tid; idx < G * p.n_chg; idx += c.nt) {
-      const int g = idx / p.n_chg, ci = idx - g * p.n_chg;
+      const int g = idx == c.tid ? c.dh_g0 : idx / p.n_chg, ci = idx == c.tid ? c.dh_ci0 : idx - g * p.n_chg;
       const uint32_t sel = G == 1 ? 0xFFFFFFFFu : G == 2 ? (0x55555555u << g) : G == 3 ? (0x49249249u << g) : (0x11111111u << g);
       const float4 pi4 = c.s.cpos[ci];
       V3 f = {0.f, 0.f, 0.f};
-      if (pi4.w != 0.0f) {
+      if (pi4.w != 0.0f && c.dense) {
+        // dense mode: every charged particle is a candidate; sub-thread g takes every G-th one
+        const float qi = p.dh_pref * pi4.w;
+        const int nq = c.s.flag[0];
+        for (int k = g; k < nq; k += G) {
+          const int cj = c.s.qlist[k];
+          const float4 pj4 = c.s.cpos[cj];
+          V3 d;
+          const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
+          if (r2 < c.rc2 && cj != ci) {
+            float fr;
+            dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr);
+            fr *= qi * pj4.w;
+            f.x = fmaf(fr, d.x, f.x); f.y = fmaf(fr, d.y, f.y); f.z = fmaf(fr, d.z, f.z);
+          }
+        }
+      } else if (pi4.w != 0.0f) {
         const float qi = p.dh_pref * pi4.w;
         const int w_end = c.s.wrange[2 * ci + 1];
         for (int w = c.s.wrange[2 * ci]; w < w_end; ++w) {
@@ -453,6 +491,7 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
   const DevParams &p = c.p;
   if (n_steps <= 0) return;
   if (!lists_valid) { build_lists(c, t); lists_valid = true; }
+  if (p.use_dh) { build_qlist(c); __syncthreads(); }   // charges may have changed since the last burst
   if (!f_valid) { compute_forces(c, t, true, counter); f_valid = true; }
   for (int step = 0; step < n_steps; ++step) {
     int moved = 0;
@@ -736,6 +775,9 @@ __device__ void init_ctx(Ctx &c) {
   c.rlist_d2 = (rc + p.skin) * (rc + p.skin);
   c.rlist_max = fmaxf(p.use_dh ? rc + p.skin : 0.f, p.use_wca ? sqrtf(p.rlist_w2) : 0.f);
   c.wrap = true;
+  c.dense = false;
+  c.dh_g0 = p.n_chg > 0 ? c.tid / p.n_chg : 0;
+  c.dh_ci0 = c.tid - c.dh_g0 * p.n_chg;
   c.gamma = c.g.gamma[c.r];
   c.noise_pref = sqrtf(24.0f * c.gamma * c.g.kT[c.r] / p.dt);
   c.err = 0;
@@ -769,6 +811,7 @@ __device__ __forceinline__ void bind_smem(const DevParams &p, ChainSmem *s) {
   s->wrange = smem_raw + f.wrange;
   s->wflag = smem_raw + f.wflag;
   s->ratio = reinterpret_cast<float *>(smem_raw + f.ratio);
+  s->qlist = reinterpret_cast<uint16_t *>(smem_raw + f.qlist);
 }
 
 // ---- kernels -----------------------------------------------------------------------------------
@@ -805,6 +848,7 @@ k_steepest_descent(const __grid_constant__ DevParams p, const __grid_constant__ 
   Thr<ITEMS> t;
   load_state(c, t, false);
   build_lists(c, t);
+  if (p.use_dh) { build_qlist(c); __syncthreads(); }
   compute_forces(c, t, false, 0ull);
   for (int step = 0; step < n_steps; ++step) {
     int moved = 0, big = 0;
@@ -872,6 +916,7 @@ k_md_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
   Thr<ITEMS> t;
   load_state(c, t, false);
   build_lists(c, t);
+  if (p.use_dh) { build_qlist(c); __syncthreads(); }
   compute_forces(c, t, false, 0ull);
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {

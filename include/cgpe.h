@@ -37,7 +37,7 @@ extern "C" {
 #define CGPE_API
 #endif
 
-#define CGPE_ABI_VERSION 3
+#define CGPE_ABI_VERSION 4
 #define CGPE_MAX_TYPES 16     /* interacting particle types (the reference uses 8, M.py:58-76) */
 #define CGPE_MAX_REACTIONS 4  /* reaction objects (the reference uses 2, M.py:211-233)         */
 #define CGPE_MAX_MC_BLOCKS 4  /* MC blocks per sample (the reference uses 2, E.py:94-95)       */
@@ -105,6 +105,12 @@ typedef struct cgpe_config {
                                            ESPResSo's internals); 0 = library default          */
   /* defaults broadcast to every replica; override with cgpe_set_replica_params                */
   double pH, kappa, r_cut, kT, gamma;
+  /* The torsion gradient grows like 1/sin(theta) when a bond angle theta of the quadruple
+     straightens (ESPResSo's expression shares this and only drops the term for |b1 x b2| <= 1e-4).
+     With soft angle terms straight angles are thermally reachable and the force diverges.  The
+     gradient is therefore evaluated with sin(theta) >= dihedral_sin_min.  0 = library default
+     (0.02, i.e. within 1.1 degrees of collinear); negative = ESPResSo's guard only.               */
+  double dihedral_sin_min;
   double wca_eps[CGPE_MAX_TYPES * CGPE_MAX_TYPES]; /* row-major [t1][t2] (M.py:74-76)          */
   double wca_sig[CGPE_MAX_TYPES * CGPE_MAX_TYPES];
   cgpe_reaction reactions[CGPE_MAX_REACTIONS];

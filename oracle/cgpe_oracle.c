@@ -228,14 +228,17 @@ static double dihedral_energy_force(const cgpe_config *c, const double *p1, cons
   cross(b2, b3, n);
   double m2 = dot(m, m), n2 = dot(n, n), l2sq = dot(b2, b2), l2 = sqrt(l2sq);
   for (int k = 0; k < 3; ++k) f1[k] = f2[k] = f3[k] = f4[k] = 0.0;
-  if (m2 < 1e-20 || n2 < 1e-20) return 0.0; /* collinear triple: torsion undefined, no force */
+  if (m2 <= 1e-8 || n2 <= 1e-8) return 0.0; /* |b1 x b2| <= 1e-4: torsion undefined, no force (ESPResSo's guard) */
+  /* gradient evaluated with sin(theta) >= dihedral_sin_min (see cgpe.h) */
+  const double smin = c->dihedral_sin_min == 0.0 ? 0.02 : (c->dihedral_sin_min < 0.0 ? 0.0 : c->dihedral_sin_min);
+  const double m2g = fmax(m2, smin * smin * dot(b1, b1) * l2sq), n2g = fmax(n2, smin * smin * dot(b3, b3) * l2sq);
   double phi = atan2(l2 * dot(b1, n), dot(m, n));
   double arg = c->dihedral_mult * phi - c->dihedral_phase;
   double e = c->dihedral_k * (1.0 - cos(arg));
   double dedphi = c->dihedral_k * c->dihedral_mult * sin(arg);
   /* dphi/dp1 = -|b2|/|m|^2 m ; dphi/dp4 = +|b2|/|n|^2 n */
   double g1[3], g4[3];
-  for (int k = 0; k < 3; ++k) { g1[k] = -l2 / m2 * m[k]; g4[k] = l2 / n2 * n[k]; }
+  for (int k = 0; k < 3; ++k) { g1[k] = -l2 / m2g * m[k]; g4[k] = l2 / n2g * n[k]; }
   double s12 = dot(b1, b2) / l2sq, s32 = dot(b3, b2) / l2sq;
   for (int k = 0; k < 3; ++k) {
     double g2 = -g1[k] - s12 * g1[k] + s32 * g4[k];

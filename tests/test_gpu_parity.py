@@ -256,3 +256,26 @@ def test_invalid_calls_fail_loudly(Engine):
     w.cfg.abi_version = 1
     with pytest.raises(_abi.CgpeError):
         Engine(w.cfg)
+
+
+def test_dihedral_near_straight_angle_matches_oracle_and_divergence_is_reported(Engine, oracle_mod):
+    cfg = _abi.make_config(n_replicas=1, n_beads=4, n_types=1, box_l=40.0, time_step=1e-3, use_dihedral=1,
+                           dihedral_k=6.5, dihedral_mult=3, dihedral_phase=np.pi)
+    x = np.array([[-np.cos(1e-3), np.sin(1e-3), 0, 0], [0, 0, 0, 0], [1, 0, 0, 0],
+                  [1.5, 0.6 * np.cos(0.7), 0.6 * np.sin(0.7), 0]], np.float32) + np.float32([5, 5, 5, 0])
+    g, o = Engine(cfg), oracle_mod.OracleEngine(cfg)
+    for e in (g, o):
+        e.set_state(x, None, np.zeros(4, np.uint8))
+    fo = o.forces_f64()[0]
+    assert np.abs(fo).max() < 1.2e3
+    for fg in (g.forces()[0], g.md_forces()[0]):
+        assert np.abs(fg - fo).max() < 2e-4 * np.abs(fo).max()      # FP32 cross products of nearly parallel bonds
+    # a replica whose velocities ran away is reported, not returned silently
+    v = np.zeros((4, 4), np.float32)
+    v[0, 0] = 5e3
+    g.set_state(x, v, np.zeros(4, np.uint8))
+    g.set_thermostat_seed(1)
+    g.md_run(1)
+    with pytest.raises(_abi.CgpeError) as ei:
+        g.synchronize()
+    assert ei.value.status == _abi.ERR_NUMERIC and "diverged" in str(ei.value)

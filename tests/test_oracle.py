@@ -200,3 +200,24 @@ def test_sharding_invariance(oracle_mod):
         s = load(oracle_mod.OracleEngine(w.cfg), w, tuple(a[lo:lo + 3] for a in state))
         parts.append(s.sample_loop(s.sample_params(12, **kw))[0])
     np.testing.assert_array_equal(ref, np.concatenate(parts, axis=0))
+
+
+def test_dihedral_gradient_is_bounded_near_straight_bond_angles(oracle_mod):
+    """The torsion gradient grows like 1/sin(theta); it is evaluated with sin(theta) >= 0.02 so a
+    thermally reachable straight angle cannot blow the integration up (cgpe.h, dihedral_sin_min).
+    Away from the 1.1 degree cone nothing changes."""
+    def forces(eps_angle, sin_min):
+        cfg = _abi.make_config(n_replicas=1, n_beads=4, n_types=1, box_l=40.0, time_step=1e-3, use_dihedral=1,
+                               dihedral_k=6.5, dihedral_mult=3, dihedral_phase=np.pi, dihedral_sin_min=sin_min)
+        o = oracle_mod.OracleEngine(cfg)
+        # p1-p2-p3 almost collinear (angle pi - eps_angle), p4 out of plane at an oblique torsion
+        x = np.array([[-np.cos(eps_angle), np.sin(eps_angle), 0, 0], [0, 0, 0, 0], [1, 0, 0, 0],
+                      [1.5, 0.6 * np.cos(0.7), 0.6 * np.sin(0.7), 0]], float) + [5, 5, 5, 0]
+        o.set_state(x.astype(np.float32), None, np.zeros(4, np.uint8))
+        o.set_positions_f64(x[None, :, :3])
+        return o.forces_f64()[0]
+    wild, tame = forces(1e-3, -1.0), forces(1e-3, 0.0)
+    assert np.abs(wild).max() > 5e3                      # ESPResSo's expression: ~3k/(l sin theta)
+    assert np.abs(tame).max() < 1.2e3                    # regularised
+    np.testing.assert_allclose(tame.sum(axis=0), 0.0, atol=1e-9)
+    np.testing.assert_allclose(forces(0.3, -1.0), forces(0.3, 0.0), rtol=1e-13)   # outside the cone: identical

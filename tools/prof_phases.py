@@ -34,3 +34,5 @@ if __name__ == "__main__":
     if which in ("all", "d"): run(1000, 128, 2e-2, 4.0, "20mM charged")
     if which in ("all", "e"): run(1000, 128, 2e-2, 12.0, "20mM neutral")
     if which in ("all", "f"): run(1000, 1, 2e-2, 8.0, "single replica")
+    if which in ("g",): run(1000, 128, 1e-3, 3.0, "1mM charged")
+    if which in ("h",): run(1000, 128, 2e-3, 3.0, "2mM charged")
