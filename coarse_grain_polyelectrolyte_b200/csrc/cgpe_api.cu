@@ -8,7 +8,7 @@
 #include <new>
 #include <vector>
 
-#include "chain_engine.cuh"
+#include "wide_engine.cuh"
 
 using namespace cgpe;
 
@@ -17,6 +17,10 @@ struct cgpe_handle {
   DevParams p;
   DevState g;
   ChainLaunch launch;
+  WideState w;          // global-memory engine (replicas beyond the shared-memory engine)
+  bool wide;
+  std::vector<void *> wide_allocs;
+  std::vector<int> chg_host;   // [R][n_chg] chargeable particle ids (host copy)
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
   int device;
@@ -166,13 +170,63 @@ int check_device_errors(cgpe_handle *h) {
   if (any & kErrFene) return fail(h, CGPE_ERR_NUMERIC, "FENE bond stretched beyond d_r_max (first replica %d)", first);
   if (any & kErrDiverged)
     return fail(h, CGPE_ERR_NUMERIC, "replica %d diverged (a velocity exceeds 1000 sqrt(kT/m)): the integration is unstable, reduce the time step", first);
-  return fail(h, CGPE_ERR_CAPACITY, "WCA neighbour list overflow (cap_wca=%d, first replica %d): raise cap_wca or lower skin", h->p.cap_w, first);
+  if (any & kErrDhCap)
+    return fail(h, CGPE_ERR_CAPACITY, "Debye-Hueckel neighbour list overflow (cap_dh=%d, first replica %d): raise cap_dh", h->w.cap_d, first);
+  return fail(h, CGPE_ERR_CAPACITY, "WCA neighbour list overflow (cap_wca=%d, first replica %d): raise cap_wca or lower skin",
+              h->wide ? h->w.cap_w : h->p.cap_w, first);
 }
 
 int require_engine(cgpe_handle *h) {
   if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
-  if (h->launch.items == 0)
-    return fail(h, CGPE_ERR_UNSUPPORTED, "P=%d particles per replica exceed the shared-memory engine (max 2048)", h->p.P);
+  if (h->launch.items == 0 && !h->wide)
+    return fail(h, CGPE_ERR_UNSUPPORTED, "P=%d particles per replica: no engine available", h->p.P);
+  return CGPE_OK;
+}
+
+void free_wide(cgpe_handle *h) {
+  for (void *ptr : h->wide_allocs) cudaFree(ptr);
+  h->wide_allocs.clear();
+  h->wide = false;
+}
+
+// arrays of the global-memory engine, sized for the current shapes
+int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
+  free_wide(h);
+  const DevParams &p = h->p;
+  WideState &w = h->w;
+  std::memset(&w, 0, sizeof(w));
+  w.cap_w = h->cfg.cap_wca > 0 ? h->cfg.cap_wca : 64;
+  if (h->cfg.cap_dh > 0) w.cap_d = h->cfg.cap_dh;
+  else {
+    // HBM is plentiful (180 GB) and rows cost only what they hold: size them for compact starts
+    int cap = (int)(256 + 24.0 * (h->cfg.r_cut + p.skin));
+    w.cap_d = (cap + 7) / 8 * 8;
+  }
+  if (w.cap_d > (p.n_chg > 1 ? p.n_chg - 1 : 1)) w.cap_d = p.n_chg > 1 ? p.n_chg - 1 : 1;
+  const size_t RP = (size_t)p.R * p.P, RC = (size_t)p.R * (p.n_chg > 0 ? p.n_chg : 1);
+  auto alloc = [&](void **ptr, size_t bytes) {
+    cudaError_t e = cudaMalloc(ptr, bytes > 0 ? bytes : 1);
+    if (e == cudaSuccess) { h->wide_allocs.push_back(*ptr); e = cudaMemset(*ptr, 0, bytes > 0 ? bytes : 1); }
+    return e;
+  };
+  CU(alloc((void **)&w.ref, sizeof(float4) * RP));
+  CU(alloc((void **)&w.wl, sizeof(uint32_t) * RP * w.cap_w));
+  CU(alloc((void **)&w.wn, sizeof(int) * RP));
+  CU(alloc((void **)&w.dl, sizeof(uint32_t) * RC * w.cap_d));
+  CU(alloc((void **)&w.dn, sizeof(int) * RC));
+  CU(alloc((void **)&w.cidx, sizeof(int) * RP));
+  CU(alloc((void **)&w.flag, sizeof(int) * p.R));
+  CU(alloc((void **)&w.nsteps, sizeof(int) * p.R));
+  CU(alloc((void **)&w.sched_max, sizeof(int)));
+  CU(alloc((void **)&w.phi, sizeof(float) * RC));
+  CU(alloc((void **)&w.wcache, sizeof(float) * RC));
+  CU(alloc((void **)&w.rxof, RC));
+  CU(alloc((void **)&w.wflag, RC));
+  std::vector<int> cidx(RP, -1);
+  for (int r = 0; r < p.R; ++r)
+    for (int c = 0; c < p.n_chg; ++c) cidx[(size_t)r * p.P + chg_packed[(size_t)r * p.n_chg + c]] = c;
+  CU(cudaMemcpy(w.cidx, cidx.data(), sizeof(int) * RP, cudaMemcpyHostToDevice));
+  h->wide = true;
   return CGPE_OK;
 }
 
@@ -238,7 +292,9 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   p.dh_pref = (float)cfg->dh_prefactor;
   p.box_l = (float)cfg->box_l; p.inv_box_l = (float)(1.0 / cfg->box_l);
   p.dt = (float)cfg->time_step; p.half_dt = (float)(0.5 * cfg->time_step); p.dt_d = cfg->time_step;
-  const double skin = cfg->skin > 0.0 ? cfg->skin : 0.8;
+  // default Verlet skin: 0.8 for the shared-memory engine; 2.0 for the global-memory engine, whose
+  // all-pairs list build is the expensive part of a step (fewer, longer-lived lists)
+  const double skin = cfg->skin > 0.0 ? cfg->skin : (p.P > 2048 ? 2.0 : 0.8);
   p.skin = (float)skin; p.half_skin2 = (float)(0.25 * skin * skin);
   p.force_cap = 0.f;
   p.thermostat_seed = 0u;
@@ -299,6 +355,7 @@ void cgpe_destroy(cgpe_handle *h) {
   DeviceGuard guard(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   for (void *ptr : h->allocs) cudaFree(ptr);
+  for (void *ptr : h->wide_allocs) cudaFree(ptr);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_qdist) cudaFree(h->d_qdist);
   if (h->d_trace) cudaFree(h->d_trace);
@@ -376,6 +433,7 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
   for (int r = 0; r < p.R; ++r)
     for (int i = 0; i < n_chg; ++i) chg_packed[(size_t)r * n_chg + i] = chg[(size_t)r * p.P + i];
   p.n_chg = n_chg;
+  h->chg_host = chg_packed;
   {
     int rc_cap = choose_capacities(h);
     if (rc_cap) return rc_cap;
@@ -383,9 +441,13 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
   if (h->launch.items != 0) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, h->device));
-    if (h->launch.smem > (size_t)prop.sharedMemPerBlockOptin)
-      return fail(h, CGPE_ERR_UNSUPPORTED, "replica needs %zu B of shared memory, device offers %zu B per block",
-                  h->launch.smem, (size_t)prop.sharedMemPerBlockOptin);
+    if (h->launch.smem > (size_t)prop.sharedMemPerBlockOptin) h->launch.items = 0;   // -> global-memory engine
+  }
+  if (h->launch.items == 0) {
+    int rc_w = ensure_wide(h, chg_packed);
+    if (rc_w) return rc_w;
+  } else {
+    free_wide(h);
   }
   // bookkeeping lists in particle-id order
   const size_t nrx = p.n_rx > 0 ? p.n_rx : 1;
@@ -448,10 +510,15 @@ int cgpe_set_replica_params(cgpe_handle *h, const double *pH, const double *kapp
         return fail(h, CGPE_ERR_INVALID, "r_cut + skin must lie in (0, box_l/2] (replica %d: %g)", r, r_cut[r]);
       rc_max = std::fmax(rc_max, r_cut[r]);
     }
+    const bool grew = rc_max > h->cfg.r_cut;
     h->cfg.r_cut = rc_max;
     if (h->have_state) {
       int rc_cap = choose_capacities(h);
       if (rc_cap) return rc_cap;
+      if (h->wide && grew && h->cfg.cap_dh <= 0) {   // longer rows are needed
+        rc_cap = ensure_wide(h, h->chg_host);
+        if (rc_cap) return rc_cap;
+      }
     }
     CU(up(h->g.rcut, r_cut));
   }
@@ -529,8 +596,10 @@ int cgpe_md_run(cgpe_handle *h, int32_t n_steps) {
   if (rc) return rc;
   DeviceGuard guard(h->device);
   begin_timing(h);
-  CU(launch_md_run(h->p, h->g, h->launch, n_steps, h->stream));
-  end_timing(h, 1);
+  int launches = 1;
+  if (h->wide) { launches = 0; CU(wide_md_run(h->p, h->g, h->w, n_steps, h->stream, &launches)); }
+  else CU(launch_md_run(h->p, h->g, h->launch, n_steps, h->stream));
+  end_timing(h, launches);
   return CGPE_OK;
 }
 
@@ -542,8 +611,10 @@ int cgpe_steepest_descent(cgpe_handle *h, int32_t n_steps, double f_max, double 
   if (rc) return rc;
   DeviceGuard guard(h->device);
   begin_timing(h);
-  CU(launch_steepest_descent(h->p, h->g, h->launch, n_steps, (float)f_max, (float)gamma, (float)max_displacement, h->stream));
-  end_timing(h, 1);
+  int launches = 1;
+  if (h->wide) { launches = 0; CU(wide_steepest_descent(h->p, h->g, h->w, n_steps, (float)f_max, (float)gamma, (float)max_displacement, h->stream, &launches)); }
+  else CU(launch_steepest_descent(h->p, h->g, h->launch, n_steps, (float)f_max, (float)gamma, (float)max_displacement, h->stream));
+  end_timing(h, launches);
   return CGPE_OK;
 }
 
@@ -566,8 +637,10 @@ int cgpe_mc_run(cgpe_handle *h, int32_t reaction_id, int32_t n_trials, cgpe_tria
     d_trace = h->d_trace;
   }
   begin_timing(h);
-  CU(launch_mc_run(h->p, h->g, h->launch, reaction_id, n_trials, d_trace, h->stream));
-  end_timing(h, 1);
+  int launches = 1;
+  if (h->wide) { launches = 0; CU(wide_mc_run(h->p, h->g, h->w, reaction_id, n_trials, d_trace, h->stream, &launches)); }
+  else CU(launch_mc_run(h->p, h->g, h->launch, reaction_id, n_trials, d_trace, h->stream));
+  end_timing(h, launches);
   if (d_trace) {
     CU(cudaMemcpyAsync(trace, d_trace, sizeof(cgpe_trial_record) * n_rec, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -605,9 +678,16 @@ int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp) {
   if (n_q > 0) CU(cudaMemsetAsync(h->d_qdist, 0, sizeof(float) * n_q, h->stream));
   h->last_ns = sp->n_samples; h->last_qrows = rows;
   begin_timing(h);
-  CU(launch_sample_loop(h->p, h->g, h->launch, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
-                        h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
-  end_timing(h, 1);
+  int launches = 1;
+  if (h->wide) {
+    launches = 0;
+    CU(wide_sample_loop(h->p, h->g, h->w, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
+                        h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->d_tmp_d, h->d_tmp_i, h->stream, &launches));
+  } else {
+    CU(launch_sample_loop(h->p, h->g, h->launch, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
+                          h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
+  }
+  end_timing(h, launches);
   return CGPE_OK;
 }
 
@@ -657,7 +737,8 @@ int cgpe_md_forces(cgpe_handle *h, float *out) {
   int rc = require_engine(h);
   if (rc) return rc;
   DeviceGuard guard(h->device);
-  CU(launch_md_forces(h->p, h->g, h->launch, h->d_tmp_f4, h->stream));
+  if (h->wide) CU(wide_md_forces(h->p, h->g, h->w, h->d_tmp_f4, h->stream));
+  else CU(launch_md_forces(h->p, h->g, h->launch, h->d_tmp_f4, h->stream));
   CU(cudaMemcpyAsync(out, h->d_tmp_f4, sizeof(float4) * (size_t)h->p.R * h->p.P, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return check_device_errors(h);
@@ -706,7 +787,8 @@ int cgpe_list_stats(cgpe_handle *h, double *out) {
   int rc = require_engine(h);
   if (rc) return rc;
   DeviceGuard guard(h->device);
-  CU(launch_list_stats(h->p, h->g, h->launch, h->d_tmp_d, h->stream));
+  if (h->wide) CU(wide_list_stats(h->p, h->g, h->w, h->d_tmp_d, h->stream));
+  else CU(launch_list_stats(h->p, h->g, h->launch, h->d_tmp_d, h->stream));
   CU(cudaMemcpyAsync(out, h->d_tmp_d, sizeof(double) * h->p.R * 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return check_device_errors(h);

@@ -15,7 +15,7 @@ constexpr int kMaxRx = CGPE_MAX_REACTIONS;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // error bits raised by kernels into DevState::err[r]
-enum : int { kErrWcaCap = 1, kErrNonFinite = 4, kErrFene = 8, kErrDiverged = 16 };
+enum : int { kErrWcaCap = 1, kErrDhCap = 2, kErrNonFinite = 4, kErrFene = 8, kErrDiverged = 16 };
 
 struct DevReaction {
   int type_prot, type_deprot, type_ion;

@@ -91,7 +91,8 @@ typedef struct cgpe_config {
   int32_t use_dh;         /* electrostatics.DH (M.py:97-107)                                   */
   int32_t n_reactions;
   int32_t cap_wca;        /* WCA neighbour-list row capacity, 0 = library default              */
-  int32_t cap_dh;         /* unused (the Debye-Hueckel list is a fixed-size bit matrix)        */
+  int32_t cap_dh;         /* Debye-Hueckel row capacity of the large-replica engine (P > 2048);
+                             the shared-memory engine keeps a fixed-size bit matrix instead    */
   int32_t device;         /* CUDA ordinal, -1 = current device                                 */
   int32_t reserved0;
   double bond_k, bond_r0, fene_drmax;   /* M.py:35-39                                          */

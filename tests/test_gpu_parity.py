@@ -37,6 +37,7 @@ def _pair(Engine, oracle_mod, w, state):
     (100, {"USE_ELECTROSTATICS": False}),
     (1000, None),
     (1500, None),
+    (2500, None),      # beyond the shared-memory engine: global-memory (wide) engine
 ])
 def test_energy_and_forces_match_oracle(Engine, oracle_mod, n_mon, flags):
     w = make_workload(n_mon, pH=[6.0, 8.0, 10.0], flags=flags)
@@ -59,7 +60,7 @@ def test_energy_and_forces_match_oracle(Engine, oracle_mod, n_mon, flags):
     np.testing.assert_array_equal(cnt_g, cnt_o)
 
 
-@pytest.mark.parametrize("n_mon,n_trials", [(50, 4000), (100, 6000), (1000, 20000)])
+@pytest.mark.parametrize("n_mon,n_trials", [(50, 4000), (100, 6000), (1000, 20000), (2500, 6000)])
 def test_mc_bookkeeping_bit_exact(Engine, oracle_mod, n_mon, n_trials):
     """Same Philox proposal stream on both sides -> identical sites, directions, decisions,
     types and charges; Delta-E within 1e-5 of the FP64 value.  A decision may differ only on a
@@ -92,7 +93,7 @@ def test_mc_bookkeeping_bit_exact(Engine, oracle_mod, n_mon, n_trials):
     np.testing.assert_array_equal(g.observables()[2], o.observables()[2])
 
 
-@pytest.mark.parametrize("n_mon", [50, 100, 1000])
+@pytest.mark.parametrize("n_mon", [50, 100, 1000, 2500])
 def test_md_steps_match_oracle(Engine, oracle_mod, n_mon):
     """One velocity-Verlet + Langevin step is a deterministic map given the Philox noise; FP32
     vs FP64 differ by rounding only.  The gap then grows with the Lyapunov exponent."""
@@ -279,3 +280,31 @@ def test_dihedral_near_straight_angle_matches_oracle_and_divergence_is_reported(
     with pytest.raises(_abi.CgpeError) as ei:
         g.synchronize()
     assert ei.value.status == _abi.ERR_NUMERIC and "diverged" in str(ei.value)
+
+
+def test_wide_engine_sample_loop_and_steepest_descent(Engine, oracle_mod):
+    """Replicas above 2048 particles run on the global-memory engine: same Markov chain."""
+    w = make_workload(2100, pH=[8.0, 9.5])
+    state = random_state(w, seed=77, jitter=0.02)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    o.set_list_mode(True, 0.8)
+    sp = g.sample_params(6, md_steps_per_burst=5, use_md=True, mc_blocks=((0, 301), (1, 11)), q_snapshot_every=4,
+                         q_snapshot_rows=2, p_burst1=0.7, p_burst2=0.3)
+    og, qg = g.sample_loop(sp)
+    oo, qo = o.sample_loop(sp)
+    np.testing.assert_array_equal(og[..., :3], oo[..., :3])
+    np.testing.assert_allclose(og[..., 3:5], oo[..., 3:5], rtol=2e-4)
+    np.testing.assert_allclose(og[..., 5], oo[..., 5], rtol=1e-9)
+    np.testing.assert_array_equal(qg, qo)
+    cg, co = g.counters(), o.counters()
+    for k in ("md_steps", "trials", "accepted"):
+        np.testing.assert_array_equal(cg[k], co[k])
+    g2, o2 = _pair(Engine, oracle_mod, w, state)
+    for e in (g2, o2):
+        e.steepest_descent(10, f_max=0.0, gamma=1e-4, max_displacement=0.01)
+    dx = np.abs(g2.get_state()[0][..., :3] - o2.state_f64()[0])
+    # FP32 coordinates at |x| ~ 100 (ulp 7.6e-6), ten clamped steps; a bead next to a nearly straight
+    # bond angle is more sensitive, hence the looser bound on the maximum
+    assert np.median(dx) < 2e-5 and np.percentile(dx, 99.9) < 1e-4 and dx.max() < 2e-3
+    s = g.list_stats()
+    assert np.all(s[:, 0] > 0) and np.all(s[:, 1] <= s[:, 0]) and np.all(s[:, 3] <= s[:, 2])
