@@ -93,7 +93,7 @@ struct orc_handle {
      summation order).  Full rows: wl row i holds every j within rc_wca_max+skin, dl row i (only
      chargeable i) every chargeable j within r_cut+skin. */
   int use_lists; double skin;
-  int *wl, *wn, *dl, *dn; int cap_wl, cap_dl;   /* [R][P][cap], [R][P] */
+  int **wl, **wn, **dl, **dn; int *cap_wl, *cap_dl;   /* per replica: [P][cap], [P]; rows grow on demand */
   double *ref;                                  /* [R][P][3] positions at the last build */
   int *lists_valid;                             /* [R] */
   uint8_t *chargeable;                          /* [R][P] */
@@ -333,28 +333,34 @@ static void build_lists(orc_handle *h, int r) {
   const double L = h->cfg.box_l;
   const double rw = wca_rc_max(h) + h->skin, rw2 = rw * rw;
   const double rd = h->rcut[r] + h->skin, rd2 = rd * rd;
-  int *wl = h->wl + (size_t)r * P * h->cap_wl, *wn = h->wn + (size_t)r * P;
-  int *dl = h->dl + (size_t)r * P * h->cap_dl, *dn = h->dn + (size_t)r * P;
   const uint8_t *chg = h->chargeable + (size_t)r * P;
-  memset(wn, 0, sizeof(int) * P);
-  memset(dn, 0, sizeof(int) * P);
-  for (int i = 0; i < P; ++i) {
-    const double *xi = X(h, r, i);
-    for (int j = i + 1; j < P; ++j) {
-      const double *xj = X(h, r, j);
-      double d0 = min_image(xi[0] - xj[0], L), d1 = min_image(xi[1] - xj[1], L), d2 = min_image(xi[2] - xj[2], L);
-      double r2 = d0 * d0 + d1 * d1 + d2 * d2;
-      if (h->cfg.use_wca && r2 < rw2) {
-        if (wn[i] >= h->cap_wl || wn[j] >= h->cap_wl) { fprintf(stderr, "oracle: WCA list overflow\n"); abort(); }
-        wl[(size_t)i * h->cap_wl + wn[i]++] = j;
-        wl[(size_t)j * h->cap_wl + wn[j]++] = i;
-      }
-      if (h->cfg.use_dh && chg[i] && chg[j] && r2 < rd2) {
-        if (dn[i] >= h->cap_dl || dn[j] >= h->cap_dl) { fprintf(stderr, "oracle: DH list overflow\n"); abort(); }
-        dl[(size_t)i * h->cap_dl + dn[i]++] = j;
-        dl[(size_t)j * h->cap_dl + dn[j]++] = i;
+  for (;;) {   /* restart with longer rows when one overflows */
+    int *wl = h->wl[r], *wn = h->wn[r], *dl = h->dl[r], *dn = h->dn[r];
+    const int cw = h->cap_wl[r], cd = h->cap_dl[r];
+    int overflow_w = 0, overflow_d = 0;
+    memset(wn, 0, sizeof(int) * P);
+    memset(dn, 0, sizeof(int) * P);
+    for (int i = 0; i < P && !overflow_w && !overflow_d; ++i) {
+      const double *xi = X(h, r, i);
+      for (int j = i + 1; j < P; ++j) {
+        const double *xj = X(h, r, j);
+        double d0 = min_image(xi[0] - xj[0], L), d1 = min_image(xi[1] - xj[1], L), d2 = min_image(xi[2] - xj[2], L);
+        double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+        if (h->cfg.use_wca && r2 < rw2) {
+          if (wn[i] >= cw || wn[j] >= cw) { overflow_w = 1; break; }
+          wl[(size_t)i * cw + wn[i]++] = j;
+          wl[(size_t)j * cw + wn[j]++] = i;
+        }
+        if (h->cfg.use_dh && chg[i] && chg[j] && r2 < rd2) {
+          if (dn[i] >= cd || dn[j] >= cd) { overflow_d = 1; break; }
+          dl[(size_t)i * cd + dn[i]++] = j;
+          dl[(size_t)j * cd + dn[j]++] = i;
+        }
       }
     }
+    if (!overflow_w && !overflow_d) break;
+    if (overflow_w) { h->cap_wl[r] *= 2; free(h->wl[r]); h->wl[r] = malloc(sizeof(int) * (size_t)P * h->cap_wl[r]); }
+    if (overflow_d) { h->cap_dl[r] *= 2; free(h->dl[r]); h->dl[r] = malloc(sizeof(int) * (size_t)P * h->cap_dl[r]); }
   }
   memcpy(h->ref + (size_t)r * P * 3, h->x + (size_t)r * P * 3, sizeof(double) * 3 * P);
   h->lists_valid[r] = 1;
@@ -379,14 +385,14 @@ static void nonbonded_listed(orc_handle *h, int r, double *f, double e[3]) {
   const double *q = h->q + (size_t)r * P;
   const double L = c->box_l;
   ensure_lists(h, r);
-  const int *wl = h->wl + (size_t)r * P * h->cap_wl, *wn = h->wn + (size_t)r * P;
-  const int *dl = h->dl + (size_t)r * P * h->cap_dl, *dn = h->dn + (size_t)r * P;
+  const int *wl = h->wl[r], *wn = h->wn[r], *dl = h->dl[r], *dn = h->dn[r];
+  const int cw = h->cap_wl[r], cd = h->cap_dl[r];
   for (int i = 0; i < P; ++i) {
     if (ty[i] >= T) continue;
     const double *xi = X(h, r, i);
     if (c->use_wca)
       for (int k = 0; k < wn[i]; ++k) {
-        const int j = wl[(size_t)i * h->cap_wl + k];
+        const int j = wl[(size_t)i * cw + k];
         if (j < i || ty[j] >= T) continue;
         const double *xj = X(h, r, j);
         double d[3] = {min_image(xi[0] - xj[0], L), min_image(xi[1] - xj[1], L), min_image(xi[2] - xj[2], L)};
@@ -396,7 +402,7 @@ static void nonbonded_listed(orc_handle *h, int r, double *f, double e[3]) {
       }
     if (c->use_dh && q[i] != 0.0)
       for (int k = 0; k < dn[i]; ++k) {
-        const int j = dl[(size_t)i * h->cap_dl + k];
+        const int j = dl[(size_t)i * cd + k];
         if (j < i || ty[j] >= T || q[j] == 0.0) continue;
         const double *xj = X(h, r, j);
         double d[3] = {min_image(xi[0] - xj[0], L), min_image(xi[1] - xj[1], L), min_image(xi[2] - xj[2], L)};
@@ -453,7 +459,7 @@ int orc_create(const cgpe_config *cfg, orc_handle **out) {
     h->kT[r] = cfg->kT; h->gamma[r] = cfg->gamma;
   }
   h->thermostat_seed = 0;
-  h->use_lists = 0; h->skin = 0.8; h->cap_wl = 96; h->cap_dl = 256;
+  h->use_lists = 0; h->skin = 0.8;
   h->lists_valid = calloc(h->R, sizeof(int));
   h->rebuilds = calloc(h->R, sizeof(int64_t));
   h->chargeable = calloc(RP, 1);
@@ -469,7 +475,9 @@ void orc_destroy(orc_handle *h) {
   free(h->pH); free(h->kappa); free(h->rcut); free(h->kT); free(h->gamma); free(h->time);
   free(h->md_counter); free(h->md_steps); free(h->samples_done); free(h->f_valid);
   free(h->trials); free(h->accepted); free(h->last_obs); free(h->last_qdist);
-  free(h->wl); free(h->wn); free(h->dl); free(h->dn); free(h->ref); free(h->lists_valid); free(h->rebuilds); free(h->chargeable);
+  if (h->wl) for (int r = 0; r < h->R; ++r) { free(h->wl[r]); free(h->wn[r]); free(h->dl[r]); free(h->dn[r]); }
+  free(h->wl); free(h->wn); free(h->dl); free(h->dn); free(h->cap_wl); free(h->cap_dl);
+  free(h->ref); free(h->lists_valid); free(h->rebuilds); free(h->chargeable);
   free(h);
 }
 
@@ -554,10 +562,15 @@ int orc_set_list_mode(orc_handle *h, int32_t on, double skin) {
   h->use_lists = on != 0;
   if (skin > 0.0) h->skin = skin;
   if (on && !h->wl) {
-    size_t RP = (size_t)h->R * h->P;
-    h->wl = malloc(sizeof(int) * RP * h->cap_wl); h->wn = calloc(RP, sizeof(int));
-    h->dl = malloc(sizeof(int) * RP * h->cap_dl); h->dn = calloc(RP, sizeof(int));
-    h->ref = calloc(RP * 3, sizeof(double));
+    h->wl = calloc(h->R, sizeof(int *)); h->wn = calloc(h->R, sizeof(int *));
+    h->dl = calloc(h->R, sizeof(int *)); h->dn = calloc(h->R, sizeof(int *));
+    h->cap_wl = malloc(sizeof(int) * h->R); h->cap_dl = malloc(sizeof(int) * h->R);
+    for (int r = 0; r < h->R; ++r) {
+      h->cap_wl[r] = 32; h->cap_dl[r] = 64;
+      h->wl[r] = malloc(sizeof(int) * (size_t)h->P * h->cap_wl[r]); h->wn[r] = calloc(h->P, sizeof(int));
+      h->dl[r] = malloc(sizeof(int) * (size_t)h->P * h->cap_dl[r]); h->dn[r] = calloc(h->P, sizeof(int));
+    }
+    h->ref = calloc((size_t)h->R * h->P * 3, sizeof(double));
   }
   for (int r = 0; r < h->R; ++r) h->lists_valid[r] = 0;
   return CGPE_OK;
@@ -703,8 +716,8 @@ static double site_delta_e(const orc_handle *h, int r, int i, int t_old, int t_n
   if (h->use_lists) {
     orc_handle *hm = (orc_handle *)h;
     ensure_lists(hm, r);
-    const int *wl = h->wl + ((size_t)r * h->P + i) * h->cap_wl, *dl = h->dl + ((size_t)r * h->P + i) * h->cap_dl;
-    const int nw = h->wn[(size_t)r * h->P + i], nd = h->dn[(size_t)r * h->P + i];
+    const int *wl = h->wl[r] + (size_t)i * h->cap_wl[r], *dl = h->dl[r] + (size_t)i * h->cap_dl[r];
+    const int nw = h->wn[r][i], nd = h->dn[r][i];
     if (c->use_wca)
       for (int k = 0; k < nw; ++k) {
         const int j = wl[k];
@@ -928,16 +941,16 @@ int orc_list_stats(orc_handle *h, double *out) {
     const double *q = h->q + (size_t)r * h->P;
     for (int i = 0; i < h->P; ++i) {
       const double *xi = X(h, r, i);
-      for (int k = 0; k < h->wn[(size_t)r * h->P + i]; ++k) {
-        const int j = h->wl[((size_t)r * h->P + i) * h->cap_wl + k];
+      for (int k = 0; k < h->wn[r][i]; ++k) {
+        const int j = h->wl[r][(size_t)i * h->cap_wl[r] + k];
         const double *xj = X(h, r, j);
         double d0 = min_image(xi[0] - xj[0], c->box_l), d1 = min_image(xi[1] - xj[1], c->box_l), d2 = min_image(xi[2] - xj[2], c->box_l);
         double s = ty[i] < h->T && ty[j] < h->T ? c->wca_sig[ty[i] * CGPE_MAX_TYPES + ty[j]] : 0.0;
         a[0] += 1;
         if (d0 * d0 + d1 * d1 + d2 * d2 < 1.2599210498948731648 * s * s) a[1] += 1;
       }
-      for (int k = 0; k < h->dn[(size_t)r * h->P + i]; ++k) {
-        const int j = h->dl[((size_t)r * h->P + i) * h->cap_dl + k];
+      for (int k = 0; k < h->dn[r][i]; ++k) {
+        const int j = h->dl[r][(size_t)i * h->cap_dl[r] + k];
         const double *xj = X(h, r, j);
         double d0 = min_image(xi[0] - xj[0], c->box_l), d1 = min_image(xi[1] - xj[1], c->box_l), d2 = min_image(xi[2] - xj[2], c->box_l);
         a[2] += 1;
