@@ -170,6 +170,8 @@ int check_device_errors(cgpe_handle *h) {
   if (any & kErrFene) return fail(h, CGPE_ERR_NUMERIC, "FENE bond stretched beyond d_r_max (first replica %d)", first);
   if (any & kErrDiverged)
     return fail(h, CGPE_ERR_NUMERIC, "replica %d diverged (a velocity exceeds 1000 sqrt(kT/m)): the integration is unstable, reduce the time step", first);
+  if (any & kErrIonPool)
+    return fail(h, CGPE_ERR_CAPACITY, "explicit-ion pool exhausted (n_ion_slots=%d, first replica %d): add spare hidden slots", h->p.n_ions, first);
   if (any & kErrDhCap)
     return fail(h, CGPE_ERR_CAPACITY, "Debye-Hueckel neighbour list overflow (cap_dh=%d, first replica %d): raise cap_dh", h->w.cap_d, first);
   return fail(h, CGPE_ERR_CAPACITY, "WCA neighbour list overflow (cap_wca=%d, first replica %d): raise cap_wca or lower skin",
@@ -256,7 +258,28 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   *out = nullptr;
   int rc = validate(cfg);
   if (rc) return rc;
-  if (cfg->n_ion_slots > 0) return fail(nullptr, CGPE_ERR_UNSUPPORTED, "explicit ions are not implemented yet");
+  if (cfg->n_ion_slots > 0) {
+    if (cfg->n_reactions == 0) return fail(nullptr, CGPE_ERR_INVALID, "explicit ions need at least one reaction");
+    double rc_ion = 0.0;   // largest WCA cutoff of the ion type
+    const int tb = cfg->reactions[0].type_ion;
+    for (int m = 0; m < cfg->n_reactions; ++m) {
+      const cgpe_reaction &r = cfg->reactions[m];
+      if (r.type_ion != tb || r.q_ion != cfg->reactions[0].q_ion || tb < 0 || tb >= cfg->n_types)
+        return fail(nullptr, CGPE_ERR_INVALID, "explicit ions: all reactions must release the same ion type");
+      if (tb == r.type_prot || tb == r.type_deprot) return fail(nullptr, CGPE_ERR_INVALID, "explicit ions: the ion type must differ from the site types");
+    }
+    if (cfg->use_wca)
+      for (int t = 0; t < cfg->n_types; ++t)
+        if (cfg->wca_eps[tb * CGPE_MAX_TYPES + t] > 0.0)
+          rc_ion = std::fmax(rc_ion, 1.122462048309373 * cfg->wca_sig[tb * CGPE_MAX_TYPES + t]);
+    for (int m = 0; m < cfg->n_reactions; ++m)
+      if (cfg->reactions[m].exclusion_range < rc_ion)
+        return fail(nullptr, CGPE_ERR_UNSUPPORTED,
+                    "reaction %d: exclusion_range %g is below the ion's largest WCA cutoff %g (an inserted ion would "
+                    "carry WCA energy, which this build does not evaluate)", m, cfg->reactions[m].exclusion_range, rc_ion);
+    if (cfg->n_chains * cfg->n_beads + cfg->n_ion_slots > 2048)
+      return fail(nullptr, CGPE_ERR_UNSUPPORTED, "explicit ions are served by the shared-memory engine only (<= 2048 particles per replica)");
+  }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -276,7 +299,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   DevParams &p = h->p;
   std::memset(&p, 0, sizeof(p));
   p.R = cfg->n_replicas; p.N = cfg->n_beads; p.NC = cfg->n_chains * cfg->n_beads;
-  p.P = p.NC + cfg->n_ion_slots; p.T = cfg->n_types; p.n_rx = cfg->n_reactions;
+  p.P = p.NC + cfg->n_ion_slots; p.T = cfg->n_types; p.n_rx = cfg->n_reactions; p.n_ions = cfg->n_ion_slots;
   p.bond_kind = cfg->bond_kind; p.use_angle = cfg->use_angle; p.use_dih = cfg->use_dihedral;
   p.dih_mult = cfg->dihedral_mult; p.use_wca = cfg->use_wca; p.use_dh = cfg->use_dh;
   p.replica_offset = cfg->replica_offset;
@@ -306,6 +329,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
     d.seed = (uint32_t)r.seed;
     d.q_prot = (float)r.q_prot; d.q_deprot = (float)r.q_deprot; d.q_ion = (float)r.q_ion;
     d.inv_kT = (float)(1.0 / r.kT); d.pK = r.pK;
+    d.excl2 = (float)(r.exclusion_range * r.exclusion_range); d.sqrt_kT = (float)std::sqrt(r.kT);
   }
   // chargeable particles are fixed at set_state; size the lists for "every third bead" + ions
   p.n_chg = 0;
@@ -330,6 +354,8 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   ALLOC(g.chg, RP);
   ALLOC(g.lst_prot, (size_t)p.R * nrx * p.P); ALLOC(g.lst_deprot, (size_t)p.R * nrx * p.P);
   ALLOC(g.cnt, (size_t)p.R * nrx * 2);
+  ALLOC(g.ion_active, (size_t)p.R * (p.n_ions > 0 ? p.n_ions : 1)); ALLOC(g.ion_free, (size_t)p.R * (p.n_ions > 0 ? p.n_ions : 1));
+  ALLOC(g.ion_cnt, (size_t)p.R * 2);
   ALLOC(g.kappa, p.R); ALLOC(g.rcut, p.R); ALLOC(g.kT, p.R); ALLOC(g.gamma, p.R); ALLOC(g.pH, p.R);
   ALLOC(g.time, p.R); ALLOC(g.md_counter, p.R); ALLOC(g.md_steps, p.R); ALLOC(g.samples_done, p.R);
   ALLOC(g.rebuilds, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
@@ -465,6 +491,29 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     }
   std::vector<float> zero;
   if (!vel) zero.assign(RP * 4, 0.f);
+  std::vector<float> xq_fix, vel_fix;
+  if (p.n_ions > 0) {
+    // hidden slots (non-interacting type) carry neither charge nor velocity; pools in id order
+    xq_fix.assign(xyzq, xyzq + RP * 4);
+    vel_fix.assign(vel ? vel : zero.data(), (vel ? vel : zero.data()) + RP * 4);
+    std::vector<int> act((size_t)p.R * p.n_ions, 0), fre((size_t)p.R * p.n_ions, 0), icnt((size_t)p.R * 2, 0);
+    const int tb = h->cfg.reactions[0].type_ion;
+    for (int r = 0; r < p.R; ++r)
+      for (int i = p.NC; i < p.P; ++i) {
+        const size_t k = (size_t)r * p.P + i;
+        if (type[k] >= p.T) {
+          xq_fix[4 * k + 3] = 0.f; vel_fix[4 * k] = vel_fix[4 * k + 1] = vel_fix[4 * k + 2] = 0.f;
+          fre[(size_t)r * p.n_ions + icnt[r * 2 + 1]++] = i;
+        } else if (type[k] == tb) {
+          act[(size_t)r * p.n_ions + icnt[r * 2]++] = i;
+        }
+      }
+    xyzq = xq_fix.data(); vel = vel_fix.data();
+    CU(cudaMemcpyAsync(h->g.ion_active, act.data(), sizeof(int) * act.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->g.ion_free, fre.data(), sizeof(int) * fre.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->g.ion_cnt, icnt.data(), sizeof(int) * icnt.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   CU(cudaMemcpyAsync(h->g.pos, xyzq, sizeof(float4) * RP, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->g.vel, vel ? vel : zero.data(), sizeof(float4) * RP, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->g.type, type, RP, cudaMemcpyHostToDevice, h->stream));

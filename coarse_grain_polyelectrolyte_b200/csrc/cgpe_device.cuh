@@ -15,26 +15,29 @@ constexpr int kMaxRx = CGPE_MAX_REACTIONS;
 constexpr float kLog2e = 1.4426950408889634f;
 
 // error bits raised by kernels into DevState::err[r]
-enum : int { kErrWcaCap = 1, kErrDhCap = 2, kErrNonFinite = 4, kErrFene = 8, kErrDiverged = 16 };
+enum : int { kErrWcaCap = 1, kErrDhCap = 2, kErrNonFinite = 4, kErrFene = 8, kErrDiverged = 16, kErrIonPool = 32 };
 
 struct DevReaction {
   int type_prot, type_deprot, type_ion;
   uint32_t seed;
   float q_prot, q_deprot, q_ion;
   float inv_kT;
+  float excl2;       // exclusion_range^2 (explicit ions)
+  float sqrt_kT;     // Maxwell-Boltzmann width of an inserted ion's velocity
   double pK;
 };
 
 // Byte offsets of the shared-memory arrays of the replica engine (chain_engine.cu).  They live in
 // the kernel-parameter constant bank, so an address is one add away and no pointer stays in a register.
 struct SmemOff {
-  int pos, tab, red, slot, fd, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, cpos, wrange, wflag, ratio, qlist, total;
+  int pos, tab, red, slot, fd, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, cpos, wrange, wflag, ratio, qlist, ionA, ionF, ionV, total;
 };
 
 // Uniform (replica-independent) parameters, passed to kernels by value.
 struct DevParams {
   int R, P, NC, N, T;           // replicas, particles, chain beads (n_chains*N), beads per chain, types
   int n_chg;                    // chargeable particles per replica (sites [+ ions])
+  int n_ions;                   // explicit-ion slots per replica (0 = implicit ions)
   int n_rx;
   int bond_kind, use_angle, use_dih, dih_mult, use_wca, use_dh;
   int cap_w;                    // WCA list row capacity
@@ -69,6 +72,9 @@ struct DevState {
   int *lst_prot;      // [R][n_rx][P] bookkeeping lists (particle ids), swap-remove order
   int *lst_deprot;    // [R][n_rx][P]
   int *cnt;           // [R][n_rx][2] n_prot, n_deprot
+  int *ion_active;    // [R][n_ions] particle ids of the free H+ (type_ion), swap-remove order
+  int *ion_free;      // [R][n_ions] hidden slots, used as a stack
+  int *ion_cnt;       // [R][2] n_active, n_free
   float *kappa, *rcut, *kT, *gamma;  // [R]
   double *pH;         // [R]
   double *time;       // [R]

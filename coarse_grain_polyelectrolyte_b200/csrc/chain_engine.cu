@@ -59,6 +59,9 @@ size_t chain_smem_bytes(DevParams &p) {
   f.wflag = take(n_chg, 1);
   f.ratio = take(sizeof(float) * n_rx * (n_chg + 1), 4);
   f.qlist = take(sizeof(uint16_t) * n_chg, 2);
+  f.ionA = take(sizeof(uint16_t) * (p.n_ions > 0 ? p.n_ions : 1), 2);
+  f.ionF = take(sizeof(uint16_t) * (p.n_ions > 0 ? p.n_ions : 1), 2);
+  f.ionV = take(sizeof(float4) * (p.n_ions > 0 ? p.n_ions : 1), 16);
   f.total = (int)align_up(o, 16);
   return (size_t)f.total;
 }
@@ -135,6 +138,13 @@ __device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
     for (int i = c.tid; i < nd; i += c.nt) c.s.ld[(size_t)m * p.n_chg + i] = (uint16_t)gd[i];
     if (c.tid == 0) { c.s.cnt[m * 2] = np; c.s.cnt[m * 2 + 1] = nd; }
   }
+  if (p.n_ions > 0) {   // explicit ions: pools of free H+ and of hidden slots; flag[1], flag[2] = their sizes
+    const int na = c.g.ion_cnt[c.r * 2], nf = c.g.ion_cnt[c.r * 2 + 1];
+    for (int i = c.tid; i < na; i += c.nt) c.s.ion_active[i] = (uint16_t)c.g.ion_active[(size_t)c.r * p.n_ions + i];
+    for (int i = c.tid; i < nf; i += c.nt) c.s.ion_free[i] = (uint16_t)c.g.ion_free[(size_t)c.r * p.n_ions + i];
+    for (int i = c.tid; i < p.n_ions; i += c.nt) c.s.ion_vel[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c.tid == 0) { c.s.flag[1] = na; c.s.flag[2] = nf; c.s.flag[3] = 0; }
+  }
   __syncthreads();
   for (int i = c.tid; i < p.n_chg; i += c.nt) {
     c.s.cidx[c.s.chg[i]] = (uint16_t)i;
@@ -158,11 +168,33 @@ __device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
   }
 }
 
+// Explicit ions: a trial move may have placed an ion somewhere else or hidden it; its owner thread
+// takes position and (if pending) velocity over from shared memory.  Call behind a barrier.
+template <int ITEMS>
+__device__ void sync_ions(Ctx &c, Thr<ITEMS> &t) {
+  const DevParams &p = c.p;
+  if (p.n_ions == 0) return;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = c.tid + k * c.nt;
+    if (i >= p.NC && i < p.P) {
+      const float4 x = c.s.pos[i];
+      t.x[k][0] = x.x; t.x[k][1] = x.y; t.x[k][2] = x.z;
+      const float4 v = c.s.ion_vel[i - p.NC];
+      if (v.w != 0.f) {
+        t.v[k][0] = v.x; t.v[k][1] = v.y; t.v[k][2] = v.z;
+        c.s.ion_vel[i - p.NC].w = 0.f;
+      }
+    }
+  }
+}
+
 template <int ITEMS>
 __device__ void store_state(Ctx &c, Thr<ITEMS> &t, bool store_forces) {
   const DevParams &p = c.p;
   const size_t base = (size_t)c.r * p.P;
   __syncthreads();
+  sync_ions(c, t);
   int bad = 0;
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
@@ -186,6 +218,12 @@ __device__ void store_state(Ctx &c, Thr<ITEMS> &t, bool store_forces) {
     for (int i = c.tid; i < np; i += c.nt) gp[i] = c.s.lp[(size_t)m * p.n_chg + i];
     for (int i = c.tid; i < nd; i += c.nt) gd[i] = c.s.ld[(size_t)m * p.n_chg + i];
     if (c.tid == 0) { c.g.cnt[((size_t)c.r * p.n_rx + m) * 2] = np; c.g.cnt[((size_t)c.r * p.n_rx + m) * 2 + 1] = nd; }
+  }
+  if (p.n_ions > 0) {
+    const int na = c.s.flag[1], nf = c.s.flag[2];
+    for (int i = c.tid; i < na; i += c.nt) c.g.ion_active[(size_t)c.r * p.n_ions + i] = c.s.ion_active[i];
+    for (int i = c.tid; i < nf; i += c.nt) c.g.ion_free[(size_t)c.r * p.n_ions + i] = c.s.ion_free[i];
+    if (c.tid == 0) { c.g.ion_cnt[c.r * 2] = na; c.g.ion_cnt[c.r * 2 + 1] = nf; }
   }
   if (c.err) atomicOr(&c.g.err[c.r], c.err);
   if (c.tid == 0 && c.rebuilds) c.g.rebuilds[c.r] += c.rebuilds;
@@ -251,6 +289,25 @@ __device__ void build_rows(Ctx &c, Thr<ITEMS> &t) {
 template <int ITEMS>
 __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
   const DevParams &p = c.p;
+  sync_ions(c, t);   // positions a trial move gave to explicit ions (no-op otherwise)
+  if (p.P > p.NC) {
+    // free particles (explicit ions) wander: fold them back into the box so FP32 keeps its resolution
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int i = c.tid + k * c.nt;
+      if (i >= p.NC && i < p.P) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t.x[k][a] -= p.box_l * floorf(t.x[k][a] * p.inv_box_l);
+        float4 *sp = &c.s.pos[i];
+        sp->x = t.x[k][0]; sp->y = t.x[k][1]; sp->z = t.x[k][2];
+        if (t.ci[k] >= 0) { float4 *cp = &c.s.cpos[t.ci[k]]; cp->x = t.x[k][0]; cp->y = t.x[k][1]; cp->z = t.x[k][2]; }
+        any = true;
+      }
+    }
+    (void)any;
+    __syncthreads();
+  }
   // bounding box of the replica: if extent + list radius + skin < L no listed pair can be closer
   // through a periodic image than directly, and it stays so until the next rebuild
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -269,6 +326,7 @@ __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
     }
   float *scr = reinterpret_cast<float *>(c.s.red);   // 32 warps x 6 floats fit in the scratch
   __syncthreads();
+  if (c.tid == 0 && p.n_ions > 0) c.s.flag[3] = 0;   // rows are about to be current again
   if (c.lane == 0)
 #pragma unroll
     for (int a = 0; a < 3; ++a) { scr[c.warp * 6 + a] = lo[a]; scr[c.warp * 6 + 3 + a] = hi[a]; }
@@ -490,6 +548,7 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
                          bool &lists_valid) {
   const DevParams &p = c.p;
   if (n_steps <= 0) return;
+  sync_ions(c, t);   // explicit ions moved or hidden by trial moves since the last burst
   if (!lists_valid) { build_lists(c, t); lists_valid = true; }
   if (p.use_dh) { build_qlist(c); __syncthreads(); }   // charges may have changed since the last burst
   if (!f_valid) { compute_forces(c, t, true, counter); f_valid = true; }
@@ -620,13 +679,26 @@ __device__ void mc_prepare(Ctx &c) {
   __syncthreads();
 }
 
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// With explicit ions (p.n_ions > 0) a forward move also inserts one H+ ("B") at a uniform position
+// with a Maxwell-Boltzmann velocity and a backward move takes a random free H+ away:
+// the ion's Debye-Hueckel energy with every particle and its distance to the nearest one
+// (exclusion range, M.py:202-206) come from one lane-parallel pass over all particles.  The ion
+// carries no WCA energy because cgpe_create insists on exclusion_range >= its largest WCA cutoff.
 __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_ctr, long long &accepted,
                          cgpe_trial_record *trace) {
   const DevParams &p = c.p;
   if (c.warp == 0 && n_trials > 0) {
     const DevReaction rx = p.rx[m];
+    const bool ions = p.n_ions > 0;
     uint16_t *lp = c.s.lp + (size_t)m * p.n_chg, *ld = c.s.ld + (size_t)m * p.n_chg;
     int n_p = c.s.cnt[m * 2], n_d = c.s.cnt[m * 2 + 1];
+    int n_act = ions ? c.s.flag[1] : 0, n_free = ions ? c.s.flag[2] : 0;
     const float arg_fwd = (float)(2.302585092994045684 * (c.g.pH[c.r] - rx.pK)) * kLog2e;
     const float neg_beta_log2e = -rx.inv_kT * kLog2e;
     const float dq_fwd = rx.q_deprot - rx.q_prot, coul_fwd = p.dh_pref * dq_fwd;
@@ -634,9 +706,15 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
     const int nw = (p.n_chg + 31) >> 5;
     const float *ratio = c.s.ratio + (size_t)m * (p.n_chg + 1);
     long long acc = 0;
+    bool ion_moved = false;
     for (int base = 0; base < n_trials; base += 32) {
       const unsigned long long cnt = trial_ctr + (unsigned long long)(base + c.lane);
       const uint4 o = philox4x32_10((uint32_t)cnt, (uint32_t)(cnt >> 32), 0u, kTagMc + (uint32_t)m, k0, k1);
+      uint4 o1 = make_uint4(0, 0, 0, 0), o2 = o1;
+      if (ions) {   // block 1: insertion position, block 2: insertion velocity
+        o1 = philox4x32_10((uint32_t)cnt, (uint32_t)(cnt >> 32), 1u, kTagMc + (uint32_t)m, k0, k1);
+        o2 = philox4x32_10((uint32_t)cnt, (uint32_t)(cnt >> 32), 2u, kTagMc + (uint32_t)m, k0, k1);
+      }
       const int nb = min(32, n_trials - base);
       for (int tt = 0; tt < nb; ++tt) {
         const uint32_t a0 = __shfl_sync(0xffffffffu, o.x, tt), a1 = __shfl_sync(0xffffffffu, o.y, tt),
@@ -645,7 +723,12 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
         const int n_src = fwd ? n_p : n_d, n_dst = fwd ? n_d : n_p;
         uint16_t *src = fwd ? lp : ld, *dst = fwd ? ld : lp;
         const float u = u24(a2);
-        if (n_src == 0) {
+        // every reactant must exist: the site, and with explicit ions a free H+ to take (backward)
+        // or a spare slot to put one (forward)
+        bool possible = n_src > 0;
+        if (ions && !fwd && n_act == 0) possible = false;
+        if (ions && fwd && n_free == 0) { possible = false; c.err |= kErrIonPool; }
+        if (!possible) {
           if (trace && c.lane == 0) {
             cgpe_trial_record rec = {-1, -1, (int8_t)(fwd ? 1 : -1), 0, 0, 0, 0.f, 0.f, u};
             trace[base + tt] = rec;
@@ -655,20 +738,56 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
         const int k = (int)__umulhi(a1, (uint32_t)n_src);
         const int i = src[k];
         const int ci = c.s.cidx[i];
+        const int t_new = fwd ? rx.type_deprot : rx.type_prot;
+        const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = fwd ? dq_fwd : -dq_fwd;
         // E_new - E_old of the type/charge swap of site i from the per-site caches
         float de = c.s.wcache[ci];
         if (p.use_dh) de = fmaf(coul_fwd, c.s.phi[ci], de);
         if (!fwd) de = -de;
-        // bf = N_react/(N_prod+1) exp(-dE/kT + nu ln10 (pH-pK))   
-        const float bf = ratio[n_src] * exp2f(fmaf(neg_beta_log2e, de, fwd ? arg_fwd : -arg_fwd));
+        int b = -1, kb = 0;
+        bool excluded = false;
+        float4 pb4 = make_float4(0.f, 0.f, 0.f, rx.q_ion);
+        if (ions) {
+          if (fwd) {
+            b = c.s.ion_free[n_free - 1];
+            pb4.x = u24(__shfl_sync(0xffffffffu, o1.x, tt)) * p.box_l;
+            pb4.y = u24(__shfl_sync(0xffffffffu, o1.y, tt)) * p.box_l;
+            pb4.z = u24(__shfl_sync(0xffffffffu, o1.z, tt)) * p.box_l;
+          } else {
+            kb = (int)__umulhi(__shfl_sync(0xffffffffu, o.w, tt), (uint32_t)n_act);
+            b = c.s.ion_active[kb];
+            const float4 x = c.s.pos[b];
+            pb4.x = x.x; pb4.y = x.y; pb4.z = x.z;
+          }
+          float esum = 0.f, dmin2 = 3.0e38f;
+          for (int j = c.lane; j < p.P; j += 32) {
+            if (j == b) continue;
+            const int tj = j == i ? t_new : (int)c.s.type[j];   // the site is seen in its new state
+            if (tj >= p.T) continue;
+            const float4 pj4 = c.s.pos[j];
+            const float qj = j == i ? q_new : pj4.w;
+            V3 d;
+            const float r2 = dist2<true>(c, pb4, pj4, &d);
+            dmin2 = fminf(dmin2, r2);
+            if (p.use_dh && qj != 0.f && r2 < c.rc2) {
+              float fr;
+              esum = fmaf(qj, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), esum);
+            }
+          }
+          esum = warp_sum(esum);
+          dmin2 = warp_min(dmin2);
+          const float e_ion = p.dh_pref * rx.q_ion * esum;
+          de += fwd ? e_ion : -e_ion;
+          excluded = dmin2 < rx.excl2;
+        }
+        // bf = N_react/(N_prod+1) exp(-dE/kT + nu ln10 (pH-pK))   (SURVEY 8a-R1); E_new = +max if excluded
+        const float bf = excluded ? 0.f : ratio[n_src] * exp2f(fmaf(neg_beta_log2e, de, fwd ? arg_fwd : -arg_fwd));
         const bool accept = u < bf;
         if (trace && c.lane == 0) {
-          cgpe_trial_record rec = {i, -1, (int8_t)(fwd ? 1 : -1), (int8_t)accept, 0, 0, de, bf, u};
+          cgpe_trial_record rec = {i, b, (int8_t)(fwd ? 1 : -1), (int8_t)accept, (int8_t)excluded, 0, de, bf, u};
           trace[base + tt] = rec;
         }
         if (accept) {
-          const int t_new = fwd ? rx.type_deprot : rx.type_prot;
-          const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = fwd ? dq_fwd : -dq_fwd;
           const float4 pi4 = c.s.cpos[ci];
           // the flipped site's row: lane w fetches word w (before the bookkeeping stores)
           const uint32_t row = (p.use_dh && c.lane < nw) ? c.s.dbits[(size_t)ci * p.dw + c.lane] : 0u;
@@ -705,6 +824,57 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
             }
           }
           __syncwarp();
+          if (ions) {
+            const int cb = c.s.cidx[b];
+            const float dqb = fwd ? rx.q_ion : -rx.q_ion;
+            if (c.lane == 0) {
+              if (fwd) {   // the hidden slot becomes a free H+ at the drawn position
+                c.s.type[b] = (unsigned char)rx.type_ion;
+                c.s.pos[b] = pb4;
+                c.s.cpos[cb] = pb4;
+                c.s.qmask[cb >> 5] |= 1u << (cb & 31);
+              } else {     // the H+ turns into the non-interacting type and is gone (M.py:256-261)
+                c.s.type[b] = (unsigned char)p.T;
+                c.s.pos[b].w = 0.f;
+                c.s.cpos[cb].w = 0.f;
+                c.s.qmask[cb >> 5] &= ~(1u << (cb & 31));
+                c.s.ion_vel[b - p.NC] = make_float4(0.f, 0.f, 0.f, 1.f);
+                c.s.ion_active[kb] = c.s.ion_active[n_act - 1];
+                c.s.ion_free[n_free] = (uint16_t)b;
+              }
+            }
+            if (fwd) {
+              // velocity of the new ion: all lanes fetch the draw, lane 0 stores it
+              const uint32_t w0 = __shfl_sync(0xffffffffu, o2.x, tt), w1 = __shfl_sync(0xffffffffu, o2.y, tt),
+                             w2 = __shfl_sync(0xffffffffu, o2.z, tt), w3 = __shfl_sync(0xffffffffu, o2.w, tt);
+              if (c.lane == 0) {
+                const float ua = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f), ub = ((float)(w1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                const float uc = ((float)(w2 >> 8) + 0.5f) * (1.0f / 16777216.0f), ud = ((float)(w3 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                const float ra = rx.sqrt_kT * sqrtf(-2.0f * logf(ua)), rb = rx.sqrt_kT * sqrtf(-2.0f * logf(uc));
+                float sa, ca, sb_, cb_;
+                sincosf(6.283185307179586f * ub, &sa, &ca);
+                sincosf(6.283185307179586f * ud, &sb_, &cb_);
+                c.s.ion_vel[b - p.NC] = make_float4(ra * ca, ra * sa, rb * cb_, 1.f);
+                c.s.ion_active[n_act] = (uint16_t)b;
+              }
+              n_free -= 1; n_act += 1;
+            } else {
+              n_act -= 1; n_free += 1;
+            }
+            // the ion's charge appears in / leaves the potential of every chargeable particle in range
+            if (p.use_dh)
+              for (int ck = c.lane; ck < p.n_chg; ck += 32) {
+                if (ck == cb) continue;
+                V3 d;
+                const float r2 = dist2<true>(c, pb4, c.s.cpos[ck], &d);
+                if (r2 < c.rc2) {
+                  float fr;
+                  c.s.phi[ck] = fmaf(dqb, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), c.s.phi[ck]);
+                }
+              }
+            ion_moved = true;
+            __syncwarp();
+          }
           if (refresh) {
             // partners of i that are titratable themselves see a new neighbour type: refresh their cache
             const int l = (p.NC == p.N) ? (i < p.NC ? i : -1) : (i < p.NC ? i % p.N : -1);
@@ -727,7 +897,10 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
         }
       }
     }
-    if (c.lane == 0) { c.s.cnt[m * 2] = n_p; c.s.cnt[m * 2 + 1] = n_d; }
+    if (c.lane == 0) {
+      c.s.cnt[m * 2] = n_p; c.s.cnt[m * 2 + 1] = n_d;
+      if (ions) { c.s.flag[1] = n_act; c.s.flag[2] = n_free; if (ion_moved) c.s.flag[3] = 1; }
+    }
     accepted += acc;  // only meaningful on warp 0; thread 0 writes it back
   }
   trial_ctr += (unsigned long long)n_trials;
@@ -812,6 +985,9 @@ __device__ __forceinline__ void bind_smem(const DevParams &p, ChainSmem *s) {
   s->wflag = smem_raw + f.wflag;
   s->ratio = reinterpret_cast<float *>(smem_raw + f.ratio);
   s->qlist = reinterpret_cast<uint16_t *>(smem_raw + f.qlist);
+  s->ion_active = reinterpret_cast<uint16_t *>(smem_raw + f.ionA);
+  s->ion_free = reinterpret_cast<uint16_t *>(smem_raw + f.ionF);
+  s->ion_vel = reinterpret_cast<float4 *>(smem_raw + f.ionV);
 }
 
 // ---- kernels -----------------------------------------------------------------------------------
@@ -1035,6 +1211,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
       mc_block(c, m, sp.mc_trials[b], trial_ctr[m], accepted[m], nullptr);
       if (sp.mc_trials[b] > 0) f_valid = false;
     }
+    if (p.n_ions > 0 && c.s.flag[3]) lists_valid = false;   // ions were inserted / taken away: rows are stale
     double rg, ree;
     chain_observables(c, t, &rg, &ree);   // E.py:100-101
     if (c.tid == 0) {
@@ -1043,7 +1220,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
       for (int m = 0; m < p.n_rx; ++m) n_ion += c.s.cnt[m * 2 + 1];
       o6[0] = p.n_rx > 0 ? c.s.cnt[1] : 0;   // E.py:97
       o6[1] = p.n_rx > 1 ? c.s.cnt[3] : 0;   // E.py:98
-      o6[2] = n_ion;                          // E.py:99 (implicit ions: N_B = N_N + N_N2)
+      o6[2] = p.n_ions > 0 ? c.s.flag[1] : n_ion;   // E.py:99 (implicit ions: N_B = N_N + N_N2)
       o6[3] = rg; o6[4] = ree;
       o6[5] = t0 + (double)steps * p.dt_d;   // E.py:102
     }

@@ -27,6 +27,8 @@ struct ChainSmem {
   float4 *cpos;             // [n_chg] x,y,z,q of the chargeable particles, compact (no id indirection)
   unsigned char *wrange;    // [n_chg][2] first / one-past-last non-empty word of the Debye-Hueckel row
   unsigned char *wflag;     // [n_chg] 1 if a WCA partner of the particle is titratable itself
+  uint16_t *ion_active, *ion_free;   // [n_ions] explicit-ion pools (particle ids)
+  float4 *ion_vel;          // [n_ions] velocity hand-over for ions touched by a trial move (w = 1: pending)
   uint16_t *qlist;          // [n_chg] chargeable indices of the particles that carry charge right now (dense mode)
   float *ratio;             // [n_rx][n_chg+1] N/(N_sites - N + 1): the factorial factor of the acceptance
 };

@@ -146,12 +146,14 @@ k_min_dist(const __grid_constant__ DevParams p, const __grid_constant__ DevState
   __shared__ float scratch[32];
   const int r = blockIdx.x;
   const float4 *pos = g.pos + (size_t)r * p.P;
+  const uint8_t *type = g.type + (size_t)r * p.P;
   float best = 3.0e38f;
   for (int i = threadIdx.x; i < p.P; i += blockDim.x) {
+    if (type[i] >= p.T) continue;   // hidden slots are not particles
     const float4 pi = pos[i];
     for (int j = i + 1; j < p.P; ++j) {
       V3 d;
-      best = fminf(best, pair_dist2(p, pi, pos[j], &d));
+      if (type[j] < p.T) best = fminf(best, pair_dist2(p, pi, pos[j], &d));
     }
   }
   for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -192,7 +194,7 @@ k_observables(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
         if (m < 2) counts[r * 3 + m] = nd;
         n_ion += nd;
       }
-      counts[r * 3 + 2] = n_ion;   // implicit ions: N_B = N_N + N_N2
+      counts[r * 3 + 2] = p.n_ions > 0 ? g.ion_cnt[r * 2] : n_ion;   // implicit ions: N_B = N_N + N_N2
     }
   }
 }

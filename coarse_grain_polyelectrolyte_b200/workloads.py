@@ -84,7 +84,8 @@ def num_samples(params):
 class Workload:
     """A cgpe_config + start state + sampling schedule for R replicas of one chain."""
 
-    def __init__(self, params, pH, c_salt=None, replica_offset=0, seed=12, device=-1, deprotonated=True):
+    def __init__(self, params, pH, c_salt=None, replica_offset=0, seed=12, device=-1, deprotonated=True,
+                 explicit_ions=False, ion_seed=10):
         self.params = params
         sp = params["System properties"]
         sc = params["Simulation configuration"]
@@ -109,8 +110,14 @@ class Workload:
                  pK=params["pH properties"]["pK2"], kT=1.0,
                  exclusion_range=topology.combination_sigma(ru.sigma["N2"], ru.sigma["B"])),
         ]
+        # explicit ions (M.py:173-198): n_acid B+ and Cl-, n_salt Na+ and Cl-, plus one spare hidden
+        # slot per site so that every site can release its H+
+        n_acid = sp["NH monomers"] + sp["NH2 monomers"]
+        ion_names = (["B"] * n_acid + ["Cl"] * n_acid + ["Na"] * ru.n_salt + ["Cl"] * ru.n_salt) if explicit_ions else []
+        n_spare = n_acid if explicit_ions else 0
+        self.n_ion_slots = len(ion_names) + n_spare
         self.cfg = _abi.make_config(
-            n_replicas=R, replica_offset=replica_offset, n_chains=1, n_beads=n_mon, n_ion_slots=0,
+            n_replicas=R, replica_offset=replica_offset, n_chains=1, n_beads=n_mon, n_ion_slots=self.n_ion_slots,
             n_types=len(tix), bond_kind=_abi.BOND_FENE if sc["USE_FENE"] else _abi.BOND_HARMONIC,
             use_angle=int(sc["USE_BENDING"]), use_dihedral=int(sc["USE_DIHEDRAL_POT"]), dihedral_mult=3,
             use_wca=int(sc["USE_WCA"]), use_dh=int(sc["USE_ELECTROSTATICS"]),
@@ -132,6 +139,14 @@ class Workload:
                                                 min_distance=0.9 * ru.bond_length, box_l=None)[0]
         pos += 0.5 * ru.box_length - pos.mean(axis=0)
         self.xyzq = np.concatenate([pos, self.q[:, None]], axis=1).astype(np.float32)
+        if explicit_ions:
+            rng = np.random.RandomState(ion_seed)          # np.random.seed(10), P.py:376
+            ion_pos = rng.random_sample((self.n_ion_slots, 3)) * ru.box_length
+            ion_type = np.array([tix[n] for n in ion_names] + [len(tix)] * n_spare, dtype=np.uint8)
+            ion_q = np.array([ru.charge[n] for n in ion_names] + [0.0] * n_spare, dtype=np.float32)
+            self.xyzq = np.concatenate([self.xyzq, np.concatenate([ion_pos, ion_q[:, None]], axis=1).astype(np.float32)])
+            self.type = np.concatenate([self.type, ion_type])
+            self.q = np.concatenate([self.q, ion_q])
         self.n_sites = (int(np.sum(role == 1)), int(np.sum(role == 2)))
         ns, nsi = num_samples(params)
         p = params["Montecarlo properties"]["PROB_REACTION"]

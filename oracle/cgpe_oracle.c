@@ -85,6 +85,7 @@ struct orc_handle {
   int64_t *samples_done; /* [R] */
   int *f_valid;          /* [R] */
   rx_lists *lists;       /* [R][n_reactions] */
+  int32_t *ion_active, *ion_free, *n_active, *n_free; /* explicit ions: [R][n_ion_slots] pools, [R] counts */
   int32_t thermostat_seed;
   double force_cap;
   int have_state;
@@ -430,7 +431,13 @@ static int check_config(const cgpe_config *c, char *err) {
 int orc_create(const cgpe_config *cfg, orc_handle **out) {
   int rc = check_config(cfg, g_err);
   if (rc) return rc;
-  if (cfg->n_ion_slots > 0) { snprintf(g_err, 512, "explicit ions are not implemented yet"); return CGPE_ERR_UNSUPPORTED; }
+  if (cfg->n_ion_slots > 0) {
+    for (int m = 0; m < cfg->n_reactions; ++m)
+      if (cfg->reactions[m].type_ion != cfg->reactions[0].type_ion || cfg->reactions[m].q_ion != cfg->reactions[0].q_ion ||
+          cfg->reactions[m].type_ion < 0 || cfg->reactions[m].type_ion >= cfg->n_types) {
+        snprintf(g_err, 512, "explicit ions: all reactions must release the same ion type"); return CGPE_ERR_INVALID;
+      }
+  }
   orc_handle *h = (orc_handle *)calloc(1, sizeof(orc_handle));
   h->cfg = *cfg;
   h->R = cfg->n_replicas; h->T = cfg->n_types; h->NC = cfg->n_chains * cfg->n_beads;
@@ -460,6 +467,11 @@ int orc_create(const cgpe_config *cfg, orc_handle **out) {
   }
   h->thermostat_seed = 0;
   h->use_lists = 0; h->skin = 0.8;
+  {
+    const int ni = cfg->n_ion_slots > 0 ? cfg->n_ion_slots : 1;
+    h->ion_active = calloc((size_t)h->R * ni, sizeof(int32_t)); h->ion_free = calloc((size_t)h->R * ni, sizeof(int32_t));
+    h->n_active = calloc(h->R, sizeof(int32_t)); h->n_free = calloc(h->R, sizeof(int32_t));
+  }
   h->lists_valid = calloc(h->R, sizeof(int));
   h->rebuilds = calloc(h->R, sizeof(int64_t));
   h->chargeable = calloc(RP, 1);
@@ -478,6 +490,7 @@ void orc_destroy(orc_handle *h) {
   if (h->wl) for (int r = 0; r < h->R; ++r) { free(h->wl[r]); free(h->wn[r]); free(h->dl[r]); free(h->dn[r]); }
   free(h->wl); free(h->wn); free(h->dl); free(h->dn); free(h->cap_wl); free(h->cap_dl);
   free(h->ref); free(h->lists_valid); free(h->rebuilds); free(h->chargeable);
+  free(h->ion_active); free(h->ion_free); free(h->n_active); free(h->n_free);
   free(h);
 }
 
@@ -494,6 +507,16 @@ int orc_synchronize(orc_handle *h) { (void)h; return CGPE_OK; }
 
 static void rebuild_lists(orc_handle *h) {
   /* bookkeeping lists in particle-id order (set_state contract) */
+  if (h->cfg.n_ion_slots > 0 && h->cfg.n_reactions > 0)
+    for (int r = 0; r < h->R; ++r) {
+      const int ni = h->cfg.n_ion_slots, tb = h->cfg.reactions[0].type_ion;
+      h->n_active[r] = h->n_free[r] = 0;
+      for (int i = h->NC; i < h->P; ++i) {
+        const uint8_t t = h->type[(size_t)r * h->P + i];
+        if (t == tb) h->ion_active[(size_t)r * ni + h->n_active[r]++] = i;
+        else if (t >= h->T) h->ion_free[(size_t)r * ni + h->n_free[r]++] = i;
+      }
+    }
   for (int r = 0; r < h->R; ++r)
     for (int m = 0; m < h->cfg.n_reactions; ++m) {
       rx_lists *l = &h->lists[(size_t)r * h->cfg.n_reactions + m];
@@ -518,6 +541,7 @@ int orc_set_state(orc_handle *h, const float *xyzq, const float *vel, const uint
     h->q[k] = xyzq[k * 4 + 3];
     if (type[k] > h->T) return fail(h, CGPE_ERR_INVALID, "type index out of range");
     h->type[k] = type[k];
+    if (type[k] >= h->T) { h->v[k * 3] = h->v[k * 3 + 1] = h->v[k * 3 + 2] = 0.0; h->q[k] = 0.0; }
   }
   rebuild_lists(h);
   {
@@ -754,6 +778,34 @@ static double site_delta_e(const orc_handle *h, int r, int i, int t_old, int t_n
   return de_w + de_c;
 }
 
+/* Energy of an ion of type tb / charge qb at position xb with every interacting particle except
+ * `skip`, where particle `ov` is seen with type ov_t and charge ov_q (the site being swapped in the
+ * same trial).  *dmin2 returns the squared distance to the nearest interacting particle
+ * (exclusion-range test, M.py:202-206,213). */
+static double ion_energy(const orc_handle *h, int r, const double *xb, int tb, double qb, int skip, int ov, int ov_t,
+                         double ov_q, double *dmin2) {
+  const cgpe_config *c = &h->cfg;
+  const uint8_t *ty = h->type + (size_t)r * h->P;
+  const double *q = h->q + (size_t)r * h->P;
+  double e = 0.0, fr, best = INFINITY;
+  for (int j = 0; j < h->P; ++j) {
+    if (j == skip) continue;
+    const int tj = j == ov ? ov_t : ty[j];
+    const double qj = j == ov ? ov_q : q[j];
+    if (tj >= h->T) continue;
+    const double *xj = X(h, r, j);
+    double d0 = min_image(xb[0] - xj[0], c->box_l), d1 = min_image(xb[1] - xj[1], c->box_l), d2 = min_image(xb[2] - xj[2], c->box_l);
+    double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+    if (r2 < best) best = r2;
+    if (c->use_wca) e += wca(c->wca_eps[tb * CGPE_MAX_TYPES + tj], c->wca_sig[tb * CGPE_MAX_TYPES + tj], r2, &fr);
+    if (c->use_dh && qj != 0.0) e += dh(c->dh_prefactor * qb * qj, h->kappa[r], h->rcut[r], r2, &fr);
+  }
+  *dmin2 = best;
+  return e;
+}
+
+static double unit_open(uint32_t x) { return ((double)(x >> 8) + 0.5) * (1.0 / 16777216.0); } /* (0,1) */
+
 static void mc_run_replica_follow(orc_handle *h, int r, int m, int n_trials, cgpe_trial_record *trace,
                                   const cgpe_trial_record *follow, double tie_tol, int32_t *n_ties) {
   const cgpe_reaction *rx = &h->cfg.reactions[m];
@@ -772,14 +824,44 @@ static void mc_run_replica_follow(orc_handle *h, int r, int m, int n_trials, cgp
     int32_t *src = forward ? l->prot : l->deprot, *dst = forward ? l->deprot : l->prot;
     int32_t *n_src = forward ? &l->n_prot : &l->n_deprot, *n_dst = forward ? &l->n_deprot : &l->n_prot;
     cgpe_trial_record rec = {-1, -1, (int8_t)(forward ? 1 : -1), 0, 0, 0, 0.f, 0.f, (float)u24(o[2])};
-    if (*n_src > 0) {
+    const int explicit_ions = h->cfg.n_ion_slots > 0;
+    const int ni = explicit_ions ? h->cfg.n_ion_slots : 1;
+    int32_t *ion_active = h->ion_active + (size_t)r * ni, *ion_free = h->ion_free + (size_t)r * ni;
+    /* all reactant particles must exist (backward also needs a free H+ to take; forward a spare slot) */
+    int possible = *n_src > 0;
+    if (explicit_ions && !forward && h->n_active[r] == 0) possible = 0;
+    if (explicit_ions && forward && h->n_free[r] == 0) possible = 0;
+    if (possible) {
       const uint32_t k = mulhi32(o[1], (uint32_t)*n_src);
       const int i = src[k];
       const int t_old = forward ? rx->type_prot : rx->type_deprot, t_new = forward ? rx->type_deprot : rx->type_prot;
       const double q_old = q[i], q_new = forward ? rx->q_deprot : rx->q_prot;
-      const double de = site_delta_e(h, r, i, t_old, t_new, q_old, q_new);
+      double de = site_delta_e(h, r, i, t_old, t_new, q_old, q_new);
+      int b = -1, kb = 0, excluded = 0;
+      double xb[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
+      if (explicit_ions) {
+        double dmin2;
+        if (forward) { /* insert one B at a uniform position with a Maxwell-Boltzmann velocity */
+          uint32_t c1[4] = {ctr[0], ctr[1], 1u, ctr[3]}, c2[4] = {ctr[0], ctr[1], 2u, ctr[3]}, o1[4], o2[4];
+          philox4x32_10(c1, key, o1);
+          philox4x32_10(c2, key, o2);
+          b = ion_free[h->n_free[r] - 1];
+          for (int a = 0; a < 3; ++a) xb[a] = u24(o1[a]) * h->cfg.box_l;
+          const double s = sqrt(rx->kT), ra = sqrt(-2.0 * log(unit_open(o2[0]))), rb = sqrt(-2.0 * log(unit_open(o2[2])));
+          vb[0] = s * ra * cos(6.283185307179586 * unit_open(o2[1]));
+          vb[1] = s * ra * sin(6.283185307179586 * unit_open(o2[1]));
+          vb[2] = s * rb * cos(6.283185307179586 * unit_open(o2[3]));
+          de += ion_energy(h, r, xb, rx->type_ion, rx->q_ion, b, i, t_new, q_new, &dmin2);
+        } else {       /* take a random free B away */
+          kb = (int)mulhi32(o[3], (uint32_t)h->n_active[r]);
+          b = ion_active[kb];
+          de -= ion_energy(h, r, X(h, r, b), rx->type_ion, rx->q_ion, b, i, t_new, q_new, &dmin2);
+        }
+        excluded = dmin2 < rx->exclusion_range * rx->exclusion_range;
+        rec.ion_slot = b; rec.excluded = (int8_t)excluded;
+      }
       const double nu = forward ? 1.0 : -1.0;
-      const double bf = (double)(*n_src) / (double)(*n_dst + 1) *
+      const double bf = excluded ? 0.0 : (double)(*n_src) / (double)(*n_dst + 1) *
                         exp(-de / rx->kT + nu * ORC_LN10 * (h->pH[r] - rx->pK));
       const double u = u24(o[2]);
       rec.particle = i; rec.delta_e = (float)de; rec.bf = (float)bf;
@@ -793,6 +875,21 @@ static void mc_run_replica_follow(orc_handle *h, int r, int m, int n_trials, cgp
         ty[i] = (uint8_t)t_new; q[i] = q_new;
         src[k] = src[*n_src - 1]; *n_src -= 1; /* swap-remove */
         dst[*n_dst] = i; *n_dst += 1;
+        if (explicit_ions) {
+          double *xs = h->x + ((size_t)r * h->P + b) * 3, *vs = h->v + ((size_t)r * h->P + b) * 3;
+          if (forward) {
+            ty[b] = (uint8_t)rx->type_ion; q[b] = rx->q_ion;
+            for (int a = 0; a < 3; ++a) { xs[a] = xb[a]; vs[a] = vb[a]; }
+            h->n_free[r] -= 1;
+            ion_active[h->n_active[r]++] = b;
+          } else {
+            ty[b] = (uint8_t)h->T; q[b] = 0.0; /* the non-interacting type (M.py:256-261), then gone */
+            vs[0] = vs[1] = vs[2] = 0.0;
+            ion_active[kb] = ion_active[h->n_active[r] - 1]; h->n_active[r] -= 1;
+            ion_free[h->n_free[r]++] = b;
+          }
+          h->lists_valid[r] = 0;
+        }
         *acc += 1;
         rec.accepted = 1;
       }
@@ -852,9 +949,10 @@ static void observables_replica(const orc_handle *h, int r, double *rg, double *
   counts[0] = counts[1] = counts[2] = 0;
   for (int m = 0; m < h->cfg.n_reactions && m < 2; ++m)
     counts[m] = h->lists[(size_t)r * h->cfg.n_reactions + m].n_deprot;
-  /* implicit ions: every deprotonated site has released one (virtual) H+ : N_B = N_N + N_N2 */
-  for (int m = 0; m < h->cfg.n_reactions; ++m)
-    counts[2] += h->lists[(size_t)r * h->cfg.n_reactions + m].n_deprot;
+  if (h->cfg.n_ion_slots > 0) counts[2] = h->n_active[r]; /* number_of_particles(type=B), E.py:99 */
+  else /* implicit ions: every deprotonated site has released one (virtual) H+ : N_B = N_N + N_N2 */
+    for (int m = 0; m < h->cfg.n_reactions; ++m)
+      counts[2] += h->lists[(size_t)r * h->cfg.n_reactions + m].n_deprot;
 }
 
 int orc_observables(orc_handle *h, double *rg, double *ree, int32_t *counts) {
@@ -910,6 +1008,7 @@ int orc_min_dist(orc_handle *h, double *out) {
   for (int r = 0; r < h->R; ++r) {
     double best = INFINITY;
     for (int i = 0; i < h->P; ++i) for (int j = i + 1; j < h->P; ++j) {
+      if (h->type[(size_t)r * h->P + i] >= h->T || h->type[(size_t)r * h->P + j] >= h->T) continue; /* hidden slots */
       const double *a = X(h, r, i), *b = X(h, r, j);
       double d0 = min_image(a[0] - b[0], h->cfg.box_l), d1 = min_image(a[1] - b[1], h->cfg.box_l),
              d2 = min_image(a[2] - b[2], h->cfg.box_l);

@@ -7,12 +7,12 @@ import numpy as np
 from coarse_grain_polyelectrolyte_b200 import workloads
 
 
-def make_workload(n_mon, pH, c_salt=2e-2, flags=None, replica_offset=0, seed=12, **cfg_overrides):
+def make_workload(n_mon, pH, c_salt=2e-2, flags=None, replica_offset=0, seed=12, explicit_ions=False, **cfg_overrides):
     params = workloads.example_parameters(n_mon, c_salt=c_salt)
     if flags:
         params = copy.deepcopy(params)
         params["Simulation configuration"].update(flags)
-    w = workloads.Workload(params, pH=pH, replica_offset=replica_offset, seed=seed)
+    w = workloads.Workload(params, pH=pH, replica_offset=replica_offset, seed=seed, explicit_ions=explicit_ions)
     for k, v in cfg_overrides.items():
         setattr(w.cfg, k, v)
     return w

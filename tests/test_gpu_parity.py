@@ -308,3 +308,103 @@ def test_wide_engine_sample_loop_and_steepest_descent(Engine, oracle_mod):
     assert np.median(dx) < 2e-5 and np.percentile(dx, 99.9) < 1e-4 and dx.max() < 2e-3
     s = g.list_stats()
     assert np.all(s[:, 0] > 0) and np.all(s[:, 1] <= s[:, 0]) and np.all(s[:, 3] <= s[:, 2])
+
+
+# ---- explicit ions (the reference's particle model, M.py:173-198) ---------------
+def _ion_state(w, seed, jitter=0.02):
+    """Start state with explicit ions: chain jittered, velocities thermal, sites as built (all
+    deprotonated, so N_B = N_N + N_N2 holds from the start)."""
+    rng = np.random.default_rng(seed)
+    R, P = w.R, w.xyzq.shape[0]
+    xyzq = np.broadcast_to(w.xyzq, (R, P, 4)).copy()
+    xyzq[:, :w.cfg.n_beads, :3] += rng.normal(scale=jitter, size=(R, w.cfg.n_beads, 3)).astype(np.float32)
+    vel = np.zeros((R, P, 4), np.float32)
+    vel[..., :3] = rng.normal(size=(R, P, 3))
+    return xyzq.astype(np.float32), vel, np.broadcast_to(w.type, (R, P)).copy()
+
+
+def _wrap_ions(x, w):
+    x = np.array(x, dtype=np.float64)
+    L = w.cfg.box_l
+    x[:, w.cfg.n_beads:] -= L * np.floor(x[:, w.cfg.n_beads:] / L)
+    return x
+
+
+def _ion_dx(xg, xo, w):
+    """max |dx| with ions compared modulo the box (the engine folds free particles, the oracle does not)"""
+    d = np.asarray(xg, np.float64) - xo
+    L = w.cfg.box_l
+    d[:, w.cfg.n_beads:] -= L * np.rint(d[:, w.cfg.n_beads:] / L)
+    return np.abs(d).max()
+
+
+def test_explicit_ions_energy_forces_md(Engine, oracle_mod):
+    w = make_workload(100, pH=[7.5, 9.0], explicit_ions=True)
+    assert w.cfg.n_ion_slots == 2 * 34 + 2 * 200 + 34
+    state = _ion_state(w, seed=3)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    eg, eo = g.energy(), o.energy()
+    scale = np.maximum(np.abs(eo), 1e-3 * np.abs(eo).max(axis=1, keepdims=True))
+    assert np.max(np.abs(eg - eo) / scale) < REL_TOL, (eg, eo)
+    fo = o.forces_f64()
+    for fg in (g.forces(), g.md_forces()):
+        assert np.abs(fg - fo).max() < REL_TOL * np.abs(fo).max()
+    np.testing.assert_allclose(g.min_dist(), o.min_dist(), rtol=1e-6)
+    for e in (g, o):
+        e.md_run(12)
+    xg, vg, tg = g.get_state()
+    xo, vo, _ = o.state_f64()
+    assert _ion_dx(xg[..., :3], xo, w) < 5e-5
+    hidden = tg >= w.cfg.n_types
+    assert np.all(vg[hidden][:, :3] == 0) and np.abs(vg[..., :3] - vo).max() < 5e-3
+
+
+def test_explicit_ions_trial_moves_bit_exact(Engine, oracle_mod):
+    """Insertion / deletion of H+ with exclusion range: same sites, ions, decisions and final state."""
+    w = make_workload(100, pH=[7.0, 8.2, 9.5], explicit_ions=True)
+    state = _ion_state(w, seed=5)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    n_excl = 0
+    for rx, n in ((0, 3000), (1, 400), (0, 1500)):
+        tg = g.mc_run(rx, n, trace=True)
+        to, ties = o.mc_run_follow(rx, tg, tie_tol=1e-4)
+        assert ties <= 2
+        for f in ("particle", "ion_slot", "direction", "accepted", "excluded", "u"):
+            np.testing.assert_array_equal(tg[f], to[f], err_msg=f)
+        tried = (to["particle"] >= 0) & (to["excluded"] == 0)
+        err = np.abs(tg["delta_e"][tried] - to["delta_e"][tried]) / np.maximum(np.abs(to["delta_e"][tried]), 1.0)
+        assert err.max() < REL_TOL
+        n_excl += int(to["excluded"].sum())
+        assert tg["accepted"].sum() > 0
+    assert n_excl > 0
+    xg, vg, tyg = g.get_state()
+    xo, vo, qo = o.state_f64()
+    _, _, tyo = o.get_state()
+    np.testing.assert_array_equal(tyg, tyo)
+    np.testing.assert_array_equal(xg[..., 3], qo.astype(np.float32))
+    assert _ion_dx(xg[..., :3], xo, w) < 1e-5                    # inserted ions sit where the oracle put them
+    assert np.abs(vg[..., :3] - vo).max() < 1e-5                  # with the same Maxwell-Boltzmann velocity
+    cg, co = g.observables()[2], o.observables()[2]
+    np.testing.assert_array_equal(cg, co)
+    np.testing.assert_array_equal(cg[:, 2], cg[:, 0] + cg[:, 1])  # N_B = N_N + N_N2 (NB:253-254)
+
+
+def test_explicit_ions_sample_loop(Engine, oracle_mod):
+    w = make_workload(60, pH=[8.0, 9.5], explicit_ions=True)
+    state = _ion_state(w, seed=9)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    sp = g.sample_params(16, md_steps_per_burst=5, use_md=True, mc_blocks=((0, 61), (1, 11)), p_burst1=0.7, p_burst2=0.3)
+    og, _ = g.sample_loop(sp)
+    oo, _ = o.sample_loop(sp)
+    np.testing.assert_array_equal(og[..., :3], oo[..., :3])
+    np.testing.assert_allclose(og[..., 3:5], oo[..., 3:5], rtol=2e-4)
+    np.testing.assert_array_equal(og[..., 2], og[..., 0] + og[..., 1])
+    assert len(np.unique(og[..., 2])) > 1
+
+
+def test_explicit_ion_configs_that_cannot_be_served_are_refused(Engine):
+    w = make_workload(100, pH=[8.0], explicit_ions=True)
+    w.cfg.reactions[0].exclusion_range = 0.1           # below the H+ WCA cutoff
+    with pytest.raises(_abi.CgpeError) as ei:
+        Engine(w.cfg)
+    assert ei.value.status == _abi.ERR_UNSUPPORTED
