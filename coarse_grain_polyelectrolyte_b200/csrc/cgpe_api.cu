@@ -259,16 +259,15 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   int rc = validate(cfg);
   if (rc) return rc;
   if (cfg->n_ion_slots > 0) {
-    if (cfg->n_reactions == 0) return fail(nullptr, CGPE_ERR_INVALID, "explicit ions need at least one reaction");
     double rc_ion = 0.0;   // largest WCA cutoff of the ion type
-    const int tb = cfg->reactions[0].type_ion;
+    const int tb = cfg->n_reactions > 0 ? cfg->reactions[0].type_ion : 0;
     for (int m = 0; m < cfg->n_reactions; ++m) {
       const cgpe_reaction &r = cfg->reactions[m];
       if (r.type_ion != tb || r.q_ion != cfg->reactions[0].q_ion || tb < 0 || tb >= cfg->n_types)
         return fail(nullptr, CGPE_ERR_INVALID, "explicit ions: all reactions must release the same ion type");
       if (tb == r.type_prot || tb == r.type_deprot) return fail(nullptr, CGPE_ERR_INVALID, "explicit ions: the ion type must differ from the site types");
     }
-    if (cfg->use_wca)
+    if (cfg->use_wca && cfg->n_reactions > 0)
       for (int t = 0; t < cfg->n_types; ++t)
         if (cfg->wca_eps[tb * CGPE_MAX_TYPES + t] > 0.0)
           rc_ion = std::fmax(rc_ion, 1.122462048309373 * cfg->wca_sig[tb * CGPE_MAX_TYPES + t]);
@@ -497,7 +496,7 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     xq_fix.assign(xyzq, xyzq + RP * 4);
     vel_fix.assign(vel ? vel : zero.data(), (vel ? vel : zero.data()) + RP * 4);
     std::vector<int> act((size_t)p.R * p.n_ions, 0), fre((size_t)p.R * p.n_ions, 0), icnt((size_t)p.R * 2, 0);
-    const int tb = h->cfg.reactions[0].type_ion;
+    const int tb = p.n_rx > 0 ? h->cfg.reactions[0].type_ion : -1;
     for (int r = 0; r < p.R; ++r)
       for (int i = p.NC; i < p.P; ++i) {
         const size_t k = (size_t)r * p.P + i;

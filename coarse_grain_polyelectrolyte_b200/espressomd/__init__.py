@@ -200,7 +200,10 @@ class _ParticleList:
         self._system = system
 
     def __len__(self):
-        return self._system._n_part
+        s = self._system
+        if s._hidden_type is None:
+            return s._n_part
+        return int((s._state()[2][0] < s._hidden_type).sum())     # hidden ion slots are not particles
 
     def add(self, id=None, pos=None, type=0, q=0.0, v=None, **unsupported):
         """Scalar form (M.py:130-155) and vectorised form (M.py:175-198)."""
@@ -394,6 +397,7 @@ class System:
         self._reactions = []                    # reaction_methods._Registered
         self._engine = None
         self._engine_particles = 0
+        self._hidden_type = None               # type index of hidden (non-interacting) ion slots once they exist
         self._state_cache = None
         _current_system = self
 
@@ -527,17 +531,34 @@ class System:
             raise RuntimeError("system.time_step must be set before integrating")
         n_chains, n_beads, bond_t, ang_t, dih_t = self._topology()
         n_chain = n_chains * n_beads
-        if self._n_part > n_chain:
-            raise NotImplementedError(
-                f"{self._n_part - n_chain} free particles (explicit ions) are present: this build runs the implicit-ion "
-                "model (Debye-Hueckel screening, chain only); see DESIGN.md 'scope'")
         if self._n_part < n_chain:
             raise RuntimeError("bond records reference particles that were not added")
-        T = int(max(self._wca_eps.shape[0], self._type.max(initial=0) + 1,
-                    max([max(r.type_prot, r.type_deprot) + 1 for r in self._reactions], default=1)))
+        real = self._type if self._hidden_type is None else self._type[self._type != self._hidden_type]
+        T = int(max(self._wca_eps.shape[0], real.max(initial=0) + 1,
+                    max([max(r.type_prot, r.type_deprot, r.type_ion) + 1 for r in self._reactions], default=1)))
+        if self._hidden_type is not None and T != self._hidden_type:
+            raise NotImplementedError("particle types cannot be added once hidden ion slots exist")
+        # free particles (explicit ions, M.py:173-198) live in ion slots behind the chain; one spare
+        # hidden slot per titratable site lets every site release its H+ (ESPResSo creates particles
+        # on demand; here the pool is sized up front)
+        if self._n_part > n_chain:
+            reactive = {t for r in self._reactions for t in (r.type_prot, r.type_deprot)}
+            n_sites = int(sum(int(t) in reactive for t in self._type[:n_chain]))
+            n_hidden = 0 if self._hidden_type is None else int((self._type == self._hidden_type).sum())
+            n_spare = max(0, n_sites - n_hidden)
+            if n_spare > 0:
+                self._hidden_type = T
+                self._pos = np.concatenate([self._pos, np.zeros((n_spare, 3))]); self._vel = np.concatenate([self._vel, np.zeros((n_spare, 3))])
+                self._type = np.concatenate([self._type, np.full(n_spare, T, np.int64)]); self._q = np.concatenate([self._q, np.zeros(n_spare)])
+                self._n_part = len(self._type)
+        n_ion_slots = self._n_part - n_chain
+        if n_ion_slots > 0 and n_chain + n_ion_slots > 2048:
+            raise NotImplementedError(
+                f"{n_ion_slots} free particles (explicit ions) + {n_chain} chain beads exceed the 2048 particles the "
+                "explicit-ion engine holds per replica; use ION_MODEL='implicit' (Debye-Hueckel screening only)")
         kw = dict(
             n_replicas=self.n_replicas, replica_offset=self.replica_offset, n_chains=n_chains, n_beads=n_beads,
-            n_ion_slots=0, n_types=T, device=self._device, skin=self._engine_skin,
+            n_ion_slots=n_ion_slots, n_types=T, device=self._device, skin=self._engine_skin,
             box_l=float(self.box_l[0]), time_step=float(self.time_step),
             bond_kind=_abi.BOND_NONE, use_angle=0, use_dihedral=0, use_wca=int(self._use_wca), use_dh=0,
             wca_eps=self._wca_eps, wca_sig=self._wca_sig,

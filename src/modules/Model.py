@@ -10,8 +10,8 @@ Beyond the reference:
     pH x ionic-strength grid (the reference loops over pH values serially, notebook cell 4);
   * "Simulation configuration" may carry "ION_MODEL": "implicit" (default here: the chain alone,
     small ions only through the Debye-Hueckel screening, as BASELINE.json's north star describes)
-    or "explicit" (the reference's B+/Na+/Cl- particles, M.py:173-198; not yet served by the
-    engine, which says so when first asked to integrate).
+    or "explicit" (the reference's B+/Na+/Cl- particles with H+ insertion / deletion,
+    M.py:173-198; served for systems of up to 2048 particles per replica).
 """
 import numpy as np
 

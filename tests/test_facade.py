@@ -68,11 +68,11 @@ def test_particles_and_topology():
     cfg = s._build_config()
     assert cfg.n_beads == 12 and cfg.bond_kind == _abi.BOND_HARMONIC and cfg.use_angle == 1 and cfg.use_dihedral == 1
     assert cfg.dihedral_mult == 3 and cfg.angle_phi0 == pytest.approx(2 * math.pi / 3)
-    # vectorised add of free particles = explicit ions: refused with a clear message
+    # vectorised add of free particles = explicit ions: they go to ion slots behind the chain
     s.part.add(pos=np.random.random((5, 3)) * 30, type=[2] * 5, q=[1.0] * 5)
     assert len(s.part) == 17
-    with pytest.raises(NotImplementedError, match="explicit ions"):
-        s._build_config()
+    cfg = s._build_config()
+    assert cfg.n_ion_slots == 5 and cfg.n_beads == 12
 
 
 def test_unsupported_topologies_are_refused():

@@ -96,9 +96,29 @@ def test_ensemble_dynamics_batched_titration():
     assert ens.rad_gyr[0].mean() > ens.rad_gyr[-1].mean()
 
 
-def test_explicit_ion_model_is_refused_loudly():
+def test_explicit_ion_model_end_to_end():
+    """ION_MODEL = "explicit": the reference's own particle model (B+, Na+, Cl- particles; H+ inserted and
+    deleted by the reaction, M.py:173-261) through the same driver calls."""
+    from modules.EnsembleDynamics import EnsembleDynamics
+    p = small_run_parameters(n_mon=40)
+    p["Simulation configuration"]["ION_MODEL"] = "explicit"
+    ens = EnsembleDynamics(p)
+    tp = ens.type_particles
+    n0 = len(ens.system.part)
+    assert n0 == 40 + 2 * ens.n_acid + 2 * ens.n_salt                              # M.py:175-198
+    assert ens.system.number_of_particles(type=tp["B"]) == ens.n_acid
+    ens.equilibrate_pH(6.0)
+    ens.perform_sampling(0)
+    np.testing.assert_array_equal(ens.num_B, ens.num_As + ens.num_As2)               # NB:253-254
+    assert ens.system.number_of_particles(type=tp["B"]) == ens.num_B[-1]
+    assert len(ens.system.part) == n0 - (ens.n_acid - int(ens.num_B[-1]))             # consumed H+ are gone
+    assert ens.num_As.mean() / ens.n_nh < 0.3                                         # pH 6 << pK1: mostly protonated
+    assert np.all(np.isfinite(ens.rad_gyr)) and ens.times[-1] > 0
+
+
+def test_explicit_ion_model_too_large_is_refused_loudly():
     from modules.Model import Model
-    p = small_run_parameters()
+    p = small_run_parameters(n_mon=1000)
     p["Simulation configuration"]["ION_MODEL"] = "explicit"
     with pytest.raises(NotImplementedError, match="explicit ions"):
         Model(p)
