@@ -6,6 +6,8 @@ charge-state bookkeeping bit-exact for identical proposal sequences.  Relative f
 measured against the largest force in the configuration (a per-component ratio is meaningless
 where a component passes through zero).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -408,3 +410,42 @@ def test_explicit_ion_configs_that_cannot_be_served_are_refused(Engine):
     with pytest.raises(_abi.CgpeError) as ei:
         Engine(w.cfg)
     assert ei.value.status == _abi.ERR_UNSUPPORTED
+
+
+def _binning_sem(x, n_bins=10):
+    n = (x.shape[-1] // n_bins) * n_bins
+    means = x[..., :n].reshape(x.shape[:-1] + (n_bins, -1)).mean(axis=-1)
+    return means.std(axis=-1, ddof=1) / np.sqrt(n_bins)
+
+
+def test_ensemble_observables_agree_within_error_bars(Engine, oracle_mod):
+    """Third correctness criterion of the north star: alpha(pH), <Rg>, <Ree> of the interacting chain
+    from the CUDA path and from the FP64 oracle, run with DIFFERENT random streams (independent Markov
+    chains), agree within their binning-analysis error bars."""
+    pH = np.array([6.5, 7.5, 8.2, 9.0, 10.5])
+    oracle_mod.set_threads(os.cpu_count() or 1)
+    results = {}
+    # a short chain (Rouse time ~ 20 time units) and 0.25 time units of MD per sample: the 1600 samples
+    # span ~ 400 time units, so Rg / Ree decorrelate many times and the binning error bars are honest
+    for name, seed_shift in (("gpu", 0), ("oracle", 1000)):
+        # no dihedral term here: its 13 kT barriers (k = 6.57 kT) freeze the torsions over any affordable
+        # run, so <Rg> would depend on the initial torsion sequence of each independent chain
+        w = make_workload(24, pH=pH, replica_offset=seed_shift, flags={"USE_DIHEDRAL_POT": False})
+        e = Engine(w.cfg) if name == "gpu" else oracle_mod.OracleEngine(w.cfg)
+        w.init_engine(e)
+        n1, n2 = w.n_sites
+        kw = dict(md_steps_per_burst=250, use_md=True, mc_blocks=((0, 5 * n1 + 1), (1, 5 * n2 + 1)), p_burst1=1.0, p_burst2=0.0)
+        e.sample_loop(e.sample_params(200, **kw))                      # equilibration
+        obs, _ = e.sample_loop(e.sample_params(1600, **kw))
+        results[name] = (obs, n1)
+    oracle_mod.set_threads(1)
+    (og, n1), (oo, _) = results["gpu"], results["oracle"]
+    for col, scale, label in ((0, n1, "alpha"), (3, 1.0, "Rg"), (4, 1.0, "Ree")):
+        mg, mo = og[..., col].mean(axis=1) / scale, oo[..., col].mean(axis=1) / scale
+        sg, so = _binning_sem(og[..., col]) / scale, _binning_sem(oo[..., col]) / scale
+        sigma = np.sqrt(sg ** 2 + so ** 2) + 2e-3 * np.abs(mo)
+        z = np.abs(mg - mo) / sigma
+        assert np.all(z < 4.5), (label, mg, mo, sigma, z)
+    # and the physics is the expected one: titration curve monotone, charged chain more extended
+    alpha = og[..., 0].mean(axis=1) / n1
+    assert np.all(np.diff(alpha) > 0) and alpha[0] < 0.4 and alpha[-1] > 0.97
