@@ -194,6 +194,8 @@ def main():
     if args.impl == "reference":
         return main_reference(args, rank, world)
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout; this script prints ONE line there
     import torch
     import torch.distributed as dist
     from coarse_grain_polyelectrolyte_b200.engine import Engine
