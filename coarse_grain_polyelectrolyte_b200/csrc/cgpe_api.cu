@@ -21,6 +21,7 @@ struct cgpe_handle {
   bool wide;
   std::vector<void *> wide_allocs;
   std::vector<int> chg_host;   // [R][n_chg] chargeable particle ids (host copy)
+  WideGraphCache wgraph;       // captured block of MD steps of the global-memory engine
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
   int device;
@@ -186,6 +187,7 @@ int require_engine(cgpe_handle *h) {
 }
 
 void free_wide(cgpe_handle *h) {
+  if (h->wgraph.exec) { cudaStreamSynchronize(h->stream); wide_graph_release(&h->wgraph); }
   for (void *ptr : h->wide_allocs) cudaFree(ptr);
   h->wide_allocs.clear();
   h->wide = false;
@@ -216,10 +218,12 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
   CU(alloc((void **)&w.wn, sizeof(int) * RP));
   CU(alloc((void **)&w.dl, sizeof(uint32_t) * RC * w.cap_d));
   CU(alloc((void **)&w.dn, sizeof(int) * RC));
+  CU(alloc((void **)&w.fdh, sizeof(float4) * RC));
   CU(alloc((void **)&w.cidx, sizeof(int) * RP));
   CU(alloc((void **)&w.flag, sizeof(int) * p.R));
   CU(alloc((void **)&w.nsteps, sizeof(int) * p.R));
   CU(alloc((void **)&w.sched_max, sizeof(int)));
+  CU(alloc((void **)&w.step, 2 * sizeof(int)));
   CU(alloc((void **)&w.phi, sizeof(float) * RC));
   CU(alloc((void **)&w.wcache, sizeof(float) * RC));
   CU(alloc((void **)&w.rxof, RC));
@@ -379,6 +383,7 @@ void cgpe_destroy(cgpe_handle *h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  wide_graph_release(&h->wgraph);
   for (void *ptr : h->allocs) cudaFree(ptr);
   for (void *ptr : h->wide_allocs) cudaFree(ptr);
   if (h->d_obs) cudaFree(h->d_obs);
@@ -645,7 +650,7 @@ int cgpe_md_run(cgpe_handle *h, int32_t n_steps) {
   DeviceGuard guard(h->device);
   begin_timing(h);
   int launches = 1;
-  if (h->wide) { launches = 0; CU(wide_md_run(h->p, h->g, h->w, n_steps, h->stream, &launches)); }
+  if (h->wide) { launches = 0; CU(wide_md_run(h->p, h->g, h->w, n_steps, h->stream, &launches, &h->wgraph)); }
   else CU(launch_md_run(h->p, h->g, h->launch, n_steps, h->stream));
   end_timing(h, launches);
   return CGPE_OK;
@@ -730,7 +735,7 @@ int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp) {
   if (h->wide) {
     launches = 0;
     CU(wide_sample_loop(h->p, h->g, h->w, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
-                        h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->d_tmp_d, h->d_tmp_i, h->stream, &launches));
+                        h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->d_tmp_d, h->d_tmp_i, h->stream, &launches, &h->wgraph));
   } else {
     CU(launch_sample_loop(h->p, h->g, h->launch, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                           h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));

@@ -14,10 +14,14 @@
 // forces differs.  Reference call sites: see chain_engine.cu.
 #include "wide_engine.cuh"
 
+#include <cstring>
+
 namespace cgpe {
 namespace {
 
 constexpr int kWT = 256;   // threads per CTA
+constexpr int kStepFromDevice = -1000;   // kernels of a captured step read the step index from WideState::step
+constexpr int kGraphChunk = 25;          // MD steps per captured graph
 
 __device__ __forceinline__ float wdist2(const DevParams &p, float4 a, float4 b, V3 *d) {
   d->x = min_image(a.x - b.x, p.box_l, p.inv_box_l);
@@ -35,6 +39,7 @@ __global__ void __launch_bounds__(kWT)
 wk_drift(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
          int step, float sd_gamma, float sd_max_disp) {
   const int r = blockIdx.y, i = blockIdx.x * kWT + threadIdx.x;
+  if (step == kStepFromDevice) step = w.step[0];
   if (step >= w.nsteps[r] || i >= p.P) return;
   const size_t k = (size_t)r * p.P + i;
   float4 x = g.pos[k];
@@ -57,6 +62,7 @@ wk_drift(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
 __global__ void __launch_bounds__(kWT)
 wk_rebuild(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w) {
   const int r = blockIdx.y, i = blockIdx.x * kWT + threadIdx.x;
+  if (r == 0 && i == 0) w.step[1] = w.step[0];   // the force kernels of this step read step[1]
   if (!w.flag[r]) return;
   __shared__ float4 tile[kWT];
   const size_t base = (size_t)r * p.P;
@@ -67,7 +73,8 @@ wk_rebuild(const __grid_constant__ DevParams p, const __grid_constant__ DevState
   if (l >= 0) { ex_lo = i - min(2, l); ex_hi = i + min(2, p.N - 1 - l); }
   const float rc = g.rcut[r], rlist_d2 = (rc + p.skin) * (rc + p.skin);
   int nw = 0, nd = 0;
-  uint32_t *wl = w.wl + (size_t)r * w.cap_w * p.P, *dl = w.dl + (size_t)r * w.cap_d * p.n_chg;
+  uint32_t *wl = w.wl + (size_t)r * w.cap_w * p.P;
+  uint32_t *dl = w.dl + ((size_t)r * p.n_chg + (ci >= 0 ? ci : 0)) * w.cap_d;   // this site's row
   for (int j0 = 0; j0 < p.P; j0 += kWT) {
     __syncthreads();
     if (j0 + threadIdx.x < p.P) tile[threadIdx.x] = g.pos[base + j0 + threadIdx.x];
@@ -85,7 +92,7 @@ wk_rebuild(const __grid_constant__ DevParams p, const __grid_constant__ DevState
       if (p.use_dh && ci >= 0 && r2 < rlist_d2 && j != i) {
         const int cj = w.cidx[base + j];
         if (cj >= 0) {
-          if (nd < w.cap_d) dl[(size_t)nd * p.n_chg + ci] = (uint32_t)cj;
+          if (nd < w.cap_d) dl[nd] = (uint32_t)cj;
           ++nd;
         }
       }
@@ -100,11 +107,56 @@ wk_rebuild(const __grid_constant__ DevParams p, const __grid_constant__ DevState
   if (i == 0) g.rebuilds[r] += 1;
 }
 
+// Debye-Hueckel force (mode 0) or potential sum_j q_j e(r) (mode 1) of every chargeable particle:
+// one warp per site, lanes stride over its contiguous row, warp-shuffle reduction.
+__global__ void __launch_bounds__(kWT)
+wk_dh_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
+           int step, int mode) {
+  const int r = blockIdx.y, lane = threadIdx.x & 31, ci = blockIdx.x * (kWT / 32) + (threadIdx.x >> 5);
+  if (step == kStepFromDevice) step = w.step[1];
+  if (mode == 0 && step >= w.nsteps[r]) return;
+  if (ci >= p.n_chg) return;
+  const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
+  const int *chg = g.chg + cb;
+  const float4 pi4 = g.pos[base + chg[ci]];
+  float fx = 0.f, fy = 0.f, fz = 0.f, ph = 0.f;
+  if (mode == 1 || pi4.w != 0.f) {
+    const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
+    const uint32_t *row = w.dl + (cb + ci) * w.cap_d;
+    const int n = w.dn[cb + ci];
+    for (int e = lane; e < n; e += 32) {
+      const float4 pj4 = g.pos[base + chg[row[e]]];
+      if (pj4.w == 0.f) continue;
+      V3 d;
+      const float r2 = wdist2(p, pi4, pj4, &d);
+      if (r2 < rc2) {
+        float fr;
+        const float en = dh_energy_unit(r2, kappa, nkl, &fr);
+        ph = fmaf(pj4.w, en, ph);
+        fr *= pj4.w;
+        fx = fmaf(fr, d.x, fx); fy = fmaf(fr, d.y, fy); fz = fmaf(fr, d.z, fz);
+      }
+    }
+  }
+  if (mode == 1) {
+    ph = warp_sum(ph);
+    if (lane == 0) w.phi[cb + ci] = ph;
+  } else {
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    const float s = p.dh_pref * pi4.w;
+    if (lane == 0) w.fdh[cb + ci] = make_float4(s * fx, s * fy, s * fz, 0.f);
+  }
+}
+
 // mode: 0 = forces only (initial evaluation / md_forces / steepest descent), 1 = forces + second half kick
 __global__ void __launch_bounds__(kWT)
 wk_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
           int step, int mode, int thermostat, float4 *out) {
   const int r = blockIdx.y, i = blockIdx.x * kWT + threadIdx.x;
+  if (step == kStepFromDevice) {
+    step = w.step[1];
+    if (r == 0 && i == 0) w.step[0] = step + 1;   // nothing in this launch reads step[0]; the next drift does
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) w.flag[r] = 0;   // every block of wk_rebuild has seen it
   if (step >= w.nsteps[r]) return;
   if (mode == 0 && step < 0 && g.f_valid[r] && !out) return;   // cached forces are still good
@@ -161,22 +213,9 @@ wk_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState 
     }
   }
   const int ci = w.cidx[base + i];
-  if (p.use_dh && ci >= 0 && pi4.w != 0.f) {
-    const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e, qi = p.dh_pref * pi4.w;
-    const uint32_t *dl = w.dl + (size_t)r * w.cap_d * p.n_chg;
-    const int *chg = g.chg + (size_t)r * p.n_chg;
-    const int n = w.dn[(size_t)r * p.n_chg + ci];
-    for (int e = 0; e < n; ++e) {
-      const float4 pj4 = pos[chg[dl[(size_t)e * p.n_chg + ci]]];
-      if (pj4.w == 0.f) continue;
-      V3 d;
-      const float r2 = wdist2(p, pi4, pj4, &d);
-      if (r2 < rc2) {
-        float fr;
-        dh_energy_unit(r2, kappa, nkl, &fr);
-        f = f + (qi * pj4.w * fr) * d;
-      }
-    }
+  if (p.use_dh && ci >= 0 && pi4.w != 0.f) {   // summed by wk_dh_forces, one warp per site
+    const float4 fd = w.fdh[(size_t)r * p.n_chg + ci];
+    f.x += fd.x; f.y += fd.y; f.z += fd.z;
   }
   float4 v = g.vel[base + i];
   if (thermostat && ti < p.T) {   // E.py:61-63
@@ -272,26 +311,8 @@ __global__ void __launch_bounds__(kWT)
 wk_mc_prepare(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w) {
   const int r = blockIdx.y, ci = blockIdx.x * kWT + threadIdx.x;
   if (ci >= p.n_chg) return;
-  const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
-  const int *chg = g.chg + cb;
-  const float4 pi4 = g.pos[base + chg[ci]];
-  float ph = 0.f;
-  if (p.use_dh) {
-    const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
-    const uint32_t *dl = w.dl + (size_t)r * w.cap_d * p.n_chg;
-    const int n = w.dn[cb + ci];
-    for (int e = 0; e < n; ++e) {
-      const float4 pj4 = g.pos[base + chg[dl[(size_t)e * p.n_chg + ci]]];
-      if (pj4.w == 0.f) continue;
-      V3 d;
-      const float r2 = wdist2(p, pi4, pj4, &d);
-      if (r2 < rc2) {
-        float fr;
-        ph = fmaf(pj4.w, dh_energy_unit(r2, kappa, nkl, &fr), ph);
-      }
-    }
-  }
-  w.phi[cb + ci] = ph;
+  const size_t cb = (size_t)r * p.n_chg;
+  if (!p.use_dh) w.phi[cb + ci] = 0.f;   // otherwise filled by wk_dh_rows(mode 1)
   bool tit;
   w.wcache[cb + ci] = wide_wca_swap(p, g, w, r, ci, &tit);
   w.wflag[cb + ci] = tit ? 1 : 0;
@@ -314,7 +335,6 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
   const uint32_t k0 = rx.seed, k1 = (uint32_t)(p.replica_offset + r);
   const unsigned long long trial_ctr = (unsigned long long)g.trials[(size_t)r * p.n_rx + m];
   cgpe_trial_record *trace = trace_all ? trace_all + (size_t)r * n_trials : nullptr;
-  const uint32_t *dl = w.dl + (size_t)r * w.cap_d * p.n_chg;
   const int *chg = g.chg + cb;
   long long acc = 0;
   for (int b0 = 0; b0 < n_trials; b0 += 32) {
@@ -355,8 +375,9 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
         acc += 1;
         if (p.use_dh && dq != 0.f) {
           const int n = w.dn[cb + ci];
+          const uint32_t *row = w.dl + (cb + ci) * w.cap_d;
           for (int e = lane; e < n; e += 32) {
-            const int ck = dl[(size_t)e * p.n_chg + ci];
+            const int ck = row[e];
             V3 d;
             const float r2 = wdist2(p, pi4, g.pos[base + chg[ck]], &d);
             if (r2 < rc2) {
@@ -451,9 +472,9 @@ wk_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
   const int ci = w.cidx[base + i];
   if (p.use_dh && ci >= 0) {
     const float rc = g.rcut[r];
-    const uint32_t *dl = w.dl + (size_t)r * w.cap_d * p.n_chg;
+    const uint32_t *row = w.dl + ((size_t)r * p.n_chg + ci) * w.cap_d;
     for (int e = 0; e < w.dn[(size_t)r * p.n_chg + ci]; ++e) {
-      const float4 pj4 = g.pos[base + g.chg[(size_t)r * p.n_chg + dl[(size_t)e * p.n_chg + ci]]];
+      const float4 pj4 = g.pos[base + g.chg[(size_t)r * p.n_chg + row[e]]];
       V3 d;
       a[2] += 1;
       if (pi4.w != 0.f && pj4.w != 0.f && wdist2(p, pi4, pj4, &d) < rc * rc) a[3] += 1;
@@ -463,6 +484,7 @@ wk_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
 }
 
 inline dim3 grid_particles(const DevParams &p) { return dim3((p.P + kWT - 1) / kWT, p.R); }
+inline dim3 grid_sites_warp(const DevParams &p) { const int per = kWT / 32; return dim3((p.n_chg + per - 1) / per > 0 ? (p.n_chg + per - 1) / per : 1, p.R); }
 inline dim3 grid_chargeable(const DevParams &p) { return dim3((p.n_chg + kWT - 1) / kWT > 0 ? (p.n_chg + kWT - 1) / kWT : 1, p.R); }
 
 #define WCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
@@ -476,29 +498,63 @@ cudaError_t set_ints(int *a, int n, int v, cudaStream_t st) {
 cudaError_t wide_prepare(const DevParams &p, const DevState &g, const WideState &w, int thermostat, cudaStream_t st, int *launches) {
   WCK(set_ints(w.flag, p.R, 1, st));
   wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, -1, 0);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, thermostat, nullptr);
-  *launches += 3;
+  *launches += 4;
   return cudaGetLastError();
 }
 
-cudaError_t wide_steps(const DevParams &p, const DevState &g, const WideState &w, int n_max, cudaStream_t st, int *launches) {
-  for (int s = 0; s < n_max; ++s) {
-    wk_drift<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, 0.f, 0.f);
-    wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
-    wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, 1, 1, nullptr);
+void launch_step(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st) {
+  wk_drift<<<grid_particles(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 0.f, 0.f);
+  wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 0);
+  wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 1, 1, nullptr);
+}
+
+// n_max velocity-Verlet steps for all replicas (replica r takes part in the first nsteps[r]).  The
+// step is launch-bound (4 short kernels), so blocks of kGraphChunk steps are captured once into a
+// CUDA graph and replayed; the kernels read the running step index from device memory.
+cudaError_t wide_steps(const DevParams &p, const DevState &g, const WideState &w, int n_max, cudaStream_t st, int *launches,
+                       WideGraphCache *gc) {
+  WCK(cudaMemsetAsync(w.step, 0, 2 * sizeof(int), st));
+  int done = 0;
+  if (gc && n_max >= 2 * kGraphChunk) {
+    if (gc->exec && (gc->chunk != kGraphChunk || std::memcmp(&gc->p_key, &p, sizeof(DevParams)) != 0)) {
+      WCK(cudaStreamSynchronize(st));
+      wide_graph_release(gc);
+    }
+    if (!gc->exec) {
+      cudaGraph_t graph = nullptr;
+      WCK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      for (int s = 0; s < kGraphChunk; ++s) launch_step(p, g, w, st);
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (e != cudaSuccess) return e;
+      e = cudaGraphInstantiate(&gc->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { gc->exec = nullptr; return e; }
+      gc->p_key = p;
+      gc->chunk = kGraphChunk;
+    }
+    for (; done + kGraphChunk <= n_max; done += kGraphChunk) WCK(cudaGraphLaunch(gc->exec, st));
   }
-  *launches += 3 * n_max;
+  for (; done < n_max; ++done) launch_step(p, g, w, st);
+  *launches += (p.use_dh ? 4 : 3) * n_max;
   return cudaGetLastError();
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-cudaError_t wide_md_run(const DevParams &p, const DevState &g, const WideState &w, int n_steps, cudaStream_t st, int *launches) {
+void wide_graph_release(WideGraphCache *c) {
+  if (c && c->exec) { cudaGraphExecDestroy(c->exec); c->exec = nullptr; }
+}
+
+cudaError_t wide_md_run(const DevParams &p, const DevState &g, const WideState &w, int n_steps, cudaStream_t st, int *launches,
+                        WideGraphCache *gc) {
   if (n_steps <= 0) return cudaSuccess;
   WCK(set_ints(w.nsteps, p.R, n_steps, st));
   WCK(wide_prepare(p, g, w, 1, st, launches));
-  WCK(wide_steps(p, g, w, n_steps, st, launches));
+  WCK(wide_steps(p, g, w, n_steps, st, launches, gc));
   wk_finish_md<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, n_steps, 1);
   *launches += 2;
   return cudaGetLastError();
@@ -513,9 +569,10 @@ cudaError_t wide_steepest_descent(const DevParams &p, const DevState &g, const W
   for (int s = 0; s < n_steps; ++s) {
     wk_drift<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, gamma, max_disp);
     wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+    if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, s, 0);
     wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, 0, 0, nullptr);
   }
-  *launches += 3 * n_steps + 1;
+  *launches += 4 * n_steps + 1;
   wk_finish_md<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, 0, 0);
   return cudaGetLastError();
 }
@@ -524,6 +581,7 @@ cudaError_t wide_md_forces(const DevParams &p, const DevState &g, const WideStat
   WCK(set_ints(w.nsteps, p.R, 1, st));
   WCK(set_ints(w.flag, p.R, 1, st));
   wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, 0, 0);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, 0, 0, 0, out);
   return cudaGetLastError();
 }
@@ -531,6 +589,7 @@ cudaError_t wide_md_forces(const DevParams &p, const DevState &g, const WideStat
 static cudaError_t wide_mc_blocks(const DevParams &p, const DevState &g, const WideState &w, int n_blocks, const int *rx,
                                   const int *trials, cgpe_trial_record *trace, cudaStream_t st, int *launches) {
   wk_mc_classify<<<grid_chargeable(p), kWT, 0, st>>>(p, g, w);
+  if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, 0, 1);
   wk_mc_prepare<<<grid_chargeable(p), kWT, 0, st>>>(p, g, w);
   for (int b = 0; b < n_blocks; ++b)
     if (trials[b] > 0) wk_mc_block<<<p.R, 32, 0, st>>>(p, g, w, rx[b], trials[b], trace);
@@ -560,7 +619,7 @@ cudaError_t wide_list_stats(const DevParams &p, const DevState &g, const WideSta
 // perform_sampling (E.py:88-106), host-driven: one 4-byte read-back per sample (longest burst)
 cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideState &w, const cgpe_sample_params &sp,
                              uint32_t thr1, uint32_t thr2, double *obs, float *qdist, double *tmp_d, int *tmp_i,
-                             cudaStream_t st, int *launches) {
+                             cudaStream_t st, int *launches, WideGraphCache *gc) {
   WCK(set_ints(w.nsteps, p.R, 0, st));
   WCK(set_ints(w.flag, p.R, 1, st));
   wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
@@ -574,8 +633,9 @@ cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideSt
     WCK(cudaStreamSynchronize(st));
     *launches += 1;
     if (n_max > 0) {
+      if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, -1, 0);
       wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, 1, nullptr);   // stale forces only
-      WCK(wide_steps(p, g, w, n_max, st, launches));
+      WCK(wide_steps(p, g, w, n_max, st, launches, gc));
       wk_finish_md<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, -1, 1);
       *launches += 2;
     }

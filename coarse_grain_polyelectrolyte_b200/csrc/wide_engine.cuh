@@ -9,12 +9,14 @@ struct WideState {
   float4 *ref;        // [R][P] positions at the last list build
   uint32_t *wl;       // [R][cap_w][P] WCA Verlet rows (particle ids), column per particle
   int *wn;            // [R][P]
-  uint32_t *dl;       // [R][cap_d][n_chg] Debye-Hueckel rows (chargeable indices)
+  uint32_t *dl;       // [R][n_chg][cap_d] Debye-Hueckel rows (chargeable indices), one contiguous row per site
+  float4 *fdh;        // [R][n_chg] Debye-Hueckel force on each chargeable particle (wk_dh_forces)
   int *dn;            // [R][n_chg]
   int *cidx;          // [R][P] particle -> chargeable index, -1 = never charged
   int *flag;          // [R] list rebuild vote
   int *nsteps;        // [R] MD steps of the current burst
   int *sched_max;     // [1] longest burst of the current sample
+  int *step;          // [2] step index read by the kernels of a captured step (graph replay)
   float *phi;         // [R][n_chg] per-site Debye-Hueckel potential (see chain_engine.cu, mc_prepare)
   float *wcache;      // [R][n_chg] WCA type-swap energy
   uint8_t *rxof;      // [R][n_chg]
@@ -22,7 +24,16 @@ struct WideState {
   int cap_w, cap_d;
 };
 
-cudaError_t wide_md_run(const DevParams &p, const DevState &g, const WideState &w, int n_steps, cudaStream_t st, int *launches);
+// One captured block of MD steps (CUDA graph), re-used while the kernel arguments stay the same.
+struct WideGraphCache {
+  cudaGraphExec_t exec = nullptr;
+  DevParams p_key;     // arguments baked into the captured kernels
+  int chunk = 0;
+};
+void wide_graph_release(WideGraphCache *c);
+
+cudaError_t wide_md_run(const DevParams &p, const DevState &g, const WideState &w, int n_steps, cudaStream_t st, int *launches,
+                        WideGraphCache *gc);
 cudaError_t wide_steepest_descent(const DevParams &p, const DevState &g, const WideState &w, int n_steps, float f_max,
                                   float gamma, float max_disp, cudaStream_t st, int *launches);
 cudaError_t wide_md_forces(const DevParams &p, const DevState &g, const WideState &w, float4 *out, cudaStream_t st);
@@ -31,6 +42,6 @@ cudaError_t wide_mc_run(const DevParams &p, const DevState &g, const WideState &
 cudaError_t wide_list_stats(const DevParams &p, const DevState &g, const WideState &w, double *out, cudaStream_t st);
 cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideState &w, const cgpe_sample_params &sp,
                              uint32_t thr1, uint32_t thr2, double *obs, float *qdist, double *tmp_d, int *tmp_i,
-                             cudaStream_t st, int *launches);
+                             cudaStream_t st, int *launches, WideGraphCache *gc);
 
 }  // namespace cgpe
