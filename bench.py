@@ -104,6 +104,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic.json; the capture command is recorded there).  None if absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
 def algorithmic_flops(n_mon, md_steps, trials, stats):
     """SURVEY §8d convention on the work the kernel's algorithm performs (unique listed pairs)."""
     w_all, w_in, d_all, d_in = (float(x) / 2.0 for x in stats)   # directed -> unique
@@ -318,7 +329,8 @@ def main():
             "kernel_ms_cgpe_events": kernel_ms,
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": None, "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_kind} clock; no FP32 entry in MEASURED_PEAKS.json)",
+                "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"),
+                "traffic_source": (ncu_traffic() or {}).get("source", "no ncu capture committed"), "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_kind} clock; no FP32 entry in MEASURED_PEAKS.json)",
                 "kernel": "k_sample_loop",
                 "algorithmic_flop_per_md_step": per_step, "unique_listed_pairs": [float(s) / 2 for s in stats],
                 "note": "Verlet-list algorithm: work counted on the pairs the lists hold (SURVEY 8d formula); the kernel is "
