@@ -280,8 +280,6 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
         return fail(nullptr, CGPE_ERR_UNSUPPORTED,
                     "reaction %d: exclusion_range %g is below the ion's largest WCA cutoff %g (an inserted ion would "
                     "carry WCA energy, which this build does not evaluate)", m, cfg->reactions[m].exclusion_range, rc_ion);
-    if (cfg->n_chains * cfg->n_beads + cfg->n_ion_slots > 2048)
-      return fail(nullptr, CGPE_ERR_UNSUPPORTED, "explicit ions are served by the shared-memory engine only (<= 2048 particles per replica)");
   }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);

@@ -244,7 +244,9 @@ __device__ void build_rows(Ctx &c, Thr<ITEMS> &t) {
     const int i = c.tid + k * c.nt;
     if (i < p.P) {
       t.ref[k][0] = t.x[k][0]; t.ref[k][1] = t.x[k][1]; t.ref[k][2] = t.x[k][2];
-      if (p.use_wca) {
+      if (p.use_wca && c.s.type[i] >= p.T) {
+        c.s.wn[i] = 0;   // hidden slot: not a particle (it gets rows when a trial move revives it)
+      } else if (p.use_wca) {
         const float4 pi = c.s.pos[i];
         // same-chain partners handled by the bonded owner (also excludes j == i)
         int ex_lo = i, ex_hi = i;

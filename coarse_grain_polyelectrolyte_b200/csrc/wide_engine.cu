@@ -54,9 +54,12 @@ wk_drift(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
     x.x = fmaf(p.dt, v.x, x.x); x.y = fmaf(p.dt, v.y, x.y); x.z = fmaf(p.dt, v.z, x.z);
     g.vel[k] = v;
   }
+  if (i >= p.NC) {   // free particles (explicit ions) wander: keep them inside the box
+    x.x -= p.box_l * floorf(x.x * p.inv_box_l); x.y -= p.box_l * floorf(x.y * p.inv_box_l); x.z -= p.box_l * floorf(x.z * p.inv_box_l);
+  }
   g.pos[k] = x;
-  const float dx = x.x - ref.x, dy = x.y - ref.y, dz = x.z - ref.z;
-  if (!(dx * dx + dy * dy + dz * dz <= p.half_skin2)) w.flag[r] = 1;   // benign race: all writers store 1
+  V3 dd;
+  if (!(wdist2(p, x, ref, &dd) <= p.half_skin2)) w.flag[r] = 1;   // benign race: all writers store 1 (minimum image: ions are folded)
 }
 
 __global__ void __launch_bounds__(kWT)
@@ -66,8 +69,9 @@ wk_rebuild(const __grid_constant__ DevParams p, const __grid_constant__ DevState
   if (!w.flag[r]) return;
   __shared__ float4 tile[kWT];
   const size_t base = (size_t)r * p.P;
-  const bool own = i < p.P;
-  const float4 pi = own ? g.pos[base + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool exists = i < p.P;
+  const bool own = exists && g.type[base + i] < p.T;   // hidden slots build no rows
+  const float4 pi = exists ? g.pos[base + i] : make_float4(0.f, 0.f, 0.f, 0.f);
   const int l = own ? chain_index(p, i) : -1, ci = own ? w.cidx[base + i] : -1;
   int ex_lo = i, ex_hi = i;
   if (l >= 0) { ex_lo = i - min(2, l); ex_hi = i + min(2, p.N - 1 - l); }
@@ -98,7 +102,7 @@ wk_rebuild(const __grid_constant__ DevParams p, const __grid_constant__ DevState
       }
     }
   }
-  if (!own) return;
+  if (!exists) return;
   if (nw > w.cap_w) { atomicOr(&g.err[r], kErrWcaCap); nw = w.cap_w; }
   if (nd > w.cap_d) { atomicOr(&g.err[r], kErrDhCap); nd = w.cap_d; }
   w.wn[base + i] = nw;
@@ -318,15 +322,25 @@ wk_mc_prepare(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
   w.wflag[cb + ci] = tit ? 1 : 0;
 }
 
-// one warp per replica: the trial loop of chain_engine.cu::mc_block on global-memory caches
+__device__ __forceinline__ float wwarp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// one warp per replica: the trial loop of chain_engine.cu::mc_block on global-memory caches,
+// including the explicit-ion insertion / deletion (p.n_ions > 0)
 __global__ void __launch_bounds__(32)
 wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
             int m, int n_trials, cgpe_trial_record *trace_all) {
   const int r = blockIdx.x, lane = threadIdx.x;
   const DevReaction rx = p.rx[m];
+  const bool ions = p.n_ions > 0;
   const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
   int *lp = g.lst_prot + ((size_t)r * p.n_rx + m) * p.P, *ld = g.lst_deprot + ((size_t)r * p.n_rx + m) * p.P;
+  int *ion_active = g.ion_active + (size_t)r * (ions ? p.n_ions : 1), *ion_free = g.ion_free + (size_t)r * (ions ? p.n_ions : 1);
   int n_p = g.cnt[((size_t)r * p.n_rx + m) * 2], n_d = g.cnt[((size_t)r * p.n_rx + m) * 2 + 1];
+  int n_act = ions ? g.ion_cnt[r * 2] : 0, n_free = ions ? g.ion_cnt[r * 2 + 1] : 0;
   const int n_sites = n_p + n_d;
   const float arg_fwd = (float)(2.302585092994045684 * (g.pH[r] - rx.pK)) * kLog2e;
   const float neg_beta_log2e = -rx.inv_kT * kLog2e;
@@ -337,9 +351,16 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
   cgpe_trial_record *trace = trace_all ? trace_all + (size_t)r * n_trials : nullptr;
   const int *chg = g.chg + cb;
   long long acc = 0;
+  bool ion_moved = false;
+  int err = 0;
   for (int b0 = 0; b0 < n_trials; b0 += 32) {
     const unsigned long long cnt = trial_ctr + (unsigned long long)(b0 + lane);
     const uint4 o = philox4x32_10((uint32_t)cnt, (uint32_t)(cnt >> 32), 0u, kTagMc + (uint32_t)m, k0, k1);
+    uint4 o1 = make_uint4(0, 0, 0, 0), o2 = o1;
+    if (ions) {
+      o1 = philox4x32_10((uint32_t)cnt, (uint32_t)(cnt >> 32), 1u, kTagMc + (uint32_t)m, k0, k1);
+      o2 = philox4x32_10((uint32_t)cnt, (uint32_t)(cnt >> 32), 2u, kTagMc + (uint32_t)m, k0, k1);
+    }
     const int nb = min(32, n_trials - b0);
     for (int tt = 0; tt < nb; ++tt) {
       const uint32_t a0 = __shfl_sync(0xffffffffu, o.x, tt), a1 = __shfl_sync(0xffffffffu, o.y, tt),
@@ -348,21 +369,60 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
       const int n_src = fwd ? n_p : n_d, n_dst = fwd ? n_d : n_p;
       int *src = fwd ? lp : ld, *dst = fwd ? ld : lp;
       const float u = u24(a2);
-      if (n_src == 0) {
+      bool possible = n_src > 0;
+      if (ions && !fwd && n_act == 0) possible = false;
+      if (ions && fwd && n_free == 0) { possible = false; err |= kErrIonPool; }
+      if (!possible) {
         if (trace && lane == 0) { cgpe_trial_record rec = {-1, -1, (int8_t)(fwd ? 1 : -1), 0, 0, 0, 0.f, 0.f, u}; trace[b0 + tt] = rec; }
         continue;
       }
       const int k = (int)__umulhi(a1, (uint32_t)n_src);
       const int i = src[k], ci = w.cidx[base + i];
+      const int t_new = fwd ? rx.type_deprot : rx.type_prot;
+      const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = fwd ? dq_fwd : -dq_fwd;
       float de = w.wcache[cb + ci];
       if (p.use_dh) de = fmaf(coul_fwd, w.phi[cb + ci], de);
       if (!fwd) de = -de;
-      const float bf = ((float)n_src / (float)(n_sites - n_src + 1)) * exp2f(fmaf(neg_beta_log2e, de, fwd ? arg_fwd : -arg_fwd));
+      int b = -1, kb = 0;
+      bool excluded = false;
+      float4 pb4 = make_float4(0.f, 0.f, 0.f, rx.q_ion);
+      if (ions) {   // see chain_engine.cu::mc_block
+        if (fwd) {
+          b = ion_free[n_free - 1];
+          pb4.x = u24(__shfl_sync(0xffffffffu, o1.x, tt)) * p.box_l;
+          pb4.y = u24(__shfl_sync(0xffffffffu, o1.y, tt)) * p.box_l;
+          pb4.z = u24(__shfl_sync(0xffffffffu, o1.z, tt)) * p.box_l;
+        } else {
+          kb = (int)__umulhi(__shfl_sync(0xffffffffu, o.w, tt), (uint32_t)n_act);
+          b = ion_active[kb];
+          const float4 x = g.pos[base + b];
+          pb4.x = x.x; pb4.y = x.y; pb4.z = x.z;
+        }
+        float esum = 0.f, dmin2 = 3.0e38f;
+        for (int j = lane; j < p.P; j += 32) {
+          if (j == b) continue;
+          const int tj = j == i ? t_new : (int)g.type[base + j];
+          if (tj >= p.T) continue;
+          const float4 pj4 = g.pos[base + j];
+          const float qj = j == i ? q_new : pj4.w;
+          V3 d;
+          const float r2 = wdist2(p, pb4, pj4, &d);
+          dmin2 = fminf(dmin2, r2);
+          if (p.use_dh && qj != 0.f && r2 < rc2) {
+            float fr;
+            esum = fmaf(qj, dh_energy_unit(r2, kappa, nkl, &fr), esum);
+          }
+        }
+        esum = warp_sum(esum);
+        dmin2 = wwarp_min(dmin2);
+        const float e_ion = p.dh_pref * rx.q_ion * esum;
+        de += fwd ? e_ion : -e_ion;
+        excluded = dmin2 < rx.excl2;
+      }
+      const float bf = excluded ? 0.f : ((float)n_src / (float)(n_sites - n_src + 1)) * exp2f(fmaf(neg_beta_log2e, de, fwd ? arg_fwd : -arg_fwd));
       const bool accept = u < bf;
-      if (trace && lane == 0) { cgpe_trial_record rec = {i, -1, (int8_t)(fwd ? 1 : -1), (int8_t)accept, 0, 0, de, bf, u}; trace[b0 + tt] = rec; }
+      if (trace && lane == 0) { cgpe_trial_record rec = {i, b, (int8_t)(fwd ? 1 : -1), (int8_t)accept, (int8_t)excluded, 0, de, bf, u}; trace[b0 + tt] = rec; }
       if (accept) {
-        const int t_new = fwd ? rx.type_deprot : rx.type_prot;
-        const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = fwd ? dq_fwd : -dq_fwd;
         const float4 pi4 = g.pos[base + i];
         const bool refresh = p.use_wca && w.wflag[cb + ci] != 0;
         if (lane == 0) {
@@ -387,6 +447,45 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
           }
         }
         __syncwarp();
+        if (ions) {
+          const int cbi = w.cidx[base + b];
+          const float dqb = fwd ? rx.q_ion : -rx.q_ion;
+          const uint32_t w0 = __shfl_sync(0xffffffffu, o2.x, tt), w1 = __shfl_sync(0xffffffffu, o2.y, tt),
+                         w2 = __shfl_sync(0xffffffffu, o2.z, tt), w3 = __shfl_sync(0xffffffffu, o2.w, tt);
+          if (lane == 0) {
+            if (fwd) {
+              g.type[base + b] = (uint8_t)rx.type_ion;
+              g.pos[base + b] = pb4;
+              const float ua = ((float)(w0 >> 8) + 0.5f) * (1.0f / 16777216.0f), ub = ((float)(w1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+              const float uc = ((float)(w2 >> 8) + 0.5f) * (1.0f / 16777216.0f), ud = ((float)(w3 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+              const float ra = rx.sqrt_kT * sqrtf(-2.0f * logf(ua)), rb = rx.sqrt_kT * sqrtf(-2.0f * logf(uc));
+              float sa, ca, sb_, cb_;
+              sincosf(6.283185307179586f * ub, &sa, &ca);
+              sincosf(6.283185307179586f * ud, &sb_, &cb_);
+              g.vel[base + b] = make_float4(ra * ca, ra * sa, rb * cb_, 0.f);
+              ion_active[n_act] = b;
+            } else {
+              g.type[base + b] = (uint8_t)p.T;
+              g.pos[base + b].w = 0.f;
+              g.vel[base + b] = make_float4(0.f, 0.f, 0.f, 0.f);
+              ion_active[kb] = ion_active[n_act - 1];
+              ion_free[n_free] = b;
+            }
+          }
+          if (fwd) { n_free -= 1; n_act += 1; } else { n_act -= 1; n_free += 1; }
+          if (p.use_dh)
+            for (int ck = lane; ck < p.n_chg; ck += 32) {
+              if (ck == cbi) continue;
+              V3 d;
+              const float r2 = wdist2(p, pb4, g.pos[base + chg[ck]], &d);
+              if (r2 < rc2) {
+                float fr;
+                w.phi[cb + ck] = fmaf(dqb, dh_energy_unit(r2, kappa, nkl, &fr), w.phi[cb + ck]);
+              }
+            }
+          ion_moved = true;
+          __syncwarp();
+        }
         if (refresh) {
           const int l = chain_index(p, i), n_w = w.wn[base + i];
           const uint32_t *wl = w.wl + (size_t)r * w.cap_w * p.P;
@@ -413,6 +512,11 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
     g.trials[(size_t)r * p.n_rx + m] = (long long)(trial_ctr + (unsigned long long)n_trials);
     g.accepted[(size_t)r * p.n_rx + m] += acc;
     if (n_trials > 0) g.f_valid[r] = 0;
+    if (ions) {
+      g.ion_cnt[r * 2] = n_act; g.ion_cnt[r * 2 + 1] = n_free;
+      if (ion_moved) w.flag[r] = 1;   // rows are stale: rebuild before the next force evaluation
+    }
+    if (err) atomicOr(&g.err[r], err);
   }
 }
 
@@ -633,6 +737,7 @@ cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideSt
     WCK(cudaStreamSynchronize(st));
     *launches += 1;
     if (n_max > 0) {
+      wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);   // only replicas whose ions moved in the last MC block
       if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, -1, 0);
       wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, 1, nullptr);   // stale forces only
       WCK(wide_steps(p, g, w, n_max, st, launches, gc));

@@ -548,14 +548,13 @@ class System:
             n_spare = max(0, n_sites - n_hidden)
             if n_spare > 0:
                 self._hidden_type = T
-                self._pos = np.concatenate([self._pos, np.zeros((n_spare, 3))]); self._vel = np.concatenate([self._vel, np.zeros((n_spare, 3))])
+                # parked at scattered positions (they do not interact; a revived slot gets a fresh position)
+                park = np.random.RandomState(12345).random_sample((n_spare, 3)) * float(self.box_l[0])
+                self._pos = np.concatenate([self._pos, park]); self._vel = np.concatenate([self._vel, np.zeros((n_spare, 3))])
                 self._type = np.concatenate([self._type, np.full(n_spare, T, np.int64)]); self._q = np.concatenate([self._q, np.zeros(n_spare)])
                 self._n_part = len(self._type)
         n_ion_slots = self._n_part - n_chain
-        if n_ion_slots > 0 and n_chain + n_ion_slots > 2048:
-            raise NotImplementedError(
-                f"{n_ion_slots} free particles (explicit ions) + {n_chain} chain beads exceed the 2048 particles the "
-                "explicit-ion engine holds per replica; use ION_MODEL='implicit' (Debye-Hueckel screening only)")
+
         kw = dict(
             n_replicas=self.n_replicas, replica_offset=self.replica_offset, n_chains=n_chains, n_beads=n_beads,
             n_ion_slots=n_ion_slots, n_types=T, device=self._device, skin=self._engine_skin,

@@ -11,7 +11,7 @@ Beyond the reference:
   * "Simulation configuration" may carry "ION_MODEL": "implicit" (default here: the chain alone,
     small ions only through the Debye-Hueckel screening, as BASELINE.json's north star describes)
     or "explicit" (the reference's B+/Na+/Cl- particles with H+ insertion / deletion,
-    M.py:173-198; served for systems of up to 2048 particles per replica).
+    M.py:173-198).
 """
 import numpy as np
 

@@ -116,9 +116,20 @@ def test_explicit_ion_model_end_to_end():
     assert np.all(np.isfinite(ens.rad_gyr)) and ens.times[-1] > 0
 
 
-def test_explicit_ion_model_too_large_is_refused_loudly():
+def test_explicit_ion_model_beyond_shared_memory():
+    """N = 300 with explicit ions is 300 + 2*100 + 2*600 + 100 spare = 1800 particles (shared-memory
+    engine); N = 400 is 2402 (global-memory engine): the same driver calls serve both."""
     from modules.Model import Model
-    p = small_run_parameters(n_mon=1000)
-    p["Simulation configuration"]["ION_MODEL"] = "explicit"
-    with pytest.raises(NotImplementedError, match="explicit ions"):
-        Model(p)
+    for n_mon in (300, 400):
+        p = small_run_parameters(n_mon=n_mon)
+        p["Simulation configuration"]["ION_MODEL"] = "explicit"
+        m = Model(p)
+        assert len(m.system.part) == n_mon + 2 * m.n_acid + 2 * m.n_salt          # M.py:175-198
+        m.system.thermostat.set_langevin(kT=1.0, gamma=1.0, seed=42)
+        m.reaction1.constant_pH = 7.0
+        m.reaction1.reaction(reaction_steps=300)
+        m.system.integrator.run(20)
+        tp = m.type_particles
+        n_b = m.system.number_of_particles(type=tp["B"])
+        assert n_b == m.system.number_of_particles(type=tp["N"]) + m.system.number_of_particles(type=tp["N2"])
+        assert n_b < m.n_acid and np.isfinite(m.system.analysis.energy()["total"])

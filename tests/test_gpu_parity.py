@@ -449,3 +449,39 @@ def test_ensemble_observables_agree_within_error_bars(Engine, oracle_mod):
     # and the physics is the expected one: titration curve monotone, charged chain more extended
     alpha = og[..., 0].mean(axis=1) / n1
     assert np.all(np.diff(alpha) > 0) and alpha[0] < 0.4 and alpha[-1] > 0.97
+
+
+def test_explicit_ions_on_the_wide_engine(Engine, oracle_mod):
+    """More than 2048 particles per replica (chain + ions): the global-memory engine serves the same
+    explicit-ion model.  N = 400 -> 400 + 2*134 + 2*800 + 134 spare = 2402 particles."""
+    w = make_workload(400, pH=[7.5, 9.0], explicit_ions=True)
+    assert w.xyzq.shape[0] == 400 + 3 * sum(w.n_sites) + 2 * w.ru.n_salt > 2048
+    state = _ion_state(w, seed=13)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    eg, eo = g.energy(), o.energy()
+    scale = np.maximum(np.abs(eo), 1e-3 * np.abs(eo).max(axis=1, keepdims=True))
+    assert np.max(np.abs(eg - eo) / scale) < REL_TOL
+    fo = o.forces_f64()
+    assert np.abs(g.md_forces() - fo).max() < REL_TOL * np.abs(fo).max()
+    for rx, n in ((0, 2500), (1, 200)):
+        tg = g.mc_run(rx, n, trace=True)
+        to, ties = o.mc_run_follow(rx, tg, tie_tol=1e-4)
+        assert ties <= 2
+        for f in ("particle", "ion_slot", "direction", "accepted", "excluded", "u"):
+            np.testing.assert_array_equal(tg[f], to[f], err_msg=f)
+        tried = (to["particle"] >= 0) & (to["excluded"] == 0)
+        err = np.abs(tg["delta_e"][tried] - to["delta_e"][tried]) / np.maximum(np.abs(to["delta_e"][tried]), 1.0)
+        assert err.max() < REL_TOL and tg["accepted"].sum() > 0
+    o.set_list_mode(True, 0.8)
+    for e in (g, o):
+        e.md_run(8)
+    xg, vg, tyg = g.get_state()
+    xo, vo, qo = o.state_f64()
+    np.testing.assert_array_equal(tyg, o.get_state()[2])
+    assert _ion_dx(xg[..., :3], xo, w) < 1e-4 and np.abs(vg[..., :3] - vo).max() < 5e-3
+    sp = g.sample_params(5, md_steps_per_burst=4, use_md=True, mc_blocks=((0, 201), (1, 11)), p_burst1=0.7, p_burst2=0.3)
+    og, _ = g.sample_loop(sp)
+    oo, _ = o.sample_loop(sp)
+    np.testing.assert_array_equal(og[..., :3], oo[..., :3])
+    np.testing.assert_array_equal(og[..., 2], og[..., 0] + og[..., 1])
+    np.testing.assert_allclose(og[..., 3:5], oo[..., 3:5], rtol=2e-4)
