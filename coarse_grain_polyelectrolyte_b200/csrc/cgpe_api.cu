@@ -1,5 +1,6 @@
 // cgpe_api.cu — the C-ABI of libcgpe.so (include/cgpe.h): handle management, validation, host
 // <-> device copies and kernel launches.  No torch types, no C++ types across the boundary.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -220,7 +221,7 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
   CU(alloc((void **)&w.dn, sizeof(int) * RC));
   CU(alloc((void **)&w.fdh, sizeof(float4) * RC));
   CU(alloc((void **)&w.cidx, sizeof(int) * RP));
-  CU(alloc((void **)&w.flag, sizeof(int) * p.R));
+  CU(alloc((void **)&w.flag, sizeof(int) * (p.R + 1)));
   CU(alloc((void **)&w.nsteps, sizeof(int) * p.R));
   CU(alloc((void **)&w.sched_max, sizeof(int)));
   CU(alloc((void **)&w.step, 2 * sizeof(int)));
@@ -228,6 +229,26 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
   CU(alloc((void **)&w.wcache, sizeof(float) * RC));
   CU(alloc((void **)&w.rxof, RC));
   CU(alloc((void **)&w.wflag, RC));
+  // cell grids of the list build: at most ~2 cells per member, edge never below the list radius
+  // (the kernels pick the cells per edge from the list radius in force at each build)
+  auto grid = [&](CellGrid &cg, int n) -> cudaError_t {
+    cg.n = n;
+    const int nc = (int)std::floor(std::cbrt(2.0 * (n > 0 ? n : 1)));
+    cg.nc_max = nc >= 3 ? nc : 1;
+    cg.m_max = cg.nc_max * cg.nc_max * cg.nc_max;
+    const size_t Rn = (size_t)p.R * (n > 0 ? n : 1);
+    cudaError_t e;
+    if ((e = alloc((void **)&cg.start, sizeof(int) * p.R * (cg.m_max + 1))) != cudaSuccess) return e;
+    if ((e = alloc((void **)&cg.cursor, sizeof(int) * p.R * cg.m_max)) != cudaSuccess) return e;
+    if ((e = alloc((void **)&cg.cell_of, sizeof(int) * Rn)) != cudaSuccess) return e;
+    if ((e = alloc((void **)&cg.tmp, sizeof(int) * Rn)) != cudaSuccess) return e;
+    if ((e = alloc((void **)&cg.order, sizeof(int) * Rn)) != cudaSuccess) return e;
+    if ((e = alloc((void **)&cg.spos, sizeof(float4) * Rn)) != cudaSuccess) return e;
+    if ((e = alloc((void **)&cg.nf, sizeof(int) * p.R)) != cudaSuccess) return e;
+    return alloc((void **)&cg.nc, sizeof(int) * p.R);
+  };
+  CU(grid(w.cw, p.P));
+  CU(grid(w.cd, p.n_chg));
   std::vector<int> cidx(RP, -1);
   for (int r = 0; r < p.R; ++r)
     for (int c = 0; c < p.n_chg; ++c) cidx[(size_t)r * p.P + chg_packed[(size_t)r * p.n_chg + c]] = c;
@@ -316,9 +337,8 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   p.dh_pref = (float)cfg->dh_prefactor;
   p.box_l = (float)cfg->box_l; p.inv_box_l = (float)(1.0 / cfg->box_l);
   p.dt = (float)cfg->time_step; p.half_dt = (float)(0.5 * cfg->time_step); p.dt_d = cfg->time_step;
-  // default Verlet skin: 0.8 for the shared-memory engine; 2.0 for the global-memory engine, whose
-  // all-pairs list build is the expensive part of a step (fewer, longer-lived lists)
-  const double skin = cfg->skin > 0.0 ? cfg->skin : (p.P > 2048 ? 2.0 : 0.8);
+  // default Verlet skin (both engines: list builds are cheap next to the steps they serve)
+  const double skin = cfg->skin > 0.0 ? cfg->skin : 0.8;
   p.skin = (float)skin; p.half_skin2 = (float)(0.25 * skin * skin);
   p.force_cap = 0.f;
   p.thermostat_seed = 0u;

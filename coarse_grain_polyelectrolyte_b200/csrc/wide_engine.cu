@@ -3,9 +3,9 @@
 // Verlet lists in global memory (L2-resident: 160 KB of positions per N = 10^4 replica), one
 // thread per particle.
 //
-//   MD step   = wk_drift (half kick + drift + skin/2 vote)  ->  wk_rebuild (only replicas that
-//               voted)  ->  wk_forces (all terms + thermostat + second half kick)
-//   MC block  = wk_mc_prepare (per-site potentials, all threads) -> wk_mc_block (one warp per
+//   MD step   = wk_drift (half kick + drift + skin/2 vote)  ->  wk_cells + wk_rows (cell-grid list
+//               build, only replicas that voted)  ->  wk_forces (all terms + thermostat + second half kick)
+//   MC block  = wk_mc_prepare (per-site potentials, all threads) -> wk_mc_block (one CTA per
 //               replica, same trial logic and Philox streams as the shared-memory engine)
 //   sampling  = the loop of perform_sampling driven from the host, one small read-back per sample
 //
@@ -14,6 +14,7 @@
 // forces differs.  Reference call sites: see chain_engine.cu.
 #include "wide_engine.cuh"
 
+#include <algorithm>
 #include <cstring>
 
 namespace cgpe {
@@ -59,56 +60,207 @@ wk_drift(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
   }
   g.pos[k] = x;
   V3 dd;
-  if (!(wdist2(p, x, ref, &dd) <= p.half_skin2)) w.flag[r] = 1;   // benign race: all writers store 1 (minimum image: ions are folded)
+  if (!(wdist2(p, x, ref, &dd) <= p.half_skin2)) w.flag[p.R] = 1;   // see rebuild_due; benign race: all writers store 1 (minimum image: ions are folded)
 }
 
-__global__ void __launch_bounds__(kWT)
-wk_rebuild(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w) {
-  const int r = blockIdx.y, i = blockIdx.x * kWT + threadIdx.x;
-  if (r == 0 && i == 0) w.step[1] = w.step[0];   // the force kernels of this step read step[1]
-  if (!w.flag[r]) return;
-  __shared__ float4 tile[kWT];
+// ---- list build: cell grids, then rows -----------------------------------------------------------
+// flag[r]: replica r needs new rows (forced, or its ions were moved by a trial).  flag[R]: some
+// particle of some replica has left its skin/2 sphere in this step; then every replica taking part
+// in the burst rebuilds.  A build is a chain of short dependent phases, so R replicas building
+// together cost one such chain instead of R of them scattered over the burst, and since the
+// largest displacement among thousands of particles grows at nearly the same pace everywhere the
+// replicas lose little by sharing the vote.
+__device__ __forceinline__ bool rebuild_due(const DevParams &p, const WideState &w, int r, int step) {
+  if (step == kStepFromDevice) step = w.step[0];
+  return w.flag[r] || (w.flag[p.R] && step < w.nsteps[r]);
+}
+
+constexpr int kCT = 1024;   // threads of the one CTA that sorts a replica's particle set into cells
+
+// Geometry of a grid: the box is cut into nf^3 cells with edge >= the list radius.  A chain fills a
+// small part of a dilute box, so the nf^3 cells are mostly empty; they are folded onto a table of
+// A^3 buckets (A^3 ~ 2 members, bucket coordinate = cell coordinate mod A).  Members of aliased
+// cells share a bucket and are told apart by the distance test, the 27 cells around a particle
+// fall into 27 different buckets (A >= 3 and nf mod A not in {1, 2}, so that the periodic wrap
+// does not alias neighbours either).
+struct GridDims { int nf, A; };
+
+__device__ __forceinline__ GridDims grid_dims(const DevParams &p, float rlist, int nc_max) {
+  GridDims d;
+  d.nf = (int)fminf(p.box_l / (rlist * 1.0001f), 1.0e6f);
+  d.A = min(d.nf, nc_max);
+  if (d.A < 3) { d.nf = d.A = 1; return d; }
+  if (d.nf > d.A && d.nf % d.A >= 1 && d.nf % d.A <= 2) d.nf -= d.nf % d.A;
+  return d;
+}
+__device__ __forceinline__ int cell_coord(const DevParams &p, float x, int nf) {
+  const float xf = x - p.box_l * floorf(x * p.inv_box_l);
+  return min(max((int)(xf * p.inv_box_l * (float)nf), 0), nf - 1);
+}
+__device__ __forceinline__ int bucket_id(const DevParams &p, float4 x, GridDims d) {
+  return ((cell_coord(p, x.x, d.nf) % d.A) * d.A + cell_coord(p, x.y, d.nf) % d.A) * d.A + cell_coord(p, x.z, d.nf) % d.A;
+}
+
+// Sort the particles (blockIdx.x = 0: all, for the WCA rows) or the chargeable particles
+// (blockIdx.x = 1, for the Debye-Hueckel rows) of replica blockIdx.y into buckets: count,
+// exclusive scan, scatter, then order every bucket by member index so that the rows - and with
+// them the summation order of the forces - do not depend on the order in which the atomics landed.
+__global__ void __launch_bounds__(kCT)
+wk_cells(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w, int step) {
+  const int r = blockIdx.y, kind = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!rebuild_due(p, w, r, step) || (kind == 0 ? !p.use_wca : !p.use_dh)) return;
+  const CellGrid &cg = kind == 0 ? w.cw : w.cd;
+  const GridDims gd = grid_dims(p, kind == 0 ? sqrtf(p.rlist_w2) : g.rcut[r] + p.skin, cg.nc_max);
+  const int M = gd.A * gd.A * gd.A, n = cg.n;
   const size_t base = (size_t)r * p.P;
-  const bool exists = i < p.P;
-  const bool own = exists && g.type[base + i] < p.T;   // hidden slots build no rows
-  const float4 pi = exists ? g.pos[base + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-  const int l = own ? chain_index(p, i) : -1, ci = own ? w.cidx[base + i] : -1;
-  int ex_lo = i, ex_hi = i;
-  if (l >= 0) { ex_lo = i - min(2, l); ex_hi = i + min(2, p.N - 1 - l); }
-  const float rc = g.rcut[r], rlist_d2 = (rc + p.skin) * (rc + p.skin);
-  int nw = 0, nd = 0;
-  uint32_t *wl = w.wl + (size_t)r * w.cap_w * p.P;
-  uint32_t *dl = w.dl + ((size_t)r * p.n_chg + (ci >= 0 ? ci : 0)) * w.cap_d;   // this site's row
-  for (int j0 = 0; j0 < p.P; j0 += kWT) {
+  const int *chg = g.chg + (size_t)r * p.n_chg;
+  int *start = cg.start + (size_t)r * (cg.m_max + 1), *cursor = cg.cursor + (size_t)r * cg.m_max;
+  int *cell_of = cg.cell_of + (size_t)r * n, *tmp = cg.tmp + (size_t)r * n, *order = cg.order + (size_t)r * n;
+  float4 *spos = cg.spos + (size_t)r * n;
+  __shared__ int warp_tot[2][32];
+
+  for (int c = tid; c < M; c += kCT) cursor[c] = 0;
+  __syncthreads();
+#pragma unroll 2
+  for (int e = tid; e < n; e += kCT) {
+    const int i = kind == 0 ? e : chg[e];
+    int c = -1;
+    if (g.type[base + i] < p.T) {   // hidden slots stay out of the grid
+      c = bucket_id(p, g.pos[base + i], gd);
+      atomicAdd(&cursor[c], 1);
+    }
+    cell_of[e] = c;
+  }
+  __syncthreads();
+  int carry = 0;   // exclusive scan of the counts, one barrier per 1024 buckets
+  for (int c0 = 0, buf = 0; c0 < M; c0 += kCT, buf ^= 1) {
+    const int c = c0 + tid, v = c < M ? cursor[c] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[buf][warp] = incl;
     __syncthreads();
-    if (j0 + threadIdx.x < p.P) tile[threadIdx.x] = g.pos[base + j0 + threadIdx.x];
-    __syncthreads();
-    if (!own) continue;
-    const int jn = min(kWT, p.P - j0);
-    for (int jj = 0; jj < jn; ++jj) {
-      const int j = j0 + jj;
-      V3 d;
-      const float r2 = wdist2(p, pi, tile[jj], &d);
-      if (p.use_wca && r2 < p.rlist_w2 && (j < ex_lo || j > ex_hi)) {
-        if (nw < w.cap_w) wl[(size_t)nw * p.P + i] = (uint32_t)j;
-        ++nw;
-      }
-      if (p.use_dh && ci >= 0 && r2 < rlist_d2 && j != i) {
-        const int cj = w.cidx[base + j];
-        if (cj >= 0) {
-          if (nd < w.cap_d) dl[nd] = (uint32_t)cj;
-          ++nd;
+    int t = warp_tot[buf][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+    const int before = __shfl_sync(0xffffffffu, t, warp > 0 ? warp - 1 : 0);
+    const int excl = carry + (warp > 0 ? before : 0) + incl - v;
+    if (c < M) { start[c] = excl; cursor[c] = excl; }
+    carry += __shfl_sync(0xffffffffu, t, 31);
+  }
+  const int members = carry;
+  if (tid == 0) { start[M] = members; cg.nc[r] = gd.A; cg.nf[r] = gd.nf; }
+  __syncthreads();
+#pragma unroll 2
+  for (int e = tid; e < n; e += kCT) {
+    const int c = cell_of[e];
+    if (c >= 0) tmp[atomicAdd(&cursor[c], 1)] = e;
+  }
+  __syncthreads();
+#pragma unroll 2
+  for (int s = tid; s < members; s += kCT) {
+    const int e = tmp[s], c = cell_of[e], lo = start[c], hi = start[c + 1];
+    int rank = 0;
+    for (int t = lo; t < hi; ++t) rank += tmp[t] < e ? 1 : 0;
+    order[lo + rank] = e;
+    spos[lo + rank] = g.pos[base + (kind == 0 ? e : chg[e])];
+  }
+}
+
+// Runs [lo, hi) of grid slots that hold the buckets of the 27 cells around x: the buckets of one
+// (x, y) column are contiguous in z, so a column gives one run where the three z are consecutive.
+template <class F>
+__device__ __forceinline__ void for_cell_runs(const DevParams &p, const int *start, GridDims d, float4 x, F &&visit) {
+  if (d.A == 1) { visit(0, start[1]); return; }
+  const int cx = cell_coord(p, x.x, d.nf), cy = cell_coord(p, x.y, d.nf), cz = cell_coord(p, x.z, d.nf);
+  const int z0 = (cz > 0 ? cz - 1 : d.nf - 1) % d.A, z1 = cz % d.A, z2 = (cz < d.nf - 1 ? cz + 1 : 0) % d.A;
+  const bool one_run = z0 + 1 == z1 && z1 + 1 == z2;
+  for (int dx = -1; dx <= 1; ++dx)
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int X = ((cx + dx + d.nf) % d.nf) % d.A, Y = ((cy + dy + d.nf) % d.nf) % d.A, col = (X * d.A + Y) * d.A;
+      if (one_run) visit(start[col + z0], start[col + z2 + 1]);
+      else { visit(start[col + z0], start[col + z0 + 1]); visit(start[col + z1], start[col + z1 + 1]); visit(start[col + z2], start[col + z2 + 1]); }
+    }
+}
+
+constexpr int kRowSiteBlocks = 64;   // blocks per replica that build Debye-Hueckel rows (warps stride over the sites)
+
+// Verlet rows of the replicas that rebuild.  Blocks [0, nbw): one thread per particle collects its
+// WCA row from the 27 cells around it; the other blocks: one warp per chargeable site collects
+// the Debye-Hueckel row, lanes striding over each run of slots (ballot compaction keeps the row
+// in slot order).
+__global__ void __launch_bounds__(kWT)
+wk_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w, int nbw,
+        int step) {
+  const int r = blockIdx.y;
+  if (r == 0 && blockIdx.x == 0 && threadIdx.x == 0) w.step[1] = w.step[0];   // the force kernels of this step read step[1]
+  if (!rebuild_due(p, w, r, step)) return;
+  const size_t base = (size_t)r * p.P;
+  if ((int)blockIdx.x < nbw) {
+    const int i = blockIdx.x * kWT + threadIdx.x;
+    if (i >= p.P) return;
+    const float4 pi = g.pos[base + i];
+    int nw = 0;
+    if (p.use_wca && g.type[base + i] < p.T) {   // hidden slots build no rows
+      const int l = chain_index(p, i);
+      int ex_lo = i, ex_hi = i;
+      if (l >= 0) { ex_lo = i - min(2, l); ex_hi = i + min(2, p.N - 1 - l); }
+      const CellGrid &cg = w.cw;
+      const GridDims gd = {cg.nf[r], cg.nc[r]};
+      const int *order = cg.order + (size_t)r * cg.n;
+      const float4 *spos = cg.spos + (size_t)r * cg.n;
+      uint32_t *wl = w.wl + (size_t)r * w.cap_w * p.P;
+      for_cell_runs(p, cg.start + (size_t)r * (cg.m_max + 1), gd, pi, [&](int lo, int hi) {
+        for (int s = lo; s < hi; ++s) {
+          V3 d;
+          if (wdist2(p, pi, spos[s], &d) < p.rlist_w2) {
+            const int j = order[s];
+            if (j < ex_lo || j > ex_hi) {
+              if (nw < w.cap_w) wl[(size_t)nw * p.P + i] = (uint32_t)j;
+              ++nw;
+            }
+          }
         }
+      });
+      if (nw > w.cap_w) { atomicOr(&g.err[r], kErrWcaCap); nw = w.cap_w; }
+    }
+    w.wn[base + i] = nw;
+    w.ref[base + i] = pi;
+    if (i == 0) g.rebuilds[r] += 1;
+  } else {
+    const int lane = threadIdx.x & 31, per = kWT / 32;
+    const size_t cb = (size_t)r * p.n_chg;
+    const CellGrid &cg = w.cd;
+    const GridDims gd = {cg.nf[r], cg.nc[r]};
+    const int *order = cg.order + (size_t)r * cg.n, *start = cg.start + (size_t)r * (cg.m_max + 1);
+    const float4 *spos = cg.spos + (size_t)r * cg.n;
+    const float rl = g.rcut[r] + p.skin, rlist_d2 = rl * rl;
+    for (int ci = ((int)blockIdx.x - nbw) * per + (threadIdx.x >> 5); ci < p.n_chg; ci += ((int)gridDim.x - nbw) * per) {
+      const int i = g.chg[cb + ci];
+      int nd = 0;
+      if (g.type[base + i] < p.T) {
+        const float4 pi = g.pos[base + i];
+        uint32_t *dl = w.dl + (cb + ci) * w.cap_d;
+        for_cell_runs(p, start, gd, pi, [&](int lo, int hi) {
+          for (int s0 = lo; s0 < hi; s0 += 32) {
+            const int s = s0 + lane;
+            int cj = -1;
+            if (s < hi) {
+              V3 d;
+              if (wdist2(p, pi, spos[s], &d) < rlist_d2) cj = order[s];
+              if (cj == ci) cj = -1;
+            }
+            const uint32_t hit = __ballot_sync(0xffffffffu, cj >= 0);
+            const int slot = nd + __popc(hit & ((1u << lane) - 1u));
+            if (cj >= 0 && slot < w.cap_d) dl[slot] = (uint32_t)cj;
+            nd += __popc(hit);
+          }
+        });
+        if (nd > w.cap_d) { if (lane == 0) atomicOr(&g.err[r], kErrDhCap); nd = w.cap_d; }
       }
+      if (lane == 0) w.dn[cb + ci] = nd;
     }
   }
-  if (!exists) return;
-  if (nw > w.cap_w) { atomicOr(&g.err[r], kErrWcaCap); nw = w.cap_w; }
-  if (nd > w.cap_d) { atomicOr(&g.err[r], kErrDhCap); nd = w.cap_d; }
-  w.wn[base + i] = nw;
-  if (ci >= 0) w.dn[(size_t)r * p.n_chg + ci] = nd;
-  w.ref[base + i] = pi;
-  if (i == 0) g.rebuilds[r] += 1;
 }
 
 // Debye-Hueckel force (mode 0) or potential sum_j q_j e(r) (mode 1) of every chargeable particle:
@@ -161,7 +313,7 @@ wk_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState 
     step = w.step[1];
     if (r == 0 && i == 0) w.step[0] = step + 1;   // nothing in this launch reads step[0]; the next drift does
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) w.flag[r] = 0;   // every block of wk_rebuild has seen it
+  if (blockIdx.x == 0 && threadIdx.x == 0) { w.flag[r] = 0; if (r == 0) w.flag[p.R] = 0; }   // every block of wk_cells / wk_rows has seen them
   if (step >= w.nsteps[r]) return;
   if (mode == 0 && step < 0 && g.f_valid[r] && !out) return;   // cached forces are still good
   if (i >= p.P) return;
@@ -328,15 +480,81 @@ __device__ __forceinline__ float wwarp_min(float v) {
   return v;
 }
 
-// one warp per replica: the trial loop of chain_engine.cu::mc_block on global-memory caches,
-// including the explicit-ion insertion / deletion (p.n_ions > 0)
-__global__ void __launch_bounds__(32)
+// Work a trial hands to the whole CTA (explicit ions): the sums over all particles.
+struct McOrder { int op, b, i, t_new, cbi; float q_new, dqb; float4 pb; };
+enum { kMcExit = 0, kMcIonEnergy = 1, kMcIonPhi = 2 };
+constexpr int kMcThreads = 1024;
+
+__device__ __forceinline__ void mc_bar(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+
+// interaction of the ion at o.pb with every visible particle (site o.i taken in its trial state):
+// this thread's share of  sum_j q_j e(r)  and of the smallest squared distance
+__device__ __forceinline__ void mc_ion_energy_share(const DevParams &p, const DevState &g, size_t base, const McOrder &o,
+                                                    float kappa, float nkl, float rc2, int tid, int n_threads,
+                                                    float *esum, float *dmin2) {
+  float es = 0.f, dm = 3.0e38f;
+  for (int j = tid; j < p.P; j += n_threads) {
+    if (j == o.b) continue;
+    const int tj = j == o.i ? o.t_new : (int)g.type[base + j];
+    if (tj >= p.T) continue;
+    const float4 pj4 = g.pos[base + j];
+    const float qj = j == o.i ? o.q_new : pj4.w;
+    V3 d;
+    const float r2 = wdist2(p, o.pb, pj4, &d);
+    dm = fminf(dm, r2);
+    if (p.use_dh && qj != 0.f && r2 < rc2) {
+      float fr;
+      es = fmaf(qj, dh_energy_unit(r2, kappa, nkl, &fr), es);
+    }
+  }
+  *esum = warp_sum(es);
+  *dmin2 = wwarp_min(dm);
+}
+
+// the cached site potentials after the ion at o.pb appeared (dqb > 0) or vanished
+__device__ __forceinline__ void mc_ion_phi_share(const DevParams &p, const DevState &g, const WideState &w, size_t base, size_t cb,
+                                                 const McOrder &o, float kappa, float nkl, float rc2, int tid, int n_threads) {
+  const int *chg = g.chg + cb;
+  for (int ck = tid; ck < p.n_chg; ck += n_threads) {
+    if (ck == o.cbi) continue;
+    V3 d;
+    const float r2 = wdist2(p, o.pb, g.pos[base + chg[ck]], &d);
+    if (r2 < rc2) {
+      float fr;
+      w.phi[cb + ck] = fmaf(o.dqb, dh_energy_unit(r2, kappa, nkl, &fr), w.phi[cb + ck]);
+    }
+  }
+}
+
+// One CTA per replica: warp 0 runs the trial loop of chain_engine.cu::mc_block on global-memory
+// caches.  With explicit ions (p.n_ions > 0, blockDim = kMcThreads) an insertion / deletion needs
+// sums over all particles; warp 0 posts them as orders and the other warps, parked at a named
+// barrier, take their share.  Without ions the CTA is the one warp.
+__global__ void __launch_bounds__(kMcThreads)
 wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
             int m, int n_trials, cgpe_trial_record *trace_all) {
-  const int r = blockIdx.x, lane = threadIdx.x;
+  const int r = blockIdx.x, lane = threadIdx.x & 31, tid = threadIdx.x, n_threads = blockDim.x, n_warps = n_threads >> 5;
   const DevReaction rx = p.rx[m];
   const bool ions = p.n_ions > 0;
   const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
+  const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
+  __shared__ McOrder ord;
+  __shared__ float red_sum[32], red_min[32];
+  if (tid >= 32) {   // helpers
+    for (;;) {
+      mc_bar(n_threads);   // an order is posted
+      const McOrder o = ord;
+      if (o.op == kMcExit) return;
+      if (o.op == kMcIonEnergy) {
+        float es, dm;
+        mc_ion_energy_share(p, g, base, o, kappa, nkl, rc2, tid, n_threads, &es, &dm);
+        if (lane == 0) { red_sum[tid >> 5] = es; red_min[tid >> 5] = dm; }
+      } else {
+        mc_ion_phi_share(p, g, w, base, cb, o, kappa, nkl, rc2, tid, n_threads);
+      }
+      mc_bar(n_threads);   // shares are in
+    }
+  }
   int *lp = g.lst_prot + ((size_t)r * p.n_rx + m) * p.P, *ld = g.lst_deprot + ((size_t)r * p.n_rx + m) * p.P;
   int *ion_active = g.ion_active + (size_t)r * (ions ? p.n_ions : 1), *ion_free = g.ion_free + (size_t)r * (ions ? p.n_ions : 1);
   int n_p = g.cnt[((size_t)r * p.n_rx + m) * 2], n_d = g.cnt[((size_t)r * p.n_rx + m) * 2 + 1];
@@ -345,7 +563,6 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
   const float arg_fwd = (float)(2.302585092994045684 * (g.pH[r] - rx.pK)) * kLog2e;
   const float neg_beta_log2e = -rx.inv_kT * kLog2e;
   const float dq_fwd = rx.q_deprot - rx.q_prot, coul_fwd = p.dh_pref * dq_fwd;
-  const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
   const uint32_t k0 = rx.seed, k1 = (uint32_t)(p.replica_offset + r);
   const unsigned long long trial_ctr = (unsigned long long)g.trials[(size_t)r * p.n_rx + m];
   cgpe_trial_record *trace = trace_all ? trace_all + (size_t)r * n_trials : nullptr;
@@ -398,23 +615,14 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
           const float4 x = g.pos[base + b];
           pb4.x = x.x; pb4.y = x.y; pb4.z = x.z;
         }
-        float esum = 0.f, dmin2 = 3.0e38f;
-        for (int j = lane; j < p.P; j += 32) {
-          if (j == b) continue;
-          const int tj = j == i ? t_new : (int)g.type[base + j];
-          if (tj >= p.T) continue;
-          const float4 pj4 = g.pos[base + j];
-          const float qj = j == i ? q_new : pj4.w;
-          V3 d;
-          const float r2 = wdist2(p, pb4, pj4, &d);
-          dmin2 = fminf(dmin2, r2);
-          if (p.use_dh && qj != 0.f && r2 < rc2) {
-            float fr;
-            esum = fmaf(qj, dh_energy_unit(r2, kappa, nkl, &fr), esum);
-          }
-        }
-        esum = warp_sum(esum);
-        dmin2 = wwarp_min(dmin2);
+        float esum, dmin2;
+        if (lane == 0) { ord.op = kMcIonEnergy; ord.b = b; ord.i = i; ord.t_new = t_new; ord.q_new = q_new; ord.pb = pb4; }
+        mc_bar(n_threads);
+        mc_ion_energy_share(p, g, base, ord, kappa, nkl, rc2, tid, n_threads, &esum, &dmin2);
+        if (lane == 0) { red_sum[0] = esum; red_min[0] = dmin2; }
+        mc_bar(n_threads);
+        esum = warp_sum(lane < n_warps ? red_sum[lane] : 0.f);
+        dmin2 = wwarp_min(lane < n_warps ? red_min[lane] : 3.0e38f);
         const float e_ion = p.dh_pref * rx.q_ion * esum;
         de += fwd ? e_ion : -e_ion;
         excluded = dmin2 < rx.excl2;
@@ -473,16 +681,13 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
             }
           }
           if (fwd) { n_free -= 1; n_act += 1; } else { n_act -= 1; n_free += 1; }
-          if (p.use_dh)
-            for (int ck = lane; ck < p.n_chg; ck += 32) {
-              if (ck == cbi) continue;
-              V3 d;
-              const float r2 = wdist2(p, pb4, g.pos[base + chg[ck]], &d);
-              if (r2 < rc2) {
-                float fr;
-                w.phi[cb + ck] = fmaf(dqb, dh_energy_unit(r2, kappa, nkl, &fr), w.phi[cb + ck]);
-              }
-            }
+          if (p.use_dh) {
+            __syncwarp();
+            if (lane == 0) { ord.op = kMcIonPhi; ord.cbi = cbi; ord.dqb = dqb; ord.pb = pb4; }
+            mc_bar(n_threads);
+            mc_ion_phi_share(p, g, w, base, cb, ord, kappa, nkl, rc2, tid, n_threads);
+            mc_bar(n_threads);
+          }
           ion_moved = true;
           __syncwarp();
         }
@@ -506,6 +711,10 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
         }
       }
     }
+  }
+  if (n_threads > 32) {   // release the helpers
+    if (lane == 0) ord.op = kMcExit;
+    mc_bar(n_threads);
   }
   if (lane == 0) {
     g.cnt[((size_t)r * p.n_rx + m) * 2] = n_p; g.cnt[((size_t)r * p.n_rx + m) * 2 + 1] = n_d;
@@ -598,19 +807,26 @@ cudaError_t set_ints(int *a, int n, int v, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// cell grids + rows of the replicas whose flag is set (2 launches)
+void launch_rebuild(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st, int step = -1) {
+  const int nbw = (p.P + kWT - 1) / kWT, per = kWT / 32, nbd = p.use_dh ? std::min((p.n_chg + per - 1) / per, kRowSiteBlocks) : 0;
+  if (p.use_wca || p.use_dh) wk_cells<<<dim3(p.use_dh ? 2 : 1, p.R), kCT, 0, st>>>(p, g, w, step);
+  wk_rows<<<dim3(nbw + nbd, p.R), kWT, 0, st>>>(p, g, w, nbw, step);
+}
+
 // lists for the current positions, then forces where the cache is stale
 cudaError_t wide_prepare(const DevParams &p, const DevState &g, const WideState &w, int thermostat, cudaStream_t st, int *launches) {
   WCK(set_ints(w.flag, p.R, 1, st));
-  wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  launch_rebuild(p, g, w, st);
   if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, -1, 0);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, thermostat, nullptr);
-  *launches += 4;
+  *launches += 5;
   return cudaGetLastError();
 }
 
 void launch_step(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st) {
   wk_drift<<<grid_particles(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 0.f, 0.f);
-  wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  launch_rebuild(p, g, w, st, kStepFromDevice);
   if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 0);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 1, 1, nullptr);
 }
@@ -642,7 +858,7 @@ cudaError_t wide_steps(const DevParams &p, const DevState &g, const WideState &w
     for (; done + kGraphChunk <= n_max; done += kGraphChunk) WCK(cudaGraphLaunch(gc->exec, st));
   }
   for (; done < n_max; ++done) launch_step(p, g, w, st);
-  *launches += (p.use_dh ? 4 : 3) * n_max;
+  *launches += (p.use_dh ? 5 : 4) * n_max;
   return cudaGetLastError();
 }
 
@@ -672,11 +888,11 @@ cudaError_t wide_steepest_descent(const DevParams &p, const DevState &g, const W
   WCK(wide_prepare(p, g, w, 0, st, launches));
   for (int s = 0; s < n_steps; ++s) {
     wk_drift<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, gamma, max_disp);
-    wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+    launch_rebuild(p, g, w, st, s);
     if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, s, 0);
     wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, 0, 0, nullptr);
   }
-  *launches += 4 * n_steps + 1;
+  *launches += 5 * n_steps + 1;
   wk_finish_md<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, 0, 0);
   return cudaGetLastError();
 }
@@ -684,7 +900,7 @@ cudaError_t wide_steepest_descent(const DevParams &p, const DevState &g, const W
 cudaError_t wide_md_forces(const DevParams &p, const DevState &g, const WideState &w, float4 *out, cudaStream_t st) {
   WCK(set_ints(w.nsteps, p.R, 1, st));
   WCK(set_ints(w.flag, p.R, 1, st));
-  wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  launch_rebuild(p, g, w, st);
   if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, 0, 0);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, 0, 0, 0, out);
   return cudaGetLastError();
@@ -696,7 +912,7 @@ static cudaError_t wide_mc_blocks(const DevParams &p, const DevState &g, const W
   if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, 0, 1);
   wk_mc_prepare<<<grid_chargeable(p), kWT, 0, st>>>(p, g, w);
   for (int b = 0; b < n_blocks; ++b)
-    if (trials[b] > 0) wk_mc_block<<<p.R, 32, 0, st>>>(p, g, w, rx[b], trials[b], trace);
+    if (trials[b] > 0) wk_mc_block<<<p.R, p.n_ions > 0 ? kMcThreads : 32, 0, st>>>(p, g, w, rx[b], trials[b], trace);
   *launches += 2 + n_blocks;
   return cudaGetLastError();
 }
@@ -705,15 +921,15 @@ cudaError_t wide_mc_run(const DevParams &p, const DevState &g, const WideState &
                         cgpe_trial_record *trace, cudaStream_t st, int *launches) {
   WCK(set_ints(w.nsteps, p.R, 0, st));
   WCK(set_ints(w.flag, p.R, 1, st));
-  wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  launch_rebuild(p, g, w, st);
   WCK(set_ints(w.flag, p.R, 0, st));
-  *launches += 4;
+  *launches += 5;
   return wide_mc_blocks(p, g, w, 1, &m, &n_trials, trace, st, launches);
 }
 
 cudaError_t wide_list_stats(const DevParams &p, const DevState &g, const WideState &w, double *out, cudaStream_t st) {
   WCK(set_ints(w.flag, p.R, 1, st));
-  wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  launch_rebuild(p, g, w, st);
   WCK(set_ints(w.flag, p.R, 0, st));
   WCK(cudaMemsetAsync(out, 0, sizeof(double) * 4 * p.R, st));
   wk_list_stats<<<grid_particles(p), kWT, 0, st>>>(p, g, w, out);
@@ -726,9 +942,9 @@ cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideSt
                              cudaStream_t st, int *launches, WideGraphCache *gc) {
   WCK(set_ints(w.nsteps, p.R, 0, st));
   WCK(set_ints(w.flag, p.R, 1, st));
-  wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);
+  launch_rebuild(p, g, w, st);
   WCK(set_ints(w.flag, p.R, 0, st));
-  *launches += 4;
+  *launches += 5;
   for (int s = 0; s < sp.n_samples; ++s) {
     WCK(cudaMemsetAsync(w.sched_max, 0, sizeof(int), st));
     wk_schedule<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, sp, thr1, thr2);
@@ -737,12 +953,12 @@ cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideSt
     WCK(cudaStreamSynchronize(st));
     *launches += 1;
     if (n_max > 0) {
-      wk_rebuild<<<grid_particles(p), kWT, 0, st>>>(p, g, w);   // only replicas whose ions moved in the last MC block
+      launch_rebuild(p, g, w, st);   // only replicas whose ions moved in the last MC block
       if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, -1, 0);
       wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, 1, nullptr);   // stale forces only
       WCK(wide_steps(p, g, w, n_max, st, launches, gc));
       wk_finish_md<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, -1, 1);
-      *launches += 2;
+      *launches += 5;
     }
     if (sp.n_mc_blocks > 0) WCK(wide_mc_blocks(p, g, w, sp.n_mc_blocks, sp.mc_reaction, sp.mc_trials, nullptr, st, launches));
     WCK(launch_observables(p, g, tmp_d, tmp_d + p.R, tmp_i, st));

@@ -4,6 +4,20 @@
 
 namespace cgpe {
 
+// Cell grid of one particle set per replica: members sorted by cell (counting sort, ties by member
+// index, so the order is reproducible), rebuilt together with the Verlet rows.
+struct CellGrid {
+  int *start;         // [R][m_max + 1] first slot of each bucket; start[nc^3] = number of members
+  int *cursor;        // [R][m_max] counting / scatter cursor
+  int *cell_of;       // [R][n] cell of each member (-1: hidden slot, not in the grid)
+  int *tmp;           // [R][n] members by slot before the in-cell ordering
+  int *order;         // [R][n] member index by slot
+  float4 *spos;       // [R][n] member position (+ charge) by slot
+  int *nc;            // [R] buckets per edge of the table in use (1: a single bucket, every member is a candidate)
+  int *nf;            // [R] cells per box edge (folded onto the table modulo nc)
+  int n, m_max, nc_max;
+};
+
 // device arrays the wide engine adds to DevState
 struct WideState {
   float4 *ref;        // [R][P] positions at the last list build
@@ -13,7 +27,7 @@ struct WideState {
   float4 *fdh;        // [R][n_chg] Debye-Hueckel force on each chargeable particle (wk_dh_forces)
   int *dn;            // [R][n_chg]
   int *cidx;          // [R][P] particle -> chargeable index, -1 = never charged
-  int *flag;          // [R] list rebuild vote
+  int *flag;          // [R + 1] rows of replica r are stale; [R]: a particle left its skin/2 sphere (shared vote)
   int *nsteps;        // [R] MD steps of the current burst
   int *sched_max;     // [1] longest burst of the current sample
   int *step;          // [2] step index read by the kernels of a captured step (graph replay)
@@ -21,6 +35,7 @@ struct WideState {
   float *wcache;      // [R][n_chg] WCA type-swap energy
   uint8_t *rxof;      // [R][n_chg]
   uint8_t *wflag;     // [R][n_chg]
+  CellGrid cw, cd;    // cells over all particles (edge >= WCA list radius) / over chargeable ones (edge >= DH list radius)
   int cap_w, cap_d;
 };
 
