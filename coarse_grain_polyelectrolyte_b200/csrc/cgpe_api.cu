@@ -194,6 +194,21 @@ void free_wide(cgpe_handle *h) {
   h->wide = false;
 }
 
+// How the Debye-Hueckel rows of the global-memory engine are walked: by 8 lanes when they are short.
+// Expected entries = chargeable particles of a uniform box in the list sphere + those of a coil
+// (Flory exponent 0.6) of the own chain.
+void update_wide_policy(cgpe_handle *h) {
+  const DevParams &p = h->p;
+  const double rl = h->cfg.r_cut + p.skin, L = h->cfg.box_l;
+  const double uniform = p.n_chg * 4.18879 * rl * rl * rl / (L * L * L);
+  const double b = h->cfg.bond_r0 > 0.0 ? h->cfg.bond_r0 : 1.0;
+  const double frac = p.NC > 0 ? std::fmax(0.0, (double)(p.n_chg - p.n_ions)) / p.NC : 0.0;
+  const double coil = frac * std::fmin((double)p.N, std::pow(rl / b, 1.0 / 0.6));
+  const int short_rows = uniform + coil < 48.0 ? 1 : 0;
+  if (short_rows != h->w.dh_rows_short && h->wgraph.exec) { cudaStreamSynchronize(h->stream); wide_graph_release(&h->wgraph); }
+  h->w.dh_rows_short = short_rows;
+}
+
 // arrays of the global-memory engine, sized for the current shapes
 int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
   free_wide(h);
@@ -254,6 +269,7 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
     for (int c = 0; c < p.n_chg; ++c) cidx[(size_t)r * p.P + chg_packed[(size_t)r * p.n_chg + c]] = c;
   CU(cudaMemcpy(w.cidx, cidx.data(), sizeof(int) * RP, cudaMemcpyHostToDevice));
   h->wide = true;
+  update_wide_policy(h);
   return CGPE_OK;
 }
 
@@ -590,6 +606,7 @@ int cgpe_set_replica_params(cgpe_handle *h, const double *pH, const double *kapp
         rc_cap = ensure_wide(h, h->chg_host);
         if (rc_cap) return rc_cap;
       }
+      if (h->wide) update_wide_policy(h);
     }
     CU(up(h->g.rcut, r_cut));
   }

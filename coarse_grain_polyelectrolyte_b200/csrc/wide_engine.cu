@@ -162,8 +162,9 @@ wk_cells(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
     const int e = tmp[s], c = cell_of[e], lo = start[c], hi = start[c + 1];
     int rank = 0;
     for (int t = lo; t < hi; ++t) rank += tmp[t] < e ? 1 : 0;
-    order[lo + rank] = e;
-    spos[lo + rank] = g.pos[base + (kind == 0 ? e : chg[e])];
+    const int i = kind == 0 ? e : chg[e];   // chg ascends, so the order by member index is the order by particle
+    order[lo + rank] = i;
+    spos[lo + rank] = g.pos[base + i];
   }
 }
 
@@ -241,21 +242,29 @@ wk_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState g,
       if (g.type[base + i] < p.T) {
         const float4 pi = g.pos[base + i];
         uint32_t *dl = w.dl + (cb + ci) * w.cap_d;
-        for_cell_runs(p, start, gd, pi, [&](int lo, int hi) {
-          for (int s0 = lo; s0 < hi; s0 += 32) {
-            const int s = s0 + lane;
-            int cj = -1;
-            if (s < hi) {
-              V3 d;
-              if (wdist2(p, pi, spos[s], &d) < rlist_d2) cj = order[s];
-              if (cj == ci) cj = -1;
-            }
-            const uint32_t hit = __ballot_sync(0xffffffffu, cj >= 0);
-            const int slot = nd + __popc(hit & ((1u << lane) - 1u));
-            if (cj >= 0 && slot < w.cap_d) dl[slot] = (uint32_t)cj;
-            nd += __popc(hit);
+        // lanes 0..26 take one bucket each (a single bucket: all lanes stride over it); round t looks
+        // at the t-th member of every bucket, so the loads of a round are independent
+        int s = 0, end = 0, stride = 1;
+        if (gd.A == 1) { s = lane; end = start[1]; stride = 32; }
+        else if (lane < 27) {
+          const int cx = cell_coord(p, pi.x, gd.nf) + lane / 9 - 1, cy = cell_coord(p, pi.y, gd.nf) + (lane / 3) % 3 - 1,
+                    cz = cell_coord(p, pi.z, gd.nf) + lane % 3 - 1;
+          const int bkt = ((((cx + gd.nf) % gd.nf) % gd.A) * gd.A + ((cy + gd.nf) % gd.nf) % gd.A) * gd.A + ((cz + gd.nf) % gd.nf) % gd.A;
+          s = start[bkt];
+          end = start[bkt + 1];
+        }
+        for (; __any_sync(0xffffffffu, s < end); s += stride) {
+          int j = -1;
+          if (s < end) {
+            V3 d;
+            if (wdist2(p, pi, spos[s], &d) < rlist_d2) j = order[s];
+            if (j == i) j = -1;
           }
-        });
+          const uint32_t hit = __ballot_sync(0xffffffffu, j >= 0);
+          const int slot = nd + __popc(hit & ((1u << lane) - 1u));
+          if (j >= 0 && slot < w.cap_d) dl[slot] = (uint32_t)j;
+          nd += __popc(hit);
+        }
         if (nd > w.cap_d) { if (lane == 0) atomicOr(&g.err[r], kErrDhCap); nd = w.cap_d; }
       }
       if (lane == 0) w.dn[cb + ci] = nd;
@@ -264,24 +273,25 @@ wk_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState g,
 }
 
 // Debye-Hueckel force (mode 0) or potential sum_j q_j e(r) (mode 1) of every chargeable particle:
-// one warp per site, lanes stride over its contiguous row, warp-shuffle reduction.
+// LPS lanes per site stride over its contiguous row (LPS = 32 for the long rows of weak screening,
+// 8 for the short rows of a salty box), shuffle reduction within the group.
+template <int LPS>
 __global__ void __launch_bounds__(kWT)
 wk_dh_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
            int step, int mode) {
-  const int r = blockIdx.y, lane = threadIdx.x & 31, ci = blockIdx.x * (kWT / 32) + (threadIdx.x >> 5);
+  const int r = blockIdx.y, sub = threadIdx.x % LPS, ci = blockIdx.x * (kWT / LPS) + threadIdx.x / LPS;
   if (step == kStepFromDevice) step = w.step[1];
   if (mode == 0 && step >= w.nsteps[r]) return;
-  if (ci >= p.n_chg) return;
+  const bool site = ci < p.n_chg;   // no early exit: the shuffles below name the full warp
   const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
-  const int *chg = g.chg + cb;
-  const float4 pi4 = g.pos[base + chg[ci]];
+  const float4 pi4 = site ? g.pos[base + g.chg[cb + ci]] : make_float4(0.f, 0.f, 0.f, 0.f);
   float fx = 0.f, fy = 0.f, fz = 0.f, ph = 0.f;
-  if (mode == 1 || pi4.w != 0.f) {
+  if (site && (mode == 1 || pi4.w != 0.f)) {
     const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
     const uint32_t *row = w.dl + (cb + ci) * w.cap_d;
     const int n = w.dn[cb + ci];
-    for (int e = lane; e < n; e += 32) {
-      const float4 pj4 = g.pos[base + chg[row[e]]];
+    for (int e = sub; e < n; e += LPS) {
+      const float4 pj4 = g.pos[base + row[e]];
       if (pj4.w == 0.f) continue;
       V3 d;
       const float r2 = wdist2(p, pi4, pj4, &d);
@@ -294,13 +304,30 @@ wk_dh_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState
       }
     }
   }
-  if (mode == 1) {
-    ph = warp_sum(ph);
-    if (lane == 0) w.phi[cb + ci] = ph;
+#pragma unroll
+  for (int o = LPS / 2; o > 0; o >>= 1) {
+    if (mode == 1) ph += __shfl_xor_sync(0xffffffffu, ph, o);
+    else {
+      fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+  }
+  if (!site || sub != 0) return;
+  if (mode == 1) w.phi[cb + ci] = ph;
+  else {
+    const float sc = p.dh_pref * pi4.w;
+    w.fdh[cb + ci] = make_float4(sc * fx, sc * fy, sc * fz, 0.f);
+  }
+}
+
+// rows are short when a uniform box would put fewer than ~2 dozen chargeable particles in the list sphere
+inline bool short_dh_rows(const DevParams &p, const WideState &w) { return w.dh_rows_short != 0; }
+void launch_dh_rows(const DevParams &p, const DevState &g, const WideState &w, int step, int mode, cudaStream_t st) {
+  if (short_dh_rows(p, w)) {
+    const int per = kWT / 8;
+    wk_dh_rows<8><<<dim3((p.n_chg + per - 1) / per > 0 ? (p.n_chg + per - 1) / per : 1, p.R), kWT, 0, st>>>(p, g, w, step, mode);
   } else {
-    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-    const float s = p.dh_pref * pi4.w;
-    if (lane == 0) w.fdh[cb + ci] = make_float4(s * fx, s * fy, s * fz, 0.f);
+    const int per = kWT / 32;
+    wk_dh_rows<32><<<dim3((p.n_chg + per - 1) / per > 0 ? (p.n_chg + per - 1) / per : 1, p.R), kWT, 0, st>>>(p, g, w, step, mode);
   }
 }
 
@@ -481,24 +508,51 @@ __device__ __forceinline__ float wwarp_min(float v) {
 }
 
 // Work a trial hands to the whole CTA (explicit ions): the sums over all particles.
-struct McOrder { int op, b, i, t_new, cbi; float q_new, dqb; float4 pb; };
+struct McOrder { int op, b, cbi, ci, t_new; float q_new, dqb; float4 pb; };
 enum { kMcExit = 0, kMcIonEnergy = 1, kMcIonPhi = 2 };
-constexpr int kMcThreads = 1024;
+constexpr int kMcThreads = 512;       // CTA of a block of trials with explicit ions
+constexpr int kMcLoadThreads = 256;   // without ions: threads that fill the mirrors, then warp 0 runs alone
+constexpr size_t kMcStageLimit = 220 * 1024;   // mirrors larger than this stay in global memory
 
 __device__ __forceinline__ void mc_bar(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
 
-// interaction of the ion at o.pb with every visible particle (site o.i taken in its trial state):
+// What the trial loop reads.  STAGED: mirrors in shared memory, filled when the block starts and
+// written through to the global arrays, so a trial's chain of dependent reads (list entry -> site
+// -> cached potentials -> row partners) stays on the SM; otherwise the global arrays themselves.
+struct McView {
+  float4 *cpos;        // [n_chg] chargeable particles: position + charge           (staged only)
+  uint8_t *ctype;      // [n_chg] their types                                        (staged only)
+  float4 *npos;        // [P - n_chg] the other particles: never hidden, never moved  (staged, ions)
+  float *phi, *wcache; // [n_chg]
+  uint8_t *wflag;      // [n_chg]
+  int *cidx;           // [P]
+  int *lp, *ld;        // bookkeeping lists of the reaction
+  int *ion_active, *ion_free;
+  int n_other;
+};
+
+// bytes of the mirrors (host and device agree through this one function)
+__host__ __device__ inline size_t mc_stage_bytes(int P, int n_chg, int n_ions, bool with_ions) {
+  const size_t sites = (size_t)(n_chg - n_ions > 0 ? n_chg - n_ions : 0);
+  size_t b = (size_t)n_chg * (16 + 4 + 4) + (size_t)P * 4 + 2 * 4 * sites + 2 * (((size_t)n_chg + 15) / 16 * 16);
+  if (with_ions) b += (size_t)(P - n_chg) * 16 + 2 * 4 * (size_t)n_ions;
+  return b + 64;
+}
+
+// interaction of the ion at o.pb with every visible particle (site o.ci taken in its trial state):
 // this thread's share of  sum_j q_j e(r)  and of the smallest squared distance
-__device__ __forceinline__ void mc_ion_energy_share(const DevParams &p, const DevState &g, size_t base, const McOrder &o,
-                                                    float kappa, float nkl, float rc2, int tid, int n_threads,
+template <bool STAGED>
+__device__ __forceinline__ void mc_ion_energy_share(const DevParams &p, const DevState &g, const McView &v, size_t base, size_t cb,
+                                                    const McOrder &o, float kappa, float nkl, float rc2, int tid, int n_threads,
                                                     float *esum, float *dmin2) {
   float es = 0.f, dm = 3.0e38f;
-  for (int j = tid; j < p.P; j += n_threads) {
-    if (j == o.b) continue;
-    const int tj = j == o.i ? o.t_new : (int)g.type[base + j];
+  const int *chg = g.chg + cb;
+  for (int ck = tid; ck < p.n_chg; ck += n_threads) {
+    if (ck == o.cbi) continue;
+    const int tj = ck == o.ci ? o.t_new : (int)(STAGED ? v.ctype[ck] : g.type[base + chg[ck]]);
     if (tj >= p.T) continue;
-    const float4 pj4 = g.pos[base + j];
-    const float qj = j == o.i ? o.q_new : pj4.w;
+    const float4 pj4 = STAGED ? v.cpos[ck] : g.pos[base + chg[ck]];
+    const float qj = ck == o.ci ? o.q_new : pj4.w;
     V3 d;
     const float r2 = wdist2(p, o.pb, pj4, &d);
     dm = fminf(dm, r2);
@@ -507,58 +561,119 @@ __device__ __forceinline__ void mc_ion_energy_share(const DevParams &p, const De
       es = fmaf(qj, dh_energy_unit(r2, kappa, nkl, &fr), es);
     }
   }
+  if (STAGED) {
+    for (int k = tid; k < v.n_other; k += n_threads) {
+      V3 d;
+      dm = fminf(dm, wdist2(p, o.pb, v.npos[k], &d));
+    }
+  } else {
+    for (int j = tid; j < p.P; j += n_threads) {
+      if (v.cidx[j] >= 0 || g.type[base + j] >= p.T) continue;
+      V3 d;
+      dm = fminf(dm, wdist2(p, o.pb, g.pos[base + j], &d));
+    }
+  }
   *esum = warp_sum(es);
   *dmin2 = wwarp_min(dm);
 }
 
 // the cached site potentials after the ion at o.pb appeared (dqb > 0) or vanished
-__device__ __forceinline__ void mc_ion_phi_share(const DevParams &p, const DevState &g, const WideState &w, size_t base, size_t cb,
-                                                 const McOrder &o, float kappa, float nkl, float rc2, int tid, int n_threads) {
+template <bool STAGED>
+__device__ __forceinline__ void mc_ion_phi_share(const DevParams &p, const DevState &g, const WideState &w, const McView &v,
+                                                 size_t base, size_t cb, const McOrder &o, float kappa, float nkl, float rc2,
+                                                 int tid, int n_threads) {
   const int *chg = g.chg + cb;
   for (int ck = tid; ck < p.n_chg; ck += n_threads) {
     if (ck == o.cbi) continue;
     V3 d;
-    const float r2 = wdist2(p, o.pb, g.pos[base + chg[ck]], &d);
+    const float r2 = wdist2(p, o.pb, STAGED ? v.cpos[ck] : g.pos[base + chg[ck]], &d);
     if (r2 < rc2) {
       float fr;
-      w.phi[cb + ck] = fmaf(o.dqb, dh_energy_unit(r2, kappa, nkl, &fr), w.phi[cb + ck]);
+      const float ph = fmaf(o.dqb, dh_energy_unit(r2, kappa, nkl, &fr), v.phi[ck]);
+      v.phi[ck] = ph;
+      if (STAGED) w.phi[cb + ck] = ph;
     }
   }
 }
 
-// One CTA per replica: warp 0 runs the trial loop of chain_engine.cu::mc_block on global-memory
-// caches.  With explicit ions (p.n_ions > 0, blockDim = kMcThreads) an insertion / deletion needs
-// sums over all particles; warp 0 posts them as orders and the other warps, parked at a named
-// barrier, take their share.  Without ions the CTA is the one warp.
-__global__ void __launch_bounds__(kMcThreads)
+// One CTA per replica: warp 0 runs the trial loop of chain_engine.cu::mc_block.  With explicit ions
+// (IONS, blockDim = kMcThreads) an insertion / deletion needs sums over all particles; warp 0
+// posts them as orders and the other warps, parked at a named barrier, take their share.  Without
+// ions the other warps only help to fill the mirrors.
+template <bool IONS, bool STAGED>
+__global__ void __launch_bounds__(IONS ? kMcThreads : kMcLoadThreads)
 wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
             int m, int n_trials, cgpe_trial_record *trace_all) {
   const int r = blockIdx.x, lane = threadIdx.x & 31, tid = threadIdx.x, n_threads = blockDim.x, n_warps = n_threads >> 5;
   const DevReaction rx = p.rx[m];
-  const bool ions = p.n_ions > 0;
+  constexpr bool ions = IONS;
   const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
   const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
+  const int *chg = g.chg + cb;
+  int *g_lp = g.lst_prot + ((size_t)r * p.n_rx + m) * p.P, *g_ld = g.lst_deprot + ((size_t)r * p.n_rx + m) * p.P;
+  int *g_active = g.ion_active + (size_t)r * (ions ? p.n_ions : 1), *g_free = g.ion_free + (size_t)r * (ions ? p.n_ions : 1);
+  int n_p = g.cnt[((size_t)r * p.n_rx + m) * 2], n_d = g.cnt[((size_t)r * p.n_rx + m) * 2 + 1];
+  int n_act = ions ? g.ion_cnt[r * 2] : 0, n_free = ions ? g.ion_cnt[r * 2 + 1] : 0;
   __shared__ McOrder ord;
   __shared__ float red_sum[32], red_min[32];
-  if (tid >= 32) {   // helpers
+  __shared__ int n_other_s;
+  extern __shared__ __align__(16) unsigned char mc_smem[];
+  McView v;
+  if (STAGED) {
+    const int sites = max(p.n_chg - p.n_ions, 0), pad = (p.n_chg + 15) / 16 * 16;
+    unsigned char *q = mc_smem;
+    v.cpos = reinterpret_cast<float4 *>(q); q += (size_t)p.n_chg * 16;
+    v.npos = reinterpret_cast<float4 *>(q); q += ions ? (size_t)(p.P - p.n_chg) * 16 : 0;
+    v.phi = reinterpret_cast<float *>(q); q += (size_t)p.n_chg * 4;
+    v.wcache = reinterpret_cast<float *>(q); q += (size_t)p.n_chg * 4;
+    v.cidx = reinterpret_cast<int *>(q); q += (size_t)p.P * 4;
+    v.lp = reinterpret_cast<int *>(q); q += (size_t)sites * 4;
+    v.ld = reinterpret_cast<int *>(q); q += (size_t)sites * 4;
+    v.ion_active = reinterpret_cast<int *>(q); q += ions ? (size_t)p.n_ions * 4 : 0;
+    v.ion_free = reinterpret_cast<int *>(q); q += ions ? (size_t)p.n_ions * 4 : 0;
+    v.ctype = q; q += pad;
+    v.wflag = q;
+    if (tid == 0) n_other_s = 0;
+    __syncthreads();
+    for (int ck = tid; ck < p.n_chg; ck += n_threads) {
+      const int j = chg[ck];
+      v.cpos[ck] = g.pos[base + j]; v.ctype[ck] = g.type[base + j];
+      v.phi[ck] = w.phi[cb + ck]; v.wcache[ck] = w.wcache[cb + ck]; v.wflag[ck] = w.wflag[cb + ck];
+    }
+    for (int j = tid; j < p.P; j += n_threads) {
+      const int c = w.cidx[base + j];
+      v.cidx[j] = c;
+      if (ions && c < 0 && g.type[base + j] < p.T) v.npos[atomicAdd(&n_other_s, 1)] = g.pos[base + j];
+    }
+    for (int k = tid; k < n_p; k += n_threads) v.lp[k] = g_lp[k];
+    for (int k = tid; k < n_d; k += n_threads) v.ld[k] = g_ld[k];
+    if (ions) {
+      for (int k = tid; k < n_act; k += n_threads) v.ion_active[k] = g_active[k];
+      for (int k = tid; k < n_free; k += n_threads) v.ion_free[k] = g_free[k];
+    }
+    __syncthreads();
+    v.n_other = n_other_s;
+  } else {
+    v.cpos = nullptr; v.ctype = nullptr; v.npos = nullptr; v.n_other = 0;
+    v.phi = w.phi + cb; v.wcache = w.wcache + cb; v.wflag = w.wflag + cb; v.cidx = w.cidx + base;
+    v.lp = g_lp; v.ld = g_ld; v.ion_active = g_active; v.ion_free = g_free;
+  }
+  if (!IONS && tid >= 32) return;
+  if (IONS && tid >= 32) {   // helpers
     for (;;) {
       mc_bar(n_threads);   // an order is posted
       const McOrder o = ord;
       if (o.op == kMcExit) return;
       if (o.op == kMcIonEnergy) {
         float es, dm;
-        mc_ion_energy_share(p, g, base, o, kappa, nkl, rc2, tid, n_threads, &es, &dm);
+        mc_ion_energy_share<STAGED>(p, g, v, base, cb, o, kappa, nkl, rc2, tid, n_threads, &es, &dm);
         if (lane == 0) { red_sum[tid >> 5] = es; red_min[tid >> 5] = dm; }
       } else {
-        mc_ion_phi_share(p, g, w, base, cb, o, kappa, nkl, rc2, tid, n_threads);
+        mc_ion_phi_share<STAGED>(p, g, w, v, base, cb, o, kappa, nkl, rc2, tid, n_threads);
       }
       mc_bar(n_threads);   // shares are in
     }
   }
-  int *lp = g.lst_prot + ((size_t)r * p.n_rx + m) * p.P, *ld = g.lst_deprot + ((size_t)r * p.n_rx + m) * p.P;
-  int *ion_active = g.ion_active + (size_t)r * (ions ? p.n_ions : 1), *ion_free = g.ion_free + (size_t)r * (ions ? p.n_ions : 1);
-  int n_p = g.cnt[((size_t)r * p.n_rx + m) * 2], n_d = g.cnt[((size_t)r * p.n_rx + m) * 2 + 1];
-  int n_act = ions ? g.ion_cnt[r * 2] : 0, n_free = ions ? g.ion_cnt[r * 2 + 1] : 0;
   const int n_sites = n_p + n_d;
   const float arg_fwd = (float)(2.302585092994045684 * (g.pH[r] - rx.pK)) * kLog2e;
   const float neg_beta_log2e = -rx.inv_kT * kLog2e;
@@ -566,7 +681,6 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
   const uint32_t k0 = rx.seed, k1 = (uint32_t)(p.replica_offset + r);
   const unsigned long long trial_ctr = (unsigned long long)g.trials[(size_t)r * p.n_rx + m];
   cgpe_trial_record *trace = trace_all ? trace_all + (size_t)r * n_trials : nullptr;
-  const int *chg = g.chg + cb;
   long long acc = 0;
   bool ion_moved = false;
   int err = 0;
@@ -584,7 +698,8 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
                      a2 = __shfl_sync(0xffffffffu, o.z, tt);
       const bool fwd = (a0 >> 31) == 0;
       const int n_src = fwd ? n_p : n_d, n_dst = fwd ? n_d : n_p;
-      int *src = fwd ? lp : ld, *dst = fwd ? ld : lp;
+      int *src = fwd ? v.lp : v.ld, *dst = fwd ? v.ld : v.lp;
+      int *g_src = fwd ? g_lp : g_ld, *g_dst = fwd ? g_ld : g_lp;
       const float u = u24(a2);
       bool possible = n_src > 0;
       if (ions && !fwd && n_act == 0) possible = false;
@@ -594,31 +709,33 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
         continue;
       }
       const int k = (int)__umulhi(a1, (uint32_t)n_src);
-      const int i = src[k], ci = w.cidx[base + i];
+      const int i = src[k], ci = v.cidx[i];
       const int t_new = fwd ? rx.type_deprot : rx.type_prot;
       const float q_new = fwd ? rx.q_deprot : rx.q_prot, dq = fwd ? dq_fwd : -dq_fwd;
-      float de = w.wcache[cb + ci];
-      if (p.use_dh) de = fmaf(coul_fwd, w.phi[cb + ci], de);
+      float de = v.wcache[ci];
+      if (p.use_dh) de = fmaf(coul_fwd, v.phi[ci], de);
       if (!fwd) de = -de;
-      int b = -1, kb = 0;
+      int b = -1, kb = 0, cbi = -1;
       bool excluded = false;
       float4 pb4 = make_float4(0.f, 0.f, 0.f, rx.q_ion);
       if (ions) {   // see chain_engine.cu::mc_block
         if (fwd) {
-          b = ion_free[n_free - 1];
+          b = v.ion_free[n_free - 1];
+          cbi = v.cidx[b];
           pb4.x = u24(__shfl_sync(0xffffffffu, o1.x, tt)) * p.box_l;
           pb4.y = u24(__shfl_sync(0xffffffffu, o1.y, tt)) * p.box_l;
           pb4.z = u24(__shfl_sync(0xffffffffu, o1.z, tt)) * p.box_l;
         } else {
           kb = (int)__umulhi(__shfl_sync(0xffffffffu, o.w, tt), (uint32_t)n_act);
-          b = ion_active[kb];
-          const float4 x = g.pos[base + b];
+          b = v.ion_active[kb];
+          cbi = v.cidx[b];
+          const float4 x = STAGED ? v.cpos[cbi] : g.pos[base + b];
           pb4.x = x.x; pb4.y = x.y; pb4.z = x.z;
         }
         float esum, dmin2;
-        if (lane == 0) { ord.op = kMcIonEnergy; ord.b = b; ord.i = i; ord.t_new = t_new; ord.q_new = q_new; ord.pb = pb4; }
+        if (lane == 0) { ord.op = kMcIonEnergy; ord.b = b; ord.cbi = cbi; ord.ci = ci; ord.t_new = t_new; ord.q_new = q_new; ord.pb = pb4; }
         mc_bar(n_threads);
-        mc_ion_energy_share(p, g, base, ord, kappa, nkl, rc2, tid, n_threads, &esum, &dmin2);
+        mc_ion_energy_share<STAGED>(p, g, v, base, cb, ord, kappa, nkl, rc2, tid, n_threads, &esum, &dmin2);
         if (lane == 0) { red_sum[0] = esum; red_min[0] = dmin2; }
         mc_bar(n_threads);
         esum = warp_sum(lane < n_warps ? red_sum[lane] : 0.f);
@@ -631,32 +748,50 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
       const bool accept = u < bf;
       if (trace && lane == 0) { cgpe_trial_record rec = {i, b, (int8_t)(fwd ? 1 : -1), (int8_t)accept, (int8_t)excluded, 0, de, bf, u}; trace[b0 + tt] = rec; }
       if (accept) {
-        const float4 pi4 = g.pos[base + i];
-        const bool refresh = p.use_wca && w.wflag[cb + ci] != 0;
+        const float4 pi4 = STAGED ? v.cpos[ci] : g.pos[base + i];
+        const bool refresh = p.use_wca && v.wflag[ci] != 0;
+        __syncwarp();
         if (lane == 0) {
           g.type[base + i] = (uint8_t)t_new;
           g.pos[base + i].w = q_new;
-          src[k] = src[n_src - 1];
+          const int last = src[n_src - 1];
+          src[k] = last;
           dst[n_dst] = i;
+          if (STAGED) { v.ctype[ci] = (uint8_t)t_new; v.cpos[ci].w = q_new; g_src[k] = last; g_dst[n_dst] = i; }
         }
         if (fwd) { n_p -= 1; n_d += 1; } else { n_d -= 1; n_p += 1; }
         acc += 1;
         if (p.use_dh && dq != 0.f) {
           const int n = w.dn[cb + ci];
           const uint32_t *row = w.dl + (cb + ci) * w.cap_d;
-          for (int e = lane; e < n; e += 32) {
-            const int ck = row[e];
-            V3 d;
-            const float r2 = wdist2(p, pi4, g.pos[base + chg[ck]], &d);
-            if (r2 < rc2) {
-              float fr;
-              w.phi[cb + ck] = fmaf(dq, dh_energy_unit(r2, kappa, nkl, &fr), w.phi[cb + ck]);
+          // four row entries in flight per lane: the loads of a batch do not wait for one another
+          for (int e0 = lane; e0 < n; e0 += 128) {
+            int jj[4], ck[4];
+            float4 pj[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) jj[q] = e0 + 32 * q < n ? (int)row[e0 + 32 * q] : -1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (jj[q] >= 0) {
+                ck[q] = v.cidx[jj[q]];
+                pj[q] = STAGED ? v.cpos[ck[q]] : g.pos[base + jj[q]];
+              }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (jj[q] < 0) continue;
+              V3 d;
+              const float r2 = wdist2(p, pi4, pj[q], &d);
+              if (r2 < rc2) {
+                float fr;
+                const float ph = fmaf(dq, dh_energy_unit(r2, kappa, nkl, &fr), v.phi[ck[q]]);
+                v.phi[ck[q]] = ph;
+                if (STAGED) w.phi[cb + ck[q]] = ph;
+              }
             }
           }
         }
         __syncwarp();
         if (ions) {
-          const int cbi = w.cidx[base + b];
           const float dqb = fwd ? rx.q_ion : -rx.q_ion;
           const uint32_t w0 = __shfl_sync(0xffffffffu, o2.x, tt), w1 = __shfl_sync(0xffffffffu, o2.y, tt),
                          w2 = __shfl_sync(0xffffffffu, o2.z, tt), w3 = __shfl_sync(0xffffffffu, o2.w, tt);
@@ -671,13 +806,16 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
               sincosf(6.283185307179586f * ub, &sa, &ca);
               sincosf(6.283185307179586f * ud, &sb_, &cb_);
               g.vel[base + b] = make_float4(ra * ca, ra * sa, rb * cb_, 0.f);
-              ion_active[n_act] = b;
+              v.ion_active[n_act] = b;
+              if (STAGED) { v.ctype[cbi] = (uint8_t)rx.type_ion; v.cpos[cbi] = pb4; g_active[n_act] = b; }
             } else {
               g.type[base + b] = (uint8_t)p.T;
               g.pos[base + b].w = 0.f;
               g.vel[base + b] = make_float4(0.f, 0.f, 0.f, 0.f);
-              ion_active[kb] = ion_active[n_act - 1];
-              ion_free[n_free] = b;
+              const int last = v.ion_active[n_act - 1];
+              v.ion_active[kb] = last;
+              v.ion_free[n_free] = b;
+              if (STAGED) { v.ctype[cbi] = (uint8_t)p.T; v.cpos[cbi].w = 0.f; g_active[kb] = last; g_free[n_free] = b; }
             }
           }
           if (fwd) { n_free -= 1; n_act += 1; } else { n_act -= 1; n_free += 1; }
@@ -685,15 +823,16 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
             __syncwarp();
             if (lane == 0) { ord.op = kMcIonPhi; ord.cbi = cbi; ord.dqb = dqb; ord.pb = pb4; }
             mc_bar(n_threads);
-            mc_ion_phi_share(p, g, w, base, cb, ord, kappa, nkl, rc2, tid, n_threads);
+            mc_ion_phi_share<STAGED>(p, g, w, v, base, cb, ord, kappa, nkl, rc2, tid, n_threads);
             mc_bar(n_threads);
           }
           ion_moved = true;
           __syncwarp();
         }
-        if (refresh) {
+        if (refresh) {   // rare: a titratable neighbour within the WCA cutoff; reads the (written-through) global state
           const int l = chain_index(p, i), n_w = w.wn[base + i];
           const uint32_t *wl = w.wl + (size_t)r * w.cap_w * p.P;
+          __threadfence_block();
           for (int e = lane; e < n_w + 4; e += 32) {
             int j = -1;
             if (e < 4) {
@@ -703,8 +842,12 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
               j = wl[(size_t)(e - 4) * p.P + i];
             }
             if (j >= 0) {
-              const int cj = w.cidx[base + j];
-              if (cj >= 0 && w.rxof[cb + cj] != 255) w.wcache[cb + cj] = wide_wca_swap(p, g, w, r, cj, nullptr);
+              const int cj = v.cidx[j];
+              if (cj >= 0 && w.rxof[cb + cj] != 255) {
+                const float wc = wide_wca_swap(p, g, w, r, cj, nullptr);
+                v.wcache[cj] = wc;
+                if (STAGED) w.wcache[cb + cj] = wc;
+              }
             }
           }
           __syncwarp();
@@ -712,7 +855,7 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
       }
     }
   }
-  if (n_threads > 32) {   // release the helpers
+  if (IONS) {   // release the helpers
     if (lane == 0) ord.op = kMcExit;
     mc_bar(n_threads);
   }
@@ -787,7 +930,7 @@ wk_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
     const float rc = g.rcut[r];
     const uint32_t *row = w.dl + ((size_t)r * p.n_chg + ci) * w.cap_d;
     for (int e = 0; e < w.dn[(size_t)r * p.n_chg + ci]; ++e) {
-      const float4 pj4 = g.pos[base + g.chg[(size_t)r * p.n_chg + row[e]]];
+      const float4 pj4 = g.pos[base + row[e]];
       V3 d;
       a[2] += 1;
       if (pi4.w != 0.f && pj4.w != 0.f && wdist2(p, pi4, pj4, &d) < rc * rc) a[3] += 1;
@@ -818,7 +961,7 @@ void launch_rebuild(const DevParams &p, const DevState &g, const WideState &w, c
 cudaError_t wide_prepare(const DevParams &p, const DevState &g, const WideState &w, int thermostat, cudaStream_t st, int *launches) {
   WCK(set_ints(w.flag, p.R, 1, st));
   launch_rebuild(p, g, w, st);
-  if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, -1, 0);
+  if (p.use_dh) launch_dh_rows(p, g, w, -1, 0, st);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, thermostat, nullptr);
   *launches += 5;
   return cudaGetLastError();
@@ -827,7 +970,7 @@ cudaError_t wide_prepare(const DevParams &p, const DevState &g, const WideState 
 void launch_step(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st) {
   wk_drift<<<grid_particles(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 0.f, 0.f);
   launch_rebuild(p, g, w, st, kStepFromDevice);
-  if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 0);
+  if (p.use_dh) launch_dh_rows(p, g, w, kStepFromDevice, 0, st);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, kStepFromDevice, 1, 1, nullptr);
 }
 
@@ -889,7 +1032,7 @@ cudaError_t wide_steepest_descent(const DevParams &p, const DevState &g, const W
   for (int s = 0; s < n_steps; ++s) {
     wk_drift<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, gamma, max_disp);
     launch_rebuild(p, g, w, st, s);
-    if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, s, 0);
+    if (p.use_dh) launch_dh_rows(p, g, w, s, 0, st);
     wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, 0, 0, nullptr);
   }
   *launches += 5 * n_steps + 1;
@@ -901,7 +1044,7 @@ cudaError_t wide_md_forces(const DevParams &p, const DevState &g, const WideStat
   WCK(set_ints(w.nsteps, p.R, 1, st));
   WCK(set_ints(w.flag, p.R, 1, st));
   launch_rebuild(p, g, w, st);
-  if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, 0, 0);
+  if (p.use_dh) launch_dh_rows(p, g, w, 0, 0, st);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, 0, 0, 0, out);
   return cudaGetLastError();
 }
@@ -909,10 +1052,26 @@ cudaError_t wide_md_forces(const DevParams &p, const DevState &g, const WideStat
 static cudaError_t wide_mc_blocks(const DevParams &p, const DevState &g, const WideState &w, int n_blocks, const int *rx,
                                   const int *trials, cgpe_trial_record *trace, cudaStream_t st, int *launches) {
   wk_mc_classify<<<grid_chargeable(p), kWT, 0, st>>>(p, g, w);
-  if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, 0, 1);
+  if (p.use_dh) launch_dh_rows(p, g, w, 0, 1, st);
   wk_mc_prepare<<<grid_chargeable(p), kWT, 0, st>>>(p, g, w);
   for (int b = 0; b < n_blocks; ++b)
-    if (trials[b] > 0) wk_mc_block<<<p.R, p.n_ions > 0 ? kMcThreads : 32, 0, st>>>(p, g, w, rx[b], trials[b], trace);
+    if (trials[b] > 0) {
+      const bool ions = p.n_ions > 0;
+      const size_t bytes = mc_stage_bytes(p.P, p.n_chg, p.n_ions, ions);
+      const bool staged = bytes <= kMcStageLimit;
+      auto launch = [&](auto kernel, int threads) -> cudaError_t {
+        if (staged) {
+          cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+          if (e != cudaSuccess) return e;
+        }
+        kernel<<<p.R, threads, staged ? bytes : 0, st>>>(p, g, w, rx[b], trials[b], trace);
+        return cudaSuccess;
+      };
+      if (ions && staged) WCK(launch(wk_mc_block<true, true>, kMcThreads));
+      else if (ions) WCK(launch(wk_mc_block<true, false>, kMcThreads));
+      else if (staged) WCK(launch(wk_mc_block<false, true>, kMcLoadThreads));
+      else WCK(launch(wk_mc_block<false, false>, 32));
+    }
   *launches += 2 + n_blocks;
   return cudaGetLastError();
 }
@@ -954,7 +1113,7 @@ cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideSt
     *launches += 1;
     if (n_max > 0) {
       launch_rebuild(p, g, w, st);   // only replicas whose ions moved in the last MC block
-      if (p.use_dh) wk_dh_rows<<<grid_sites_warp(p), kWT, 0, st>>>(p, g, w, -1, 0);
+      if (p.use_dh) launch_dh_rows(p, g, w, -1, 0, st);
       wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, 1, nullptr);   // stale forces only
       WCK(wide_steps(p, g, w, n_max, st, launches, gc));
       wk_finish_md<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, -1, 1);

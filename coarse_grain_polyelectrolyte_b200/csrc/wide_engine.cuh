@@ -23,7 +23,7 @@ struct WideState {
   float4 *ref;        // [R][P] positions at the last list build
   uint32_t *wl;       // [R][cap_w][P] WCA Verlet rows (particle ids), column per particle
   int *wn;            // [R][P]
-  uint32_t *dl;       // [R][n_chg][cap_d] Debye-Hueckel rows (chargeable indices), one contiguous row per site
+  uint32_t *dl;       // [R][n_chg][cap_d] Debye-Hueckel rows (particle ids of chargeable particles), one contiguous row per site
   float4 *fdh;        // [R][n_chg] Debye-Hueckel force on each chargeable particle (wk_dh_forces)
   int *dn;            // [R][n_chg]
   int *cidx;          // [R][P] particle -> chargeable index, -1 = never charged
@@ -37,6 +37,7 @@ struct WideState {
   uint8_t *wflag;     // [R][n_chg]
   CellGrid cw, cd;    // cells over all particles (edge >= WCA list radius) / over chargeable ones (edge >= DH list radius)
   int cap_w, cap_d;
+  int dh_rows_short;  // rows are expected to hold a few dozen entries at most: 8 lanes per site instead of a warp
 };
 
 // One captured block of MD steps (CUDA graph), re-used while the kernel arguments stay the same.
