@@ -248,7 +248,8 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
   // (the kernels pick the cells per edge from the list radius in force at each build)
   auto grid = [&](CellGrid &cg, int n) -> cudaError_t {
     cg.n = n;
-    const int nc = (int)std::floor(std::cbrt(2.0 * (n > 0 ? n : 1)));
+    int nc = (int)std::floor(std::cbrt(2.0 * (n > 0 ? n : 1)));
+    if (const char *force = std::getenv("CGPE_GRID_NC_MAX")) nc = std::max(1, std::min(nc, std::atoi(force)));   // diagnostics only
     cg.nc_max = nc >= 3 ? nc : 1;
     cg.m_max = cg.nc_max * cg.nc_max * cg.nc_max;
     const size_t Rn = (size_t)p.R * (n > 0 ? n : 1);

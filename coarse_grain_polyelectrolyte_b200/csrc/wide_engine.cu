@@ -547,18 +547,31 @@ __device__ __forceinline__ void mc_ion_energy_share(const DevParams &p, const De
                                                     float *esum, float *dmin2) {
   float es = 0.f, dm = 3.0e38f;
   const int *chg = g.chg + cb;
-  for (int ck = tid; ck < p.n_chg; ck += n_threads) {
-    if (ck == o.cbi) continue;
-    const int tj = ck == o.ci ? o.t_new : (int)(STAGED ? v.ctype[ck] : g.type[base + chg[ck]]);
-    if (tj >= p.T) continue;
-    const float4 pj4 = STAGED ? v.cpos[ck] : g.pos[base + chg[ck]];
-    const float qj = ck == o.ci ? o.q_new : pj4.w;
-    V3 d;
-    const float r2 = wdist2(p, o.pb, pj4, &d);
-    dm = fminf(dm, r2);
-    if (p.use_dh && qj != 0.f && r2 < rc2) {
-      float fr;
-      es = fmaf(qj, dh_energy_unit(r2, kappa, nkl, &fr), es);
+  // batches of four particles per thread: the (global-memory) loads of a batch are issued together
+  for (int c0 = tid; c0 < p.n_chg; c0 += 4 * n_threads) {
+    int tj[4];
+    float4 pj[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ck = c0 + q * n_threads;
+      tj[q] = p.T;
+      if (ck < p.n_chg && ck != o.cbi) {
+        const int j = STAGED ? 0 : chg[ck];
+        tj[q] = ck == o.ci ? o.t_new : (int)(STAGED ? v.ctype[ck] : g.type[base + j]);
+        pj[q] = STAGED ? v.cpos[ck] : g.pos[base + j];
+        if (ck == o.ci) pj[q].w = o.q_new;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (tj[q] >= p.T) continue;
+      V3 d;
+      const float r2 = wdist2(p, o.pb, pj[q], &d);
+      dm = fminf(dm, r2);
+      if (p.use_dh && pj[q].w != 0.f && r2 < rc2) {
+        float fr;
+        es = fmaf(pj[q].w, dh_energy_unit(r2, kappa, nkl, &fr), es);
+      }
     }
   }
   if (STAGED) {
@@ -567,6 +580,7 @@ __device__ __forceinline__ void mc_ion_energy_share(const DevParams &p, const De
       dm = fminf(dm, wdist2(p, o.pb, v.npos[k], &d));
     }
   } else {
+#pragma unroll 4
     for (int j = tid; j < p.P; j += n_threads) {
       if (v.cidx[j] >= 0 || g.type[base + j] >= p.T) continue;
       V3 d;
@@ -583,15 +597,25 @@ __device__ __forceinline__ void mc_ion_phi_share(const DevParams &p, const DevSt
                                                  size_t base, size_t cb, const McOrder &o, float kappa, float nkl, float rc2,
                                                  int tid, int n_threads) {
   const int *chg = g.chg + cb;
-  for (int ck = tid; ck < p.n_chg; ck += n_threads) {
-    if (ck == o.cbi) continue;
-    V3 d;
-    const float r2 = wdist2(p, o.pb, STAGED ? v.cpos[ck] : g.pos[base + chg[ck]], &d);
-    if (r2 < rc2) {
-      float fr;
-      const float ph = fmaf(o.dqb, dh_energy_unit(r2, kappa, nkl, &fr), v.phi[ck]);
-      v.phi[ck] = ph;
-      if (STAGED) w.phi[cb + ck] = ph;
+  for (int c0 = tid; c0 < p.n_chg; c0 += 4 * n_threads) {
+    float4 pj[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ck = c0 + q * n_threads;
+      if (ck < p.n_chg && ck != o.cbi) pj[q] = STAGED ? v.cpos[ck] : g.pos[base + chg[ck]];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ck = c0 + q * n_threads;
+      if (ck >= p.n_chg || ck == o.cbi) continue;
+      V3 d;
+      const float r2 = wdist2(p, o.pb, pj[q], &d);
+      if (r2 < rc2) {
+        float fr;
+        const float ph = fmaf(o.dqb, dh_energy_unit(r2, kappa, nkl, &fr), v.phi[ck]);
+        v.phi[ck] = ph;
+        if (STAGED) w.phi[cb + ck] = ph;
+      }
     }
   }
 }

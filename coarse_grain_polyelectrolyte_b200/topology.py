@@ -24,6 +24,11 @@ def linear_polymer_positions(n_polymers, beads_per_chain, bond_length, seed, min
         raise ValueError("bond_length must be positive")
     rng = np.random.Generator(np.random.Philox(int(seed)))
     box = float(box_l) if box_l is not None else None
+    if min_distance <= 0.0 and start_positions is None:   # free random walks: no rejection, vectorised
+        steps = rng.normal(size=(n_polymers, beads_per_chain, 3))
+        steps *= bond_length / np.linalg.norm(steps, axis=2, keepdims=True)
+        steps[:, 0] = rng.random((n_polymers, 3)) * (box if box is not None else 1.0)
+        return np.cumsum(steps, axis=1)
     out = np.empty((n_polymers, beads_per_chain, 3))
     placed = np.empty((n_polymers * beads_per_chain, 3))
     n_placed = 0

@@ -51,11 +51,12 @@ EXAMPLE_PARAMETERS = {
 }
 
 
-def example_parameters(n_mon=100, c_salt=2e-2, **overrides):
-    """The reference's example dictionary for a chain of `n_mon` beads; the site counts follow
-    the every-third-bead pattern of M.py:126-155."""
+def example_parameters(n_mon=100, c_salt=2e-2, n_poly=1, **overrides):
+    """The reference's example dictionary for `n_poly` chains of `n_mon` beads; the site counts
+    (per chain, as Properties reads them) follow the every-third-bead pattern of M.py:126-155."""
     p = copy.deepcopy(EXAMPLE_PARAMETERS)
     role = topology.chain_site_pattern(n_mon)
+    p["System properties"]["Number of polymers"] = int(n_poly)
     p["System properties"]["Number of monomers"] = int(n_mon)
     p["System properties"]["NH monomers"] = int(np.sum(role == 1))
     p["System properties"]["NH2 monomers"] = int(np.sum(role == 2))
@@ -82,17 +83,18 @@ def num_samples(params):
 
 
 class Workload:
-    """A cgpe_config + start state + sampling schedule for R replicas of one chain."""
+    """A cgpe_config + start state + sampling schedule for R replicas of a box with
+    "Number of polymers" chains (+ explicit ions on request)."""
 
     def __init__(self, params, pH, c_salt=None, replica_offset=0, seed=12, device=-1, deprotonated=True,
-                 explicit_ions=False, ion_seed=10):
+                 explicit_ions=False, ion_seed=10, min_distance=None):
         self.params = params
         sp = params["System properties"]
         sc = params["Simulation configuration"]
         pH = np.atleast_1d(np.asarray(pH, dtype=np.float64))
         R = pH.size
         self.ru = ru = reduced_units(params)
-        n_mon = sp["Number of monomers"]
+        n_mon, n_poly = sp["Number of monomers"], sp["Number of polymers"]
         tix = ru.type_index
         c_salt_r = np.full(R, sp["Concentration salt particles"]) if c_salt is None else np.broadcast_to(
             np.asarray(c_salt, np.float64), (R,)).copy()
@@ -112,12 +114,12 @@ class Workload:
         ]
         # explicit ions (M.py:173-198): n_acid B+ and Cl-, n_salt Na+ and Cl-, plus one spare hidden
         # slot per site so that every site can release its H+
-        n_acid = sp["NH monomers"] + sp["NH2 monomers"]
+        n_acid = n_poly * (sp["NH monomers"] + sp["NH2 monomers"])
         ion_names = (["B"] * n_acid + ["Cl"] * n_acid + ["Na"] * ru.n_salt + ["Cl"] * ru.n_salt) if explicit_ions else []
         n_spare = n_acid if explicit_ions else 0
         self.n_ion_slots = len(ion_names) + n_spare
         self.cfg = _abi.make_config(
-            n_replicas=R, replica_offset=replica_offset, n_chains=1, n_beads=n_mon, n_ion_slots=self.n_ion_slots,
+            n_replicas=R, replica_offset=replica_offset, n_chains=n_poly, n_beads=n_mon, n_ion_slots=self.n_ion_slots,
             n_types=len(tix), bond_kind=_abi.BOND_FENE if sc["USE_FENE"] else _abi.BOND_HARMONIC,
             use_angle=int(sc["USE_BENDING"]), use_dihedral=int(sc["USE_DIHEDRAL_POT"]), dihedral_mult=3,
             use_wca=int(sc["USE_WCA"]), use_dh=int(sc["USE_ELECTROSTATICS"]),
@@ -128,16 +130,21 @@ class Workload:
             pH=float(pH[0]), kappa=float(self.kappa[0]), r_cut=float(self.r_cut[0]), kT=1.0, gamma=1.0,
             wca_eps=eps, wca_sig=sig, reactions=reactions, device=device)
         # topology + start state: every site starts deprotonated (M.py:130-147)
-        role = topology.chain_site_pattern(n_mon)
+        role = np.tile(topology.chain_site_pattern(n_mon), n_poly)
         if deprotonated:
             names = np.array(["CH2", "N", "N2"])[role]
         else:
             names = np.array(["CH2", "NH", "NH2"])[role]
         self.type = np.array([tix[n] for n in names], dtype=np.uint8)
         self.q = np.array([ru.charge[n] for n in names], dtype=np.float32)
-        pos = topology.linear_polymer_positions(1, n_mon, bond_length=ru.bond_length, seed=seed,
-                                                min_distance=0.9 * ru.bond_length, box_l=None)[0]
-        pos += 0.5 * ru.box_length - pos.mean(axis=0)
+        min_distance = 0.9 * ru.bond_length if min_distance is None else min_distance
+        if n_poly == 1:
+            pos = topology.linear_polymer_positions(1, n_mon, bond_length=ru.bond_length, seed=seed,
+                                                    min_distance=min_distance, box_l=None)[0]
+            pos += 0.5 * ru.box_length - pos.mean(axis=0)
+        else:   # chains start at random points of the box (M.py:116-122), coordinates unfolded
+            pos = topology.linear_polymer_positions(n_poly, n_mon, bond_length=ru.bond_length, seed=seed,
+                                                    min_distance=min_distance, box_l=ru.box_length).reshape(-1, 3)
         self.xyzq = np.concatenate([pos, self.q[:, None]], axis=1).astype(np.float32)
         if explicit_ions:
             rng = np.random.RandomState(ion_seed)          # np.random.seed(10), P.py:376
@@ -147,7 +154,7 @@ class Workload:
             self.xyzq = np.concatenate([self.xyzq, np.concatenate([ion_pos, ion_q[:, None]], axis=1).astype(np.float32)])
             self.type = np.concatenate([self.type, ion_type])
             self.q = np.concatenate([self.q, ion_q])
-        self.n_sites = (int(np.sum(role == 1)), int(np.sum(role == 2)))
+        self.n_sites = (int(np.sum(role == 1)), int(np.sum(role == 2)))   # all chains
         ns, nsi = num_samples(params)
         p = params["Montecarlo properties"]["PROB_REACTION"]
         self.sample_kwargs = dict(

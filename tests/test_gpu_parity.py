@@ -319,7 +319,8 @@ def _ion_state(w, seed, jitter=0.02):
     rng = np.random.default_rng(seed)
     R, P = w.R, w.xyzq.shape[0]
     xyzq = np.broadcast_to(w.xyzq, (R, P, 4)).copy()
-    xyzq[:, :w.cfg.n_beads, :3] += rng.normal(scale=jitter, size=(R, w.cfg.n_beads, 3)).astype(np.float32)
+    nc = w.cfg.n_chains * w.cfg.n_beads
+    xyzq[:, :nc, :3] += rng.normal(scale=jitter, size=(R, nc, 3)).astype(np.float32)
     vel = np.zeros((R, P, 4), np.float32)
     vel[..., :3] = rng.normal(size=(R, P, 3))
     return xyzq.astype(np.float32), vel, np.broadcast_to(w.type, (R, P)).copy()
@@ -327,16 +328,16 @@ def _ion_state(w, seed, jitter=0.02):
 
 def _wrap_ions(x, w):
     x = np.array(x, dtype=np.float64)
-    L = w.cfg.box_l
-    x[:, w.cfg.n_beads:] -= L * np.floor(x[:, w.cfg.n_beads:] / L)
+    L, nc = w.cfg.box_l, w.cfg.n_chains * w.cfg.n_beads
+    x[:, nc:] -= L * np.floor(x[:, nc:] / L)
     return x
 
 
 def _ion_dx(xg, xo, w):
     """max |dx| with ions compared modulo the box (the engine folds free particles, the oracle does not)"""
     d = np.asarray(xg, np.float64) - xo
-    L = w.cfg.box_l
-    d[:, w.cfg.n_beads:] -= L * np.rint(d[:, w.cfg.n_beads:] / L)
+    L, nc = w.cfg.box_l, w.cfg.n_chains * w.cfg.n_beads
+    d[:, nc:] -= L * np.rint(d[:, nc:] / L)
     return np.abs(d).max()
 
 
@@ -485,3 +486,72 @@ def test_explicit_ions_on_the_wide_engine(Engine, oracle_mod):
     np.testing.assert_array_equal(og[..., :3], oo[..., :3])
     np.testing.assert_array_equal(og[..., 2], og[..., 0] + og[..., 1])
     np.testing.assert_allclose(og[..., 3:5], oo[..., 3:5], rtol=2e-4)
+
+
+@pytest.mark.parametrize("n_poly,n_mon,ions", [
+    (3, 40, False),     # shared-memory engine
+    (3, 40, True),
+    (6, 400, False),    # 2400 beads: global-memory engine, cell grids over several chains
+    (4, 200, True),     # 800 beads + ions > 2048 particles
+])
+def test_several_chains_per_box(Engine, oracle_mod, n_poly, n_mon, ions):
+    """"Number of polymers" > 1 (P.py:384, M.py:116-170): chains share the box, interact through WCA and
+    Debye-Hueckel across chains, and every chain carries its own titratable sites; Rg / Ree are those of
+    the first chain (E.py:100-101 analyses chain_start=0, number_of_chains=1)."""
+    w = make_workload(n_mon, pH=[7.5, 9.0], explicit_ions=ions, n_poly=n_poly)
+    nc = n_poly * n_mon
+    assert w.cfg.n_chains == n_poly and w.xyzq.shape[0] == nc + w.cfg.n_ion_slots
+    assert (w.xyzq.shape[0] > 2048) == (n_mon >= 200)
+    state = _ion_state(w, seed=5) if ions else random_state(w, seed=5, jitter=0.03)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    eg, eo = g.energy(), o.energy()
+    scale = np.maximum(np.abs(eo), 1e-3 * np.abs(eo).max(axis=1, keepdims=True))
+    assert np.max(np.abs(eg - eo) / scale) < REL_TOL, (eg, eo)
+    fo = o.forces_f64()
+    for name, fg in (("all-pairs", g.forces()), ("md-lists", g.md_forces())):
+        assert np.abs(fg - fo).max() < REL_TOL * np.abs(fo).max(), name
+    rg_g, ree_g, cnt_g = g.observables()
+    rg_o, ree_o, cnt_o = o.observables()
+    np.testing.assert_allclose(rg_g, rg_o, rtol=1e-6)
+    np.testing.assert_allclose(ree_g, ree_o, rtol=1e-6)
+    np.testing.assert_array_equal(cnt_g, cnt_o)
+    for rx, n in ((0, 1500), (1, 300)):
+        tg = g.mc_run(rx, n, trace=True)
+        to, ties = o.mc_run_follow(rx, tg, tie_tol=1e-4)
+        assert ties <= 2
+        for f in ("particle", "ion_slot", "direction", "accepted", "excluded", "u"):
+            np.testing.assert_array_equal(tg[f], to[f], err_msg=f)
+        tried = (to["particle"] >= 0) & (to["excluded"] == 0)
+        err = np.abs(tg["delta_e"][tried] - to["delta_e"][tried]) / np.maximum(np.abs(to["delta_e"][tried]), 1.0)
+        assert err.max() < REL_TOL and tg["accepted"].sum() > 0
+        assert len(np.unique(tg["particle"][tg["particle"] >= 0] // n_mon)) == n_poly   # sites of every chain are drawn
+    o.set_list_mode(True, 0.8)
+    for e in (g, o):
+        e.md_run(8)
+    xg, vg, tyg = g.get_state()
+    xo, vo, qo = o.state_f64()
+    np.testing.assert_array_equal(tyg, o.get_state()[2])
+    assert _ion_dx(xg[..., :3], xo, w) < 1e-4 and np.abs(vg[..., :3] - vo).max() < 5e-3
+
+
+@pytest.mark.parametrize("c_salt", [2e-2, 1e-3])
+def test_cell_grid_rows_hold_every_pair_for_any_table_size(Engine, c_salt, monkeypatch):
+    """The list build of the global-memory engine folds the cells of the box onto a table of A^3 buckets.
+    Whatever A is (1 = a single bucket, 3 = every bucket is its own neighbour's neighbour, sizes that
+    trigger the wrap adjustment nf mod A in {1, 2}, the default), the forces through the rows must equal
+    the all-pairs forces, and the rows must hold the same pairs."""
+    w = make_workload(2500, pH=[6.0, 9.5], c_salt=c_salt)
+    state = random_state(w, seed=77, jitter=0.03)
+    ref_forces, ref_stats = None, None
+    for nc_max in (None, 1, 3, 4, 5, 6, 7, 9, 13):
+        if nc_max is None:
+            monkeypatch.delenv("CGPE_GRID_NC_MAX", raising=False)
+        else:
+            monkeypatch.setenv("CGPE_GRID_NC_MAX", str(nc_max))
+        g = load(Engine(w.cfg), w, state)
+        f_rows, stats = g.md_forces(), g.list_stats()
+        if ref_forces is None:
+            ref_forces, ref_stats = g.forces(), stats
+            assert stats[:, 0].min() > 0 and stats[:, 2].min() > 0
+        assert np.abs(f_rows - ref_forces).max() < REL_TOL * np.abs(ref_forces).max(), nc_max
+        np.testing.assert_array_equal(stats, ref_stats, err_msg=f"nc_max={nc_max}")
