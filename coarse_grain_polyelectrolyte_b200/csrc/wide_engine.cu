@@ -343,46 +343,74 @@ wk_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState 
   if (blockIdx.x == 0 && threadIdx.x == 0) { w.flag[r] = 0; if (r == 0) w.flag[p.R] = 0; }   // every block of wk_cells / wk_rows has seen them
   if (step >= w.nsteps[r]) return;
   if (mode == 0 && step < 0 && g.f_valid[r] && !out) return;   // cached forces are still good
-  if (i >= p.P) return;
   const size_t base = (size_t)r * p.P;
   const float4 *pos = g.pos + base;
   const uint8_t *type = g.type + base;
-  const float4 pi4 = pos[i];
-  const V3 pi = xyz(pi4);
-  const int ti = type[i], S = p.T + 1, l = chain_index(p, i), N = p.N;
+  const int S = p.T + 1, N = p.N, t0 = blockIdx.x * kWT, tid = threadIdx.x;
   int err = 0;
-  V3 f = {0.f, 0.f, 0.f};
-  if (l >= 0) {
-    V3 f1, f2, f3, f4;
-    // bonded terms this bead takes part in (M.py:159-170)
-    if (p.bond_kind != CGPE_BOND_NONE) {
-      if (l >= 1) { bond_term(p, pi, xyz(pos[i - 1]), &f1, &err); f = f + f1; }
-      if (l <= N - 2) { bond_term(p, pi, xyz(pos[i + 1]), &f1, &err); f = f + f1; }
+  // Chain-local terms, each computed once by its owner bead o: bond (o, o+1), angle (o-1, o, o+1),
+  // torsion (o-1, o, o+1, o+2) (M.py:159-170) and the WCA pairs (o, o+1), (o, o+2) that the rows
+  // leave out.  The four beads of an owner receive their shares through four slot planes (self,
+  // from o-1, from o+1, from o-2: one writer per entry, no atomics); owners t0-2 .. t0+kWT serve the
+  // tile, so the three beyond it are computed twice, once per neighbouring tile.
+  __shared__ float4 tpos[kWT + 6];
+  __shared__ uint8_t ttype[kWT + 6];
+  __shared__ float slot[4][3][kWT];
+  if (t0 < p.NC) {
+    for (int k = tid; k < kWT + 6; k += kWT) {
+      const int j = t0 - 3 + k;
+      const bool in = j >= 0 && j < p.P;
+      tpos[k] = in ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      ttype[k] = in ? type[j] : (uint8_t)p.T;
     }
-    if (p.use_angle) {
-      if (l >= 2) { angle_term(p, xyz(pos[i - 2]), xyz(pos[i - 1]), pi, &f1, &f2, &f3); f = f + f3; }
-      if (l >= 1 && l <= N - 2) { angle_term(p, xyz(pos[i - 1]), pi, xyz(pos[i + 1]), &f1, &f2, &f3); f = f + f2; }
-      if (l <= N - 3) { angle_term(p, pi, xyz(pos[i + 1]), xyz(pos[i + 2]), &f1, &f2, &f3); f = f + f1; }
-    }
-    if (p.use_dih)
-      for (int role = 0; role < 4; ++role) {
-        const int o = l + 1 - role;   // owner bead of the quadruple in which this bead is p1..p4
-        if (o >= 1 && o <= N - 3) {
-          const int b = i + 1 - role;
-          dihedral_term(p, xyz(pos[b - 1]), xyz(pos[b]), xyz(pos[b + 1]), xyz(pos[b + 2]), &f1, &f2, &f3, &f4);
-          f = f + (role == 0 ? f1 : role == 1 ? f2 : role == 2 ? f3 : f4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { slot[q][0][tid] = 0.f; slot[q][1][tid] = 0.f; slot[q][2][tid] = 0.f; }
+    __syncthreads();
+    for (int oi = tid; oi < kWT + 3; oi += kWT) {
+      const int o = t0 - 2 + oi;
+      if (o < 0 || o >= p.NC) continue;
+      const int l = chain_index(p, o), k = oi + 1;   // tpos[k] is bead o
+      const V3 xm = xyz(tpos[k - 1]), x0 = xyz(tpos[k]), x1 = xyz(tpos[k + 1]), x2 = xyz(tpos[k + 2]);
+      V3 fs = {0.f, 0.f, 0.f}, fa = fs, fb = fs, fc = fs, f1, f2, f3, f4;   // self, to o+1, to o-1, to o+2
+      if (p.bond_kind != CGPE_BOND_NONE && l <= N - 2) { bond_term(p, x0, x1, &f1, &err); fs = fs + f1; fa = fa - f1; }
+      if (p.use_angle && l >= 1 && l <= N - 2) { angle_term(p, xm, x0, x1, &f1, &f2, &f3); fb = fb + f1; fs = fs + f2; fa = fa + f3; }
+      if (p.use_dih && l >= 1 && l <= N - 3) {
+        dihedral_term(p, xm, x0, x1, x2, &f1, &f2, &f3, &f4);
+        fb = fb + f1; fs = fs + f2; fa = fa + f3; fc = fc + f4;
+      }
+      const int to = ttype[k];
+      if (p.use_wca && to < p.T) {
+        if (l <= N - 2 && ttype[k + 1] < p.T) {
+          const float4 tab = g.wca_tab[to * S + ttype[k + 1]];
+          const V3 d = x0 - x1;
+          const float r2 = dot(d, d);
+          if (r2 < tab.z) { const V3 fw = wca_force_over_r(tab, r2) * d; fs = fs + fw; fa = fa - fw; }
+        }
+        if (l <= N - 3 && ttype[k + 2] < p.T) {
+          const float4 tab = g.wca_tab[to * S + ttype[k + 2]];
+          const V3 d = x0 - x2;
+          const float r2 = dot(d, d);
+          if (r2 < tab.z) { const V3 fw = wca_force_over_r(tab, r2) * d; fs = fs + fw; fc = fc - fw; }
         }
       }
-    // WCA with the chain neighbours i+-1, i+-2 (not in the rows)
-    if (p.use_wca && ti < p.T)
-      for (int off = -2; off <= 2; ++off) {
-        if (off == 0 || l + off < 0 || l + off >= N) continue;
-        const int j = i + off, tj = type[j];
-        const float4 tab = g.wca_tab[ti * S + tj];
-        const V3 d = pi - xyz(pos[j]);
-        const float r2 = dot(d, d);
-        if (tj < p.T && r2 < tab.z) f = f + wca_force_over_r(tab, r2) * d;
-      }
+      const int e = oi - 2;   // tile index of bead o
+      if (e >= 0 && e < kWT) { slot[0][0][e] = fs.x; slot[0][1][e] = fs.y; slot[0][2][e] = fs.z; }
+      if (e + 1 >= 0 && e + 1 < kWT) { slot[1][0][e + 1] = fa.x; slot[1][1][e + 1] = fa.y; slot[1][2][e + 1] = fa.z; }
+      if (e - 1 >= 0 && e - 1 < kWT) { slot[2][0][e - 1] = fb.x; slot[2][1][e - 1] = fb.y; slot[2][2][e - 1] = fb.z; }
+      if (e + 2 >= 0 && e + 2 < kWT) { slot[3][0][e + 2] = fc.x; slot[3][1][e + 2] = fc.y; slot[3][2][e + 2] = fc.z; }
+    }
+    __syncthreads();
+  }
+  if (err) atomicOr(&g.err[r], err);
+  err = 0;
+  if (i >= p.P) return;
+  const float4 pi4 = pos[i];
+  const int ti = type[i];
+  V3 f = {0.f, 0.f, 0.f};
+  if (i < p.NC) {
+    f.x = (slot[0][0][tid] + slot[1][0][tid]) + (slot[2][0][tid] + slot[3][0][tid]);
+    f.y = (slot[0][1][tid] + slot[1][1][tid]) + (slot[2][1][tid] + slot[3][1][tid]);
+    f.z = (slot[0][2][tid] + slot[1][2][tid]) + (slot[2][2][tid] + slot[3][2][tid]);
   }
   if (p.use_wca && ti < p.T) {
     const uint32_t *wl = w.wl + (size_t)r * w.cap_w * p.P;
