@@ -277,10 +277,16 @@ class _Integrator:
         eng = self._system._ensure_engine()
         if self._mode == "sd":
             eng.steepest_descent(steps, **self._sd)
-        else:
-            self._system.thermostat._require()
-            eng.md_run(steps)
-        self._system._state_cache = None
+            self._system._state_cache = None
+            return
+        self._system.thermostat._require()
+        acc = self._system.auto_update_accumulators
+        while steps > 0:   # stop at every step count at which a registered accumulator is due (O.py:13-15)
+            n = steps if len(acc) == 0 else min(steps, acc.steps_until_next())
+            eng.md_run(n)
+            self._system._state_cache = None
+            acc.advance(n)
+            steps -= n
 
 
 class _Thermostat:
@@ -384,6 +390,7 @@ class System:
         self.integrator = _Integrator(self)
         self.thermostat = _Thermostat(self)
         self.analysis = _Analysis(self)
+        self.auto_update_accumulators = accumulators.AutoUpdateAccumulators()
         self._force_cap = 0.0
         self._time = 0.0
         # host-side description until (and between) engine builds
@@ -636,4 +643,4 @@ class System:
         return out
 
 
-from . import electrostatics, interactions, polymer, reaction_methods  # noqa: E402,F401
+from . import accumulators, electrostatics, interactions, observables, polymer, reaction_methods  # noqa: E402,F401

@@ -92,6 +92,9 @@ class EnsembleDynamics(Model):
     # -- E.py:75-119 ---------------------------------------------------------------------------------
     def perform_sampling(self, npH=None):
         system = self.system
+        if len(system.auto_update_accumulators) > 0:
+            # registered accumulators are fed by integrator.run: take the reference's loop call by call
+            return self._perform_sampling_stepwise()
         system.time = 0.0
         start = time.time()
         p = self.probability_reaction
@@ -115,6 +118,38 @@ class EnsembleDynamics(Model):
         self.elapsed_seconds = time.time() - start
         if self.verbose:
             print(f" Completed. Time elapsed: {self.elapsed_seconds:.2f} seconds.")
+
+    def _perform_sampling_stepwise(self):
+        """E.py:88-106 as written there: one engine call per line, the burst decisions drawn from numpy's
+        global stream (seeded 10 in Properties, P.py:376) and therefore shared by all replicas."""
+        system, R = self.system, self.system.n_replicas
+        system.time = 0.0
+        start = time.time()
+        p = self.probability_reaction
+        out = {k: np.zeros((R, self.num_samples)) for k in ("num_As", "num_As2", "num_B", "rad_gyr", "end_2end", "times")}
+        qdist = np.zeros((R, self.n_samp_iter, self.n_mon))
+        for i in range(self.num_samples):
+            if self.USE_WCA:
+                if np.random.random() < p:
+                    system.integrator.run(self.number_integration_steps)
+                if np.random.random() < p * (2.0 / (self.n_mon - 2)):
+                    system.integrator.run(self.number_integration_steps)
+            self.reaction1.reaction(reaction_steps=5 * self.n_nh + 1)
+            self.reaction2.reaction(reaction_steps=5 * self.n_nh2 + 1)
+            out["num_As"][:, i] = system.number_of_particles(type=self.type_particles["N"])
+            out["num_As2"][:, i] = system.number_of_particles(type=self.type_particles["N2"])
+            out["num_B"][:, i] = (system.number_of_particles(type=self.type_particles["B"]) if self.ion_model == "explicit"
+                                  else out["num_As"][:, i] + out["num_As2"][:, i])
+            out["rad_gyr"][:, i] = np.reshape(system.analysis.calc_rg(chain_start=0, number_of_chains=1, chain_length=self.n_mon)[0], -1)
+            out["end_2end"][:, i] = np.reshape(system.analysis.calc_re(chain_start=0, number_of_chains=1, chain_length=self.n_mon)[0], -1)
+            out["times"][:, i] = system.time
+            if i % self.n_samp_iter == 0 and i // self.n_samp_iter < self.n_samp_iter:
+                qdist[:, i // self.n_samp_iter, :] = np.reshape(system.part.by_ids(np.arange(self.n_mon)).q, (R, self.n_mon))
+        squeeze = (lambda a: a[0]) if R == 1 else (lambda a: a)
+        for k, v in out.items():
+            setattr(self, k, squeeze(v))
+        self.qdist = squeeze(qdist)
+        self.elapsed_seconds = time.time() - start
 
     # -- notebook cell 4 (NB:276-326): the pH sweep as one batched call ------------------------------
     def titration_curve(self):
