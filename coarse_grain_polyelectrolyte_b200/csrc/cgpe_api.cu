@@ -244,6 +244,11 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
   CU(alloc((void **)&w.wcache, sizeof(float) * RC));
   CU(alloc((void **)&w.rxof, RC));
   CU(alloc((void **)&w.wflag, RC));
+  CU(alloc((void **)&w.stale, RP));
+  w.mc_grid_ok = 1;
+  w.mc_stage_limit = 220 * 1024;
+  if (const char *e = std::getenv("CGPE_MC_STAGE_LIMIT")) w.mc_stage_limit = (size_t)std::atoll(e);   // diagnostics: force the
+  if (const char *e = std::getenv("CGPE_MC_GRID")) w.mc_grid_ok = std::atoi(e);                        // other trial-loop variants
   // cell grids of the list build: at most ~2 cells per member, edge never below the list radius
   // (the kernels pick the cells per edge from the list radius in force at each build)
   auto grid = [&](CellGrid &cg, int n) -> cudaError_t {
@@ -368,6 +373,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
     d.q_prot = (float)r.q_prot; d.q_deprot = (float)r.q_deprot; d.q_ion = (float)r.q_ion;
     d.inv_kT = (float)(1.0 / r.kT); d.pK = r.pK;
     d.excl2 = (float)(r.exclusion_range * r.exclusion_range); d.sqrt_kT = (float)std::sqrt(r.kT);
+    if (cfg->n_ion_slots > 0) p.grid_w_min = std::fmax(p.grid_w_min, (float)(r.exclusion_range * 1.001));
   }
   // chargeable particles are fixed at set_state; size the lists for "every third bead" + ions
   p.n_chg = 0;

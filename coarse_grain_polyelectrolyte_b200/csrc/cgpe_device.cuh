@@ -56,6 +56,7 @@ struct DevParams {
   float skin, half_skin2;       // Verlet skin, (skin/2)^2
   float rlist_w2;               // (max WCA cutoff + skin)^2
   float rc_w_max2;              // (max WCA cutoff)^2
+  float grid_w_min;             // smallest cell edge of the all-particle grid (explicit ions: the largest exclusion range)
   float force_cap;              // 0 = off
   SmemOff off;
   DevReaction rx[kMaxRx];

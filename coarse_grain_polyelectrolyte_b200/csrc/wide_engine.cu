@@ -108,9 +108,9 @@ __device__ __forceinline__ int bucket_id(const DevParams &p, float4 x, GridDims 
 __global__ void __launch_bounds__(kCT)
 wk_cells(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w, int step) {
   const int r = blockIdx.y, kind = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (!rebuild_due(p, w, r, step) || (kind == 0 ? !p.use_wca : !p.use_dh)) return;
+  if (!rebuild_due(p, w, r, step) || (kind == 0 ? !(p.use_wca || p.n_ions > 0) : !p.use_dh)) return;
   const CellGrid &cg = kind == 0 ? w.cw : w.cd;
-  const GridDims gd = grid_dims(p, kind == 0 ? sqrtf(p.rlist_w2) : g.rcut[r] + p.skin, cg.nc_max);
+  const GridDims gd = grid_dims(p, kind == 0 ? fmaxf(sqrtf(p.rlist_w2), p.grid_w_min) : g.rcut[r] + p.skin, cg.nc_max);
   const int M = gd.A * gd.A * gd.A, n = cg.n;
   const size_t base = (size_t)r * p.P;
   const int *chg = g.chg + (size_t)r * p.n_chg;
@@ -184,6 +184,23 @@ __device__ __forceinline__ void for_cell_runs(const DevParams &p, const int *sta
     }
 }
 
+// One warp visits the members of the 27 buckets around x: lanes 0..26 take one bucket each (a
+// single bucket: all lanes stride over it); round t hands visit(slot, active) the t-th member of
+// every bucket, so the loads of a round are independent.  visit runs converged (ballots allowed).
+template <class F>
+__device__ __forceinline__ void warp_for_neighbours(const DevParams &p, const int *start, GridDims gd, float4 x, int lane, F &&visit) {
+  int s = 0, end = 0, stride = 1;
+  if (gd.A == 1) { s = lane; end = start[1]; stride = 32; }
+  else if (lane < 27) {
+    const int cx = cell_coord(p, x.x, gd.nf) + lane / 9 - 1, cy = cell_coord(p, x.y, gd.nf) + (lane / 3) % 3 - 1,
+              cz = cell_coord(p, x.z, gd.nf) + lane % 3 - 1;
+    const int bkt = ((((cx + gd.nf) % gd.nf) % gd.A) * gd.A + ((cy + gd.nf) % gd.nf) % gd.A) * gd.A + ((cz + gd.nf) % gd.nf) % gd.A;
+    s = start[bkt];
+    end = start[bkt + 1];
+  }
+  for (; __any_sync(0xffffffffu, s < end); s += stride) visit(s, s < end);
+}
+
 constexpr int kRowSiteBlocks = 64;   // blocks per replica that build Debye-Hueckel rows (warps stride over the sites)
 
 // Verlet rows of the replicas that rebuild.  Blocks [0, nbw): one thread per particle collects its
@@ -242,20 +259,9 @@ wk_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState g,
       if (g.type[base + i] < p.T) {
         const float4 pi = g.pos[base + i];
         uint32_t *dl = w.dl + (cb + ci) * w.cap_d;
-        // lanes 0..26 take one bucket each (a single bucket: all lanes stride over it); round t looks
-        // at the t-th member of every bucket, so the loads of a round are independent
-        int s = 0, end = 0, stride = 1;
-        if (gd.A == 1) { s = lane; end = start[1]; stride = 32; }
-        else if (lane < 27) {
-          const int cx = cell_coord(p, pi.x, gd.nf) + lane / 9 - 1, cy = cell_coord(p, pi.y, gd.nf) + (lane / 3) % 3 - 1,
-                    cz = cell_coord(p, pi.z, gd.nf) + lane % 3 - 1;
-          const int bkt = ((((cx + gd.nf) % gd.nf) % gd.A) * gd.A + ((cy + gd.nf) % gd.nf) % gd.A) * gd.A + ((cz + gd.nf) % gd.nf) % gd.A;
-          s = start[bkt];
-          end = start[bkt + 1];
-        }
-        for (; __any_sync(0xffffffffu, s < end); s += stride) {
+        warp_for_neighbours(p, start, gd, pi, lane, [&](int s, bool active) {
           int j = -1;
-          if (s < end) {
+          if (active) {
             V3 d;
             if (wdist2(p, pi, spos[s], &d) < rlist_d2) j = order[s];
             if (j == i) j = -1;
@@ -264,7 +270,7 @@ wk_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState g,
           const int slot = nd + __popc(hit & ((1u << lane) - 1u));
           if (j >= 0 && slot < w.cap_d) dl[slot] = (uint32_t)j;
           nd += __popc(hit);
-        }
+        });
         if (nd > w.cap_d) { if (lane == 0) atomicOr(&g.err[r], kErrDhCap); nd = w.cap_d; }
       }
       if (lane == 0) w.dn[cb + ci] = nd;
@@ -539,8 +545,8 @@ __device__ __forceinline__ float wwarp_min(float v) {
 struct McOrder { int op, b, cbi, ci, t_new; float q_new, dqb; float4 pb; };
 enum { kMcExit = 0, kMcIonEnergy = 1, kMcIonPhi = 2 };
 constexpr int kMcThreads = 512;       // CTA of a block of trials with explicit ions
+constexpr int kMcChunk = 256;          // trials per launch when the ion sums come from the cell grids (IONS = 2)
 constexpr int kMcLoadThreads = 256;   // without ions: threads that fill the mirrors, then warp 0 runs alone
-constexpr size_t kMcStageLimit = 220 * 1024;   // mirrors larger than this stay in global memory
 
 __device__ __forceinline__ void mc_bar(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
 
@@ -625,17 +631,18 @@ __device__ __forceinline__ void mc_ion_phi_share(const DevParams &p, const DevSt
                                                  size_t base, size_t cb, const McOrder &o, float kappa, float nkl, float rc2,
                                                  int tid, int n_threads) {
   const int *chg = g.chg + cb;
-  for (int c0 = tid; c0 < p.n_chg; c0 += 4 * n_threads) {
+  const int n_site = p.n_chg - p.n_ions;   // chg ascends and the ion slots follow the chains: only sites own a potential
+  for (int c0 = tid; c0 < n_site; c0 += 4 * n_threads) {
     float4 pj[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int ck = c0 + q * n_threads;
-      if (ck < p.n_chg && ck != o.cbi) pj[q] = STAGED ? v.cpos[ck] : g.pos[base + chg[ck]];
+      if (ck < n_site && ck != o.cbi) pj[q] = STAGED ? v.cpos[ck] : g.pos[base + chg[ck]];
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int ck = c0 + q * n_threads;
-      if (ck >= p.n_chg || ck == o.cbi) continue;
+      if (ck >= n_site || ck == o.cbi) continue;
       V3 d;
       const float r2 = wdist2(p, o.pb, pj[q], &d);
       if (r2 < rc2) {
@@ -652,13 +659,20 @@ __device__ __forceinline__ void mc_ion_phi_share(const DevParams &p, const DevSt
 // (IONS, blockDim = kMcThreads) an insertion / deletion needs sums over all particles; warp 0
 // posts them as orders and the other warps, parked at a named barrier, take their share.  Without
 // ions the other warps only help to fill the mirrors.
-template <bool IONS, bool STAGED>
-__global__ void __launch_bounds__(IONS ? kMcThreads : kMcLoadThreads)
+//
+// IONS = 2 (replicas too large for the mirrors, e.g. a multi-chain box of 10^5 beads): the sums of
+// an ion move are local - charged particles within r_cut, any particle within the exclusion range
+// - and are taken from the cell grids by warp 0 alone.  The host hands such a block over in chunks
+// of kMcChunk trials with the grids rebuilt before each, so the grids know every particle where it
+// is except the ions inserted during the chunk: those are marked `stale` (skipped in the buckets)
+// and kept in a journal that every ion move also scans.
+template <int IONS, bool STAGED>
+__global__ void __launch_bounds__(IONS == 1 ? kMcThreads : kMcLoadThreads)
 wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
-            int m, int n_trials, cgpe_trial_record *trace_all) {
+            int m, int n_trials, cgpe_trial_record *trace_all, int trace_stride, int trace_offset) {
   const int r = blockIdx.x, lane = threadIdx.x & 31, tid = threadIdx.x, n_threads = blockDim.x, n_warps = n_threads >> 5;
   const DevReaction rx = p.rx[m];
-  constexpr bool ions = IONS;
+  constexpr bool ions = IONS != 0;
   const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
   const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
   const int *chg = g.chg + cb;
@@ -710,8 +724,8 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
     v.phi = w.phi + cb; v.wcache = w.wcache + cb; v.wflag = w.wflag + cb; v.cidx = w.cidx + base;
     v.lp = g_lp; v.ld = g_ld; v.ion_active = g_active; v.ion_free = g_free;
   }
-  if (!IONS && tid >= 32) return;
-  if (IONS && tid >= 32) {   // helpers
+  if (IONS != 1 && tid >= 32) return;
+  if (IONS == 1 && tid >= 32) {   // helpers
     for (;;) {
       mc_bar(n_threads);   // an order is posted
       const McOrder o = ord;
@@ -732,7 +746,10 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
   const float dq_fwd = rx.q_deprot - rx.q_prot, coul_fwd = p.dh_pref * dq_fwd;
   const uint32_t k0 = rx.seed, k1 = (uint32_t)(p.replica_offset + r);
   const unsigned long long trial_ctr = (unsigned long long)g.trials[(size_t)r * p.n_rx + m];
-  cgpe_trial_record *trace = trace_all ? trace_all + (size_t)r * n_trials : nullptr;
+  cgpe_trial_record *trace = trace_all ? trace_all + (size_t)r * trace_stride + trace_offset : nullptr;
+  __shared__ int journal[kMcChunk];
+  int n_journal = 0;
+  uint8_t *stale = w.stale + base;
   long long acc = 0;
   bool ion_moved = false;
   int err = 0;
@@ -785,6 +802,39 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
           pb4.x = x.x; pb4.y = x.y; pb4.z = x.z;
         }
         float esum, dmin2;
+        if (IONS == 2) {
+          float es = 0.f, dm = 3.0e38f;
+          // the particle in slot j as the trial sees it: type (hidden slots do not interact), position, charge
+          auto look = [&](int j, bool charged_only) {
+            if (j == b) return;
+            const int tj = j == i ? t_new : (int)g.type[base + j];
+            if (tj >= p.T) return;
+            const float4 pj4 = g.pos[base + j];
+            const float qj = j == i ? q_new : pj4.w;
+            V3 d;
+            const float r2 = wdist2(p, pb4, pj4, &d);
+            if (!charged_only) dm = fminf(dm, r2);
+            else if (p.use_dh && qj != 0.f && r2 < rc2) {
+              float fr;
+              es = fmaf(qj, dh_energy_unit(r2, kappa, nkl, &fr), es);
+            }
+          };
+          if (p.use_dh) {
+            const CellGrid &cg = w.cd;
+            const int *order = cg.order + (size_t)r * cg.n;
+            warp_for_neighbours(p, cg.start + (size_t)r * (cg.m_max + 1), GridDims{cg.nf[r], cg.nc[r]}, pb4, lane,
+                                [&](int s, bool active) { if (active) { const int j = order[s]; if (!stale[j]) look(j, true); } });
+          }
+          {
+            const CellGrid &cg = w.cw;
+            const int *order = cg.order + (size_t)r * cg.n;
+            warp_for_neighbours(p, cg.start + (size_t)r * (cg.m_max + 1), GridDims{cg.nf[r], cg.nc[r]}, pb4, lane,
+                                [&](int s, bool active) { if (active) { const int j = order[s]; if (!stale[j]) look(j, false); } });
+          }
+          for (int k = lane; k < n_journal; k += 32) { look(journal[k], true); look(journal[k], false); }
+          esum = warp_sum(es);
+          dmin2 = wwarp_min(dm);
+        } else {
         if (lane == 0) { ord.op = kMcIonEnergy; ord.b = b; ord.cbi = cbi; ord.ci = ci; ord.t_new = t_new; ord.q_new = q_new; ord.pb = pb4; }
         mc_bar(n_threads);
         mc_ion_energy_share<STAGED>(p, g, v, base, cb, ord, kappa, nkl, rc2, tid, n_threads, &esum, &dmin2);
@@ -792,6 +842,7 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
         mc_bar(n_threads);
         esum = warp_sum(lane < n_warps ? red_sum[lane] : 0.f);
         dmin2 = wwarp_min(lane < n_warps ? red_min[lane] : 3.0e38f);
+        }
         const float e_ion = p.dh_pref * rx.q_ion * esum;
         de += fwd ? e_ion : -e_ion;
         excluded = dmin2 < rx.excl2;
@@ -871,7 +922,30 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
             }
           }
           if (fwd) { n_free -= 1; n_act += 1; } else { n_act -= 1; n_free += 1; }
-          if (p.use_dh) {
+          if (IONS == 2) {
+            __syncwarp();
+            if (fwd && !stale[b]) {   // the grids hold slot b elsewhere (or not at all): journal it
+              if (lane == 0) { stale[b] = 1; journal[n_journal] = b; }
+              n_journal += 1;
+            }
+            if (p.use_dh) {   // cached potentials of the titratable sites around the ion
+              const CellGrid &cg = w.cd;
+              const int *order = cg.order + (size_t)r * cg.n;
+              warp_for_neighbours(p, cg.start + (size_t)r * (cg.m_max + 1), GridDims{cg.nf[r], cg.nc[r]}, pb4, lane,
+                                  [&](int s, bool active) {
+                if (!active) return;
+                const int j = order[s], ck = v.cidx[j];
+                if (j == b || w.rxof[cb + ck] == 255) return;
+                V3 d;
+                const float r2 = wdist2(p, pb4, g.pos[base + j], &d);
+                if (r2 < rc2) {
+                  float fr;
+                  v.phi[ck] = fmaf(dqb, dh_energy_unit(r2, kappa, nkl, &fr), v.phi[ck]);
+                }
+              });
+            }
+            __syncwarp();
+          } else if (p.use_dh) {
             __syncwarp();
             if (lane == 0) { ord.op = kMcIonPhi; ord.cbi = cbi; ord.dqb = dqb; ord.pb = pb4; }
             mc_bar(n_threads);
@@ -907,9 +981,13 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
       }
     }
   }
-  if (IONS) {   // release the helpers
+  if (IONS == 1) {   // release the helpers
     if (lane == 0) ord.op = kMcExit;
     mc_bar(n_threads);
+  }
+  if (IONS == 2) {
+    __syncwarp();
+    for (int k = lane; k < n_journal; k += 32) stale[journal[k]] = 0;
   }
   if (lane == 0) {
     g.cnt[((size_t)r * p.n_rx + m) * 2] = n_p; g.cnt[((size_t)r * p.n_rx + m) * 2 + 1] = n_d;
@@ -1005,7 +1083,7 @@ cudaError_t set_ints(int *a, int n, int v, cudaStream_t st) {
 // cell grids + rows of the replicas whose flag is set (2 launches)
 void launch_rebuild(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st, int step = -1) {
   const int nbw = (p.P + kWT - 1) / kWT, per = kWT / 32, nbd = p.use_dh ? std::min((p.n_chg + per - 1) / per, kRowSiteBlocks) : 0;
-  if (p.use_wca || p.use_dh) wk_cells<<<dim3(p.use_dh ? 2 : 1, p.R), kCT, 0, st>>>(p, g, w, step);
+  if (p.use_wca || p.use_dh || p.n_ions > 0) wk_cells<<<dim3(p.use_dh ? 2 : 1, p.R), kCT, 0, st>>>(p, g, w, step);
   wk_rows<<<dim3(nbw + nbd, p.R), kWT, 0, st>>>(p, g, w, nbw, step);
 }
 
@@ -1110,19 +1188,27 @@ static cudaError_t wide_mc_blocks(const DevParams &p, const DevState &g, const W
     if (trials[b] > 0) {
       const bool ions = p.n_ions > 0;
       const size_t bytes = mc_stage_bytes(p.P, p.n_chg, p.n_ions, ions);
-      const bool staged = bytes <= kMcStageLimit;
-      auto launch = [&](auto kernel, int threads) -> cudaError_t {
+      const bool staged = bytes <= w.mc_stage_limit;
+      auto launch = [&](auto kernel, int threads, int n, int offset) -> cudaError_t {
         if (staged) {
           cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
           if (e != cudaSuccess) return e;
         }
-        kernel<<<p.R, threads, staged ? bytes : 0, st>>>(p, g, w, rx[b], trials[b], trace);
-        return cudaSuccess;
+        kernel<<<p.R, threads, staged ? bytes : 0, st>>>(p, g, w, rx[b], n, trace, trials[b], offset);
+        return cudaGetLastError();
       };
-      if (ions && staged) WCK(launch(wk_mc_block<true, true>, kMcThreads));
-      else if (ions) WCK(launch(wk_mc_block<true, false>, kMcThreads));
-      else if (staged) WCK(launch(wk_mc_block<false, true>, kMcLoadThreads));
-      else WCK(launch(wk_mc_block<false, false>, 32));
+      if (ions && staged) WCK(launch(wk_mc_block<1, true>, kMcThreads, trials[b], 0));
+      else if (ions && w.mc_grid_ok) {
+        for (int t0 = 0; t0 < trials[b]; t0 += kMcChunk) {   // grids rebuilt before every chunk (see wk_mc_block)
+          WCK(set_ints(w.flag, p.R, 1, st));
+          wk_cells<<<dim3(p.use_dh ? 2 : 1, p.R), kCT, 0, st>>>(p, g, w, -1);
+          WCK(launch(wk_mc_block<2, false>, 32, std::min(kMcChunk, trials[b] - t0), t0));
+          *launches += 2;
+        }
+      }
+      else if (ions) WCK(launch(wk_mc_block<1, false>, kMcThreads, trials[b], 0));
+      else if (staged) WCK(launch(wk_mc_block<0, true>, kMcLoadThreads, trials[b], 0));
+      else WCK(launch(wk_mc_block<0, false>, 32, trials[b], 0));
     }
   *launches += 2 + n_blocks;
   return cudaGetLastError();

@@ -36,7 +36,10 @@ struct WideState {
   uint8_t *rxof;      // [R][n_chg]
   uint8_t *wflag;     // [R][n_chg]
   CellGrid cw, cd;    // cells over all particles (edge >= WCA list radius) / over chargeable ones (edge >= DH list radius)
+  uint8_t *stale;     // [R][P] ion slots inserted since the grids were built (trial moves through the grids)
   int cap_w, cap_d;
+  int mc_grid_ok;     // ion moves of replicas too large for the mirrors take their sums from the cell grids
+  size_t mc_stage_limit;   // largest set of trial-loop mirrors kept in shared memory (bytes)
   int dh_rows_short;  // rows are expected to hold a few dozen entries at most: 8 lanes per site instead of a warp
 };
 

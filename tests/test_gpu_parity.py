@@ -555,3 +555,37 @@ def test_cell_grid_rows_hold_every_pair_for_any_table_size(Engine, c_salt, monke
             assert stats[:, 0].min() > 0 and stats[:, 2].min() > 0
         assert np.abs(f_rows - ref_forces).max() < REL_TOL * np.abs(ref_forces).max(), nc_max
         np.testing.assert_array_equal(stats, ref_stats, err_msg=f"nc_max={nc_max}")
+
+
+@pytest.mark.parametrize("variant", ["mirrors", "all-particle sums", "cell grids"])
+def test_ion_moves_of_the_global_memory_engine_agree_in_every_variant(Engine, oracle_mod, variant, monkeypatch):
+    """The trial loop of the global-memory engine has three ways to get the sums of an ion insertion /
+    deletion: shared-memory mirrors (replicas up to ~7000 particles), all-particle sums from global memory,
+    and the cell grids in chunks of 256 trials with a journal of the ions inserted since the grids were built
+    (large boxes).  All three must reproduce the oracle's decisions, also over several blocks in a row so that
+    slots are deleted and re-used."""
+    if variant != "mirrors":
+        monkeypatch.setenv("CGPE_MC_STAGE_LIMIT", "0")
+        monkeypatch.setenv("CGPE_MC_GRID", "1" if variant == "cell grids" else "0")
+    w = make_workload(400, pH=[7.0, 8.5, 10.0], explicit_ions=True)
+    state = _ion_state(w, seed=21)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    n_acc = 0
+    for rx, n in ((0, 1500), (1, 150), (0, 1100), (1, 90)):
+        tg = g.mc_run(rx, n, trace=True)
+        to, ties = o.mc_run_follow(rx, tg, tie_tol=1e-4)
+        assert ties <= 2
+        for f in ("particle", "ion_slot", "direction", "accepted", "excluded", "u"):
+            np.testing.assert_array_equal(tg[f], to[f], err_msg=f"{variant}: {f}")
+        tried = (to["particle"] >= 0) & (to["excluded"] == 0)
+        err = np.abs(tg["delta_e"][tried] - to["delta_e"][tried]) / np.maximum(np.abs(to["delta_e"][tried]), 1.0)
+        assert err.max() < REL_TOL, (variant, err.max())
+        n_acc += int(tg["accepted"].sum())
+        # move the ions: the next block sees new positions and fresh rows.  The oracle then takes the device's
+        # coordinates (FP32 and FP64 trajectories part by ~1e-6, which Delta-E would see at the 1e-5 level).
+        g.md_run(3); o.md_run(3)
+        o.set_positions_f64(np.asarray(g.get_state()[0][..., :3], np.float64))
+    assert n_acc > 300
+    xg, vg, tyg = g.get_state()
+    np.testing.assert_array_equal(tyg, o.get_state()[2])
+    np.testing.assert_array_equal(g.observables()[2], o.observables()[2])
