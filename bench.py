@@ -293,6 +293,7 @@ def main():
     value = md_all * n_mon / (t_ms * 1e-3)
     e2e_value = md_e2e_all * n_mon / t_e2e
 
+    wide = w.xyzq.shape[0] > 2048          # replicas beyond the shared-memory engine run on the global-memory one
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         sm_count = info["sm_count"] or SM_COUNT_B200
@@ -313,7 +314,10 @@ def main():
                             "per GPU; step = perform_sampling loop body (Bernoulli bursts of 500 Langevin MD steps + "
                             f"{w.sample_kwargs['mc_blocks'][0][1]}+{w.sample_kwargs['mc_blocks'][1][1]} constant-pH trials + Rg/Ree/counts)",
                 "replicas_per_gpu": w.R, "n_mon": n_mon, "n_titratable": n_acid, "ion_model": "implicit (Debye-Hueckel)",
-                "l2": "replica state is shared-memory resident inside one launch; 256 MiB L2 flush before the timed region",
+                "engine": "global-memory (cell-grid lists, CUDA-graph steps)" if wide else "shared-memory (one persistent CTA per replica)",
+                "l2": ("replica state and Verlet rows live in global memory and are streamed by every kernel of a step; "
+                       "256 MiB L2 flush before the timed region" if wide else
+                       "replica state is shared-memory resident inside one launch; 256 MiB L2 flush before the timed region"),
                 "equil_md_steps": args.equil_steps, "skin": float(w.cfg.skin) or 0.8,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(args.steps, 1),
@@ -329,12 +333,16 @@ def main():
             "kernel_ms_cgpe_events": kernel_ms,
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"),
-                "traffic_source": (ncu_traffic() or {}).get("source", "no ncu capture committed"), "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_kind} clock; no FP32 entry in MEASURED_PEAKS.json)",
-                "kernel": "k_sample_loop",
+                "traffic": None if wide else (ncu_traffic() or {}).get("dram_bytes_per_launch"),
+                "traffic_source": "no ncu --set full capture of the global-memory engine's kernels committed" if wide
+                                  else (ncu_traffic() or {}).get("source", "no ncu capture committed"), "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_kind} clock; no FP32 entry in MEASURED_PEAKS.json)",
+                "kernel": "wk_forces + wk_dh_rows (per MD step) / wk_mc_block (trials)" if wide else "k_sample_loop",
                 "algorithmic_flop_per_md_step": per_step, "unique_listed_pairs": [float(s) / 2 for s in stats],
-                "note": "Verlet-list algorithm: work counted on the pairs the lists hold (SURVEY 8d formula); the kernel is "
-                        "barrier/latency-bound at one CTA per replica, not pipe-bound",
+                "note": ("Verlet-list algorithm: work counted on the pairs the lists hold (SURVEY 8d formula) over the whole step "
+                         "(all kernels); the force kernel is bound by L2 gathers of partner positions, the trial loop by its "
+                         "chain of dependent reads" if wide else
+                         "Verlet-list algorithm: work counted on the pairs the lists hold (SURVEY 8d formula); the kernel is "
+                         "barrier/latency-bound at one CTA per replica, not pipe-bound"),
                 "allpairs_equivalent_tflops": allpairs_equiv,
             },
             "observables_check": {"alpha_mean": float(obs[..., 0].mean() / max(w.n_sites[0], 1)),

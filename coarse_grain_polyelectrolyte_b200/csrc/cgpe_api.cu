@@ -137,8 +137,8 @@ int choose_capacities(cgpe_handle *h) {
   p.dw = ((n_chg + 31) / 32) | 1;   // odd row stride: thread-per-row reads hit distinct banks
   {
     // sub-threads per Debye-Hueckel row: as many as the block has threads for, at most 4
-    const int items = (p.P + 1023) / 1024, per = (p.P + items - 1) / (items > 0 ? items : 1);
-    const int threads = ((per + 31) / 32) * 32;
+    // (counted on one thread per particle: with two particles per thread a thread takes two sub-rows)
+    const int threads = ((std::min(p.P, 1024) + 31) / 32) * 32;
     int grp = n_chg > 0 ? threads / n_chg : 1;
     p.dh_group = grp < 1 ? 1 : grp > 4 ? 4 : grp;
   }

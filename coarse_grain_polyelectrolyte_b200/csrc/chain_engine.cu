@@ -21,6 +21,9 @@
 //   calc_rg / calc_re / number_of_particles   EnsembleDynamics.py:97-101
 #include "chain_engine.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace cgpe {
 
 // ------------------------------------------------------------------------------------------------
@@ -692,12 +695,13 @@ __device__ __forceinline__ float warp_min(float v) {
 // the ion's Debye-Hueckel energy with every particle and its distance to the nearest one
 // (exclusion range, M.py:202-206) come from one lane-parallel pass over all particles.  The ion
 // carries no WCA energy because cgpe_create insists on exclusion_range >= its largest WCA cutoff.
+template <bool IONS>
 __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_ctr, long long &accepted,
                          cgpe_trial_record *trace) {
   const DevParams &p = c.p;
   if (c.warp == 0 && n_trials > 0) {
     const DevReaction rx = p.rx[m];
-    const bool ions = p.n_ions > 0;
+    constexpr bool ions = IONS;   // compile-time: the implicit-ion kernels carry none of the ion code
     uint16_t *lp = c.s.lp + (size_t)m * p.n_chg, *ld = c.s.ld + (size_t)m * p.n_chg;
     int n_p = c.s.cnt[m * 2], n_d = c.s.cnt[m * 2 + 1];
     int n_act = ions ? c.s.flag[1] : 0, n_free = ions ? c.s.flag[2] : 0;
@@ -1060,7 +1064,7 @@ k_steepest_descent(const __grid_constant__ DevParams p, const __grid_constant__ 
   if (c.tid == 0) g.f_valid[c.r] = 0;
 }
 
-template <int ITEMS>
+template <int ITEMS, bool IONS>
 __global__ void __launch_bounds__(1024, 1)
 k_mc_run(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, int m, int n_trials,
          cgpe_trial_record *trace) {
@@ -1074,7 +1078,7 @@ k_mc_run(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
   mc_prepare(c);
   unsigned long long trial_ctr = (unsigned long long)g.trials[(size_t)c.r * p.n_rx + m];
   long long accepted = 0;
-  mc_block(c, m, n_trials, trial_ctr, accepted, trace ? trace + (size_t)c.r * n_trials : nullptr);
+  mc_block<IONS>(c, m, n_trials, trial_ctr, accepted, trace ? trace + (size_t)c.r * n_trials : nullptr);
   store_state(c, t, true);
   if (c.tid == 0) {
     g.trials[(size_t)c.r * p.n_rx + m] = (long long)trial_ctr;
@@ -1166,8 +1170,8 @@ k_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevSta
 }
 
 // The sampling loop of perform_sampling (E.py:88-106), one launch for all samples.
-template <int ITEMS>
-__global__ void __launch_bounds__(1024, 1)
+template <int ITEMS, bool IONS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevState g,
               const __grid_constant__ cgpe_sample_params sp, uint32_t thr1, uint32_t thr2, double *obs,
               float *qdist) {
@@ -1210,10 +1214,10 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
     if (sp.n_mc_blocks > 0) mc_prepare(c);      // per-site caches for this sample's trial moves
     for (int b = 0; b < sp.n_mc_blocks; ++b) {   // E.py:94-95
       const int m = sp.mc_reaction[b];
-      mc_block(c, m, sp.mc_trials[b], trial_ctr[m], accepted[m], nullptr);
+      mc_block<IONS>(c, m, sp.mc_trials[b], trial_ctr[m], accepted[m], nullptr);
       if (sp.mc_trials[b] > 0) f_valid = false;
     }
-    if (p.n_ions > 0 && c.s.flag[3]) lists_valid = false;   // ions were inserted / taken away: rows are stale
+    if (IONS && c.s.flag[3]) lists_valid = false;   // ions were inserted / taken away: rows are stale
     double rg, ree;
     chain_observables(c, t, &rg, &ree);   // E.py:100-101
     if (c.tid == 0) {
@@ -1222,7 +1226,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
       for (int m = 0; m < p.n_rx; ++m) n_ion += c.s.cnt[m * 2 + 1];
       o6[0] = p.n_rx > 0 ? c.s.cnt[1] : 0;   // E.py:97
       o6[1] = p.n_rx > 1 ? c.s.cnt[3] : 0;   // E.py:98
-      o6[2] = p.n_ions > 0 ? c.s.flag[1] : n_ion;   // E.py:99 (implicit ions: N_B = N_N + N_N2)
+      o6[2] = IONS ? c.s.flag[1] : n_ion;   // E.py:99 (implicit ions: N_B = N_N + N_N2)
       o6[3] = rg; o6[4] = ree;
       o6[5] = t0 + (double)steps * p.dt_d;   // E.py:102
     }
@@ -1257,9 +1261,15 @@ cudaError_t opt_in_smem(K kernel, size_t bytes) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+int chain_items(int P) {
+  int items = (P + 1023) / 1024;
+  if (const char *e = std::getenv("CGPE_ITEMS")) items = std::max(items, std::atoi(e));   // diagnostics: particles per thread
+  return items;
+}
+
 ChainLaunch chain_launch_shape(const DevParams &p) {
   ChainLaunch L{};
-  L.items = (p.P + 1023) / 1024;
+  L.items = chain_items(p.P);
   if (L.items > 2) { L.items = 0; return L; }   // beyond the shared-memory engine
   const int per = (p.P + L.items - 1) / L.items;
   L.threads = ((per + 31) / 32) * 32;
@@ -1289,7 +1299,7 @@ cudaError_t launch_steepest_descent(const DevParams &p, const DevState &g, const
 
 cudaError_t launch_mc_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int m, int n_trials,
                           cgpe_trial_record *trace, cudaStream_t st) {
-  auto k = L.items == 1 ? k_mc_run<1> : k_mc_run<2>;
+  auto k = p.n_ions > 0 ? (L.items == 1 ? k_mc_run<1, true> : k_mc_run<2, true>) : (L.items == 1 ? k_mc_run<1, false> : k_mc_run<2, false>);
   cudaError_t e = opt_in_smem(k, L.smem);
   if (e != cudaSuccess) return e;
   k<<<p.R, L.threads, L.smem, st>>>(p, g, m, n_trials, trace);
@@ -1315,7 +1325,8 @@ cudaError_t launch_list_stats(const DevParams &p, const DevState &g, const Chain
 cudaError_t launch_sample_loop(const DevParams &p, const DevState &g, const ChainLaunch &L,
                                const cgpe_sample_params &sp, uint32_t thr1, uint32_t thr2, double *obs,
                                float *qdist, cudaStream_t st) {
-  auto k = L.items == 1 ? k_sample_loop<1> : k_sample_loop<2>;
+  auto k = p.n_ions > 0 ? (L.items == 1 ? k_sample_loop<1, true, 1024> : k_sample_loop<2, true, 1024>)
+                        : (L.items == 1 ? k_sample_loop<1, false, 1024> : L.threads <= 512 ? k_sample_loop<2, false, 512> : k_sample_loop<2, false, 1024>);
   cudaError_t e = opt_in_smem(k, L.smem);
   if (e != cudaSuccess) return e;
   k<<<p.R, L.threads, L.smem, st>>>(p, g, sp, thr1, thr2, obs, qdist);

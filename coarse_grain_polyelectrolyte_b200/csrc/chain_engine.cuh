@@ -40,6 +40,7 @@ struct ChainLaunch {
 };
 
 size_t chain_smem_bytes(DevParams &p);   // lays the arrays out, fills p.off, returns the size
+int chain_items(int P);
 ChainLaunch chain_launch_shape(const DevParams &p);
 
 cudaError_t launch_md_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int n_steps, cudaStream_t st);
