@@ -36,3 +36,6 @@ if __name__ == "__main__":
     if which in ("all", "f"): run(1000, 1, 2e-2, 8.0, "single replica")
     if which in ("g",): run(1000, 128, 1e-3, 3.0, "1mM charged")
     if which in ("h",): run(1000, 128, 2e-3, 3.0, "2mM charged")
+    if which in ("i",): run(1000, 128, 1e-3, 12.5, "1mM neutral")
+    if which in ("j",):
+        for ph in (2.0, 6.0, 8.0, 9.0, 10.0, 12.0): run(1000, 128, 1e-3, ph, f"1mM pH {ph}")
