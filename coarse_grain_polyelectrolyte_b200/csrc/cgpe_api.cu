@@ -23,6 +23,7 @@ struct cgpe_handle {
   std::vector<void *> wide_allocs;
   std::vector<int> chg_host;   // [R][n_chg] chargeable particle ids (host copy)
   WideGraphCache wgraph;       // captured block of MD steps of the global-memory engine
+  void *dhc_alloc = nullptr;   // DevState::dhc
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
   int device;
@@ -427,6 +428,7 @@ void cgpe_destroy(cgpe_handle *h) {
   wide_graph_release(&h->wgraph);
   for (void *ptr : h->allocs) cudaFree(ptr);
   for (void *ptr : h->wide_allocs) cudaFree(ptr);
+  if (h->dhc_alloc) cudaFree(h->dhc_alloc);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_qdist) cudaFree(h->d_qdist);
   if (h->d_trace) cudaFree(h->d_trace);
@@ -514,11 +516,20 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     CU(cudaGetDeviceProperties(&prop, h->device));
     if (h->launch.smem > (size_t)prop.sharedMemPerBlockOptin) h->launch.items = 0;   // -> global-memory engine
   }
+  if (h->dhc_alloc) { cudaFree(h->dhc_alloc); h->dhc_alloc = nullptr; }
+  h->g.dhc = nullptr; p.dhc_cap = 0; p.dhc_stride = 0;
   if (h->launch.items == 0) {
     int rc_w = ensure_wide(h, chg_packed);
     if (rc_w) return rc_w;
   } else {
     free_wide(h);
+    if (p.use_dh && n_chg > 0) {   // compact partner lists of the shared-memory engine (chain_engine.cu::build_dh_compact)
+      const int G = p.dh_group > 0 ? p.dh_group : 1;
+      p.dhc_stride = (G * n_chg + 31) / 32 * 32;
+      p.dhc_cap = (((32 + G - 1) / G) * ((n_chg + 31) / 32) + 7) / 8 * 8;   // whole 16-byte groups of eight entries
+      CU(cudaMalloc(&h->dhc_alloc, sizeof(uint16_t) * (size_t)p.R * p.dhc_cap * p.dhc_stride));
+      h->g.dhc = static_cast<uint16_t *>(h->dhc_alloc);
+    }
   }
   // bookkeeping lists in particle-id order
   const size_t nrx = p.n_rx > 0 ? p.n_rx : 1;

@@ -30,7 +30,7 @@ struct DevReaction {
 // Byte offsets of the shared-memory arrays of the replica engine (chain_engine.cu).  They live in
 // the kernel-parameter constant bank, so an address is one add away and no pointer stays in a register.
 struct SmemOff {
-  int pos, tab, red, slot, fd, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, cpos, wrange, wflag, ratio, qlist, ionA, ionF, ionV, total;
+  int pos, tab, red, slot, fd, dhn, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, cpos, wrange, wflag, ratio, qlist, ionA, ionF, ionV, total;
 };
 
 // Uniform (replica-independent) parameters, passed to kernels by value.
@@ -56,6 +56,7 @@ struct DevParams {
   float skin, half_skin2;       // Verlet skin, (skin/2)^2
   float rlist_w2;               // (max WCA cutoff + skin)^2
   float rc_w_max2;              // (max WCA cutoff)^2
+  int dhc_cap, dhc_stride;      // compact Debye-Hueckel partner lists: entries per sub-thread, sub-threads per replica (padded)
   float grid_w_min;             // smallest cell edge of the all-particle grid (explicit ions: the largest exclusion range)
   float force_cap;              // 0 = off
   SmemOff off;
@@ -73,6 +74,7 @@ struct DevState {
   int *lst_prot;      // [R][n_rx][P] bookkeeping lists (particle ids), swap-remove order
   int *lst_deprot;    // [R][n_rx][P]
   int *cnt;           // [R][n_rx][2] n_prot, n_deprot
+  uint16_t *dhc;      // [R][dhc_cap / 8][dhc_stride][8] listed AND charged partners of every (site, sub-thread), shared-memory engine
   int *ion_active;    // [R][n_ions] particle ids of the free H+ (type_ion), swap-remove order
   int *ion_free;      // [R][n_ions] hidden slots, used as a stack
   int *ion_cnt;       // [R][2] n_active, n_free

@@ -43,6 +43,7 @@ size_t chain_smem_bytes(DevParams &p) {
   f.red = take(sizeof(double) * 32 * 4, 8);
   f.slot = take(sizeof(float) * 9 * p.NC, 4);
   f.fd = take(sizeof(float) * 3 * grp * n_chg, 4);
+  f.dhn = take(sizeof(uint16_t) * grp * n_chg, 2);
   f.cnt = take(sizeof(int) * kMaxRx * 2, 4);
   f.flag = take(sizeof(int) * 4, 4);
   f.wl = take(sizeof(uint16_t) * (size_t)p.cap_w * p.P, 4);
@@ -87,6 +88,7 @@ struct Ctx {
   int tid, nt, lane, warp;
   float kappa, rc2, neg_kappa_log2e, rlist_d2, rlist_max, gamma, noise_pref;
   bool wrap;          // false: every listed pair is closer directly than through any periodic image
+  bool compact;       // DevState::dhc holds the partners of the current rows and charges (see build_dh_compact)
   bool dense;         // Debye-Hueckel list radius ~ replica extent: loop over all charged particles instead of the bit rows
   int dh_g0, dh_ci0;  // this thread's first (sub-thread, row) work item of the Debye-Hueckel phase
   int err;            // thread-local error bits, merged at exit
@@ -350,6 +352,7 @@ __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
   if (c.wrap) build_rows<ITEMS, true>(c, t); else build_rows<ITEMS, false>(c, t);
   __syncthreads();   // Debye-Hueckel rows are read by other threads (sub-thread split, MC warp)
   c.rebuilds += 1;
+  c.compact = false;
 }
 
 // Compact list of the chargeable particles that carry charge right now (warp 0; callers put a
@@ -366,6 +369,41 @@ __device__ void build_qlist(Ctx &c) {
     }
     if (c.lane == 0) c.s.flag[0] = base;
   }
+}
+
+// The bit rows AND the charge mask say which partners a sub-thread visits, but walking them costs a
+// find-first-set chain per partner and, worse, the lanes of a warp fall out of step at every word
+// (each word lasts as long as its fullest lane).  Between two list builds of an MD burst neither
+// rows nor charges change, so every sub-thread (site ci, class g) writes its partners out once,
+// as a plain list it alone reads back: [k/8][sub-thread][k%8] in global memory (L2-resident, one
+// coalesced 16-byte load per eight partners, the next one in flight while these are evaluated).
+// The force loop is then a straight run of pairs, lanes in step until their lists end.
+__device__ void build_dh_compact(Ctx &c) {
+  const DevParams &p = c.p;
+  c.compact = false;
+  if (!p.use_dh || c.dense || c.g.dhc == nullptr) return;
+  const int G = p.dh_group;
+  uint16_t *lst0 = c.g.dhc + (size_t)c.r * p.dhc_cap * p.dhc_stride;
+  for (int idx = c.tid; idx < G * p.n_chg; idx += c.nt) {
+    const int g = idx / p.n_chg, ci = idx - g * p.n_chg;
+    const uint32_t sel = G == 1 ? 0xFFFFFFFFu : G == 2 ? (0x55555555u << g) : G == 3 ? (0x49249249u << g) : (0x11111111u << g);
+    uint16_t *lst = lst0 + (size_t)idx * 8;   // [k / 8][sub-thread][k % 8]: eight partners per 16-byte load
+    int n = 0;
+    if (c.s.cpos[ci].w != 0.0f) {
+      const int w_end = c.s.wrange[2 * ci + 1];
+      for (int w = c.s.wrange[2 * ci]; w < w_end; ++w) {
+        uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w] & sel;
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)(w * 32 + b);
+          ++n;
+        }
+      }
+    }
+    c.s.dhn[idx] = (uint16_t)n;
+  }
+  c.compact = true;   // every list is read only by the thread that wrote it: no barrier
 }
 
 // ---- forces ------------------------------------------------------------------------------------
@@ -479,6 +517,31 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
             f.x = fmaf(fr, d.x, f.x); f.y = fmaf(fr, d.y, f.y); f.z = fmaf(fr, d.z, f.z);
           }
         }
+      } else if (pi4.w != 0.0f && c.compact) {
+        const float qi = p.dh_pref * pi4.w;
+        const int n = c.s.dhn[idx];
+        const uint4 *lst = reinterpret_cast<const uint4 *>(c.g.dhc + (size_t)c.r * p.dhc_cap * p.dhc_stride) + idx;
+        uint4 cur = n > 0 ? __ldcg(lst) : make_uint4(0u, 0u, 0u, 0u);
+        for (int k0 = 0; k0 < n; k0 += 8) {
+          const uint4 nxt = k0 + 8 < n ? __ldcg(lst + (size_t)((k0 >> 3) + 1) * p.dhc_stride) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t pk[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (k0 + e < n) {
+              const int cj = (e & 1) ? (int)(pk[e >> 1] >> 16) : (int)(pk[e >> 1] & 0xFFFFu);
+              const float4 pj4 = c.s.cpos[cj];
+              V3 d;
+              const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
+              if (r2 < c.rc2) {
+                float fr;
+                dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr);
+                fr *= qi * pj4.w;
+                f.x = fmaf(fr, d.x, f.x); f.y = fmaf(fr, d.y, f.y); f.z = fmaf(fr, d.z, f.z);
+              }
+            }
+          }
+          cur = nxt;
+        }
       } else if (pi4.w != 0.0f) {
         const float qi = p.dh_pref * pi4.w;
         const int w_end = c.s.wrange[2 * ci + 1];
@@ -556,6 +619,7 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
   sync_ions(c, t);   // explicit ions moved or hidden by trial moves since the last burst
   if (!lists_valid) { build_lists(c, t); lists_valid = true; }
   if (p.use_dh) { build_qlist(c); __syncthreads(); }   // charges may have changed since the last burst
+  build_dh_compact(c);
   if (!f_valid) { compute_forces(c, t, true, counter); f_valid = true; }
   for (int step = 0; step < n_steps; ++step) {
     int moved = 0;
@@ -577,7 +641,7 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
         moved |= !(d2 <= p.half_skin2);  // also true for NaN
       }
     }
-    if (__syncthreads_or(moved)) build_lists(c, t);
+    if (__syncthreads_or(moved)) { build_lists(c, t); build_dh_compact(c); }
     counter += 1;
     compute_forces(c, t, true, counter);
 #pragma unroll
@@ -585,6 +649,7 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
 #pragma unroll
       for (int a = 0; a < 3; ++a) t.v[k][a] = fmaf(p.half_dt, t.f[k][a], t.v[k][a]);
   }
+  c.compact = false;   // trial moves change the charges
 }
 
 // ---- constant-pH trial moves (R1) ----------------------------------------------------------------
@@ -955,6 +1020,7 @@ __device__ void init_ctx(Ctx &c) {
   c.rlist_max = fmaxf(p.use_dh ? rc + p.skin : 0.f, p.use_wca ? sqrtf(p.rlist_w2) : 0.f);
   c.wrap = true;
   c.dense = false;
+  c.compact = false;
   c.dh_g0 = p.n_chg > 0 ? c.tid / p.n_chg : 0;
   c.dh_ci0 = c.tid - c.dh_g0 * p.n_chg;
   c.gamma = c.g.gamma[c.r];
@@ -972,6 +1038,7 @@ __device__ __forceinline__ void bind_smem(const DevParams &p, ChainSmem *s) {
   s->red = reinterpret_cast<double *>(smem_raw + f.red);
   s->slot = reinterpret_cast<float *>(smem_raw + f.slot);
   s->fd = reinterpret_cast<float *>(smem_raw + f.fd);
+  s->dhn = reinterpret_cast<uint16_t *>(smem_raw + f.dhn);
   s->cnt = reinterpret_cast<int *>(smem_raw + f.cnt);
   s->flag = reinterpret_cast<int *>(smem_raw + f.flag);
   s->wl = reinterpret_cast<uint16_t *>(smem_raw + f.wl);

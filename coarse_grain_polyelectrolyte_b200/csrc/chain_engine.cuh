@@ -11,6 +11,7 @@ struct ChainSmem {
   double *red;        // [32][4] block-reduction scratch
   float *slot;        // [3 slots][3][NC] bonded hand-over slots
   float *fd;          // [dh_group][3][n_chg] partial Debye-Hueckel forces per chargeable particle
+  uint16_t *dhn;      // [dh_group * n_chg] entries of each sub-thread's compact partner list (DevState::dhc)
   int *cnt;           // [n_rx][2] n_prot, n_deprot
   int *flag;          // [4]
   uint16_t *wl;       // [cap_w][P] WCA Verlet list (column per particle)

@@ -95,7 +95,7 @@ def test_mc_bookkeeping_bit_exact(Engine, oracle_mod, n_mon, n_trials):
     np.testing.assert_array_equal(g.observables()[2], o.observables()[2])
 
 
-@pytest.mark.parametrize("n_mon", [50, 100, 1000, 2500])
+@pytest.mark.parametrize("n_mon", [50, 100, 1000, 1500, 2500])   # 1500: two particles per thread; 2500: global-memory engine
 def test_md_steps_match_oracle(Engine, oracle_mod, n_mon):
     """One velocity-Verlet + Langevin step is a deterministic map given the Philox noise; FP32
     vs FP64 differ by rounding only.  The gap then grows with the Lyapunov exponent."""
@@ -589,3 +589,27 @@ def test_ion_moves_of_the_global_memory_engine_agree_in_every_variant(Engine, or
     xg, vg, tyg = g.get_state()
     np.testing.assert_array_equal(tyg, o.get_state()[2])
     np.testing.assert_array_equal(g.observables()[2], o.observables()[2])
+
+
+def test_compact_partner_lists_follow_charges_and_rebuilds(Engine, oracle_mod):
+    """The MD loop of the shared-memory engine walks per-thread lists of the listed AND charged partners,
+    written out at the start of a burst and after every list build.  Interleave bursts long enough to rebuild
+    the lists with reaction blocks that change which sites are charged, at weak screening (long rows) and with
+    explicit ions (every ion is a partner), and compare with the oracle step by step."""
+    for n_mon, ions, c_salt in ((150, False, 1e-3), (60, True, 2e-2)):
+        w = make_workload(n_mon, pH=[6.0, 8.5, 11.0], c_salt=c_salt, explicit_ions=ions)
+        state = _ion_state(w, seed=9) if ions else random_state(w, seed=9, jitter=0.02)
+        g, o = _pair(Engine, oracle_mod, w, state)
+        o.set_list_mode(True, 0.8)
+        for burst in range(4):
+            g.md_run(60); o.md_run(60)
+            xg = g.get_state()[0]
+            assert _ion_dx(xg[..., :3], o.state_f64()[0], w) < 2e-3, (n_mon, burst)
+            o.set_positions_f64(np.asarray(xg[..., :3], np.float64))     # keep the trajectories together
+            for rx, n in ((0, 300), (1, 40)):
+                tg = g.mc_run(rx, n, trace=True)
+                to, ties = o.mc_run_follow(rx, tg, tie_tol=1e-4)
+                np.testing.assert_array_equal(tg["accepted"], to["accepted"])
+            fo = o.forces_f64()
+            assert np.abs(g.md_forces() - fo).max() < REL_TOL * np.abs(fo).max()
+        assert g.counters()["list_rebuilds"].min() >= 4
