@@ -381,7 +381,7 @@ __device__ void build_qlist(Ctx &c) {
 __device__ void build_dh_compact(Ctx &c) {
   const DevParams &p = c.p;
   c.compact = false;
-  if (!p.use_dh || c.dense || c.g.dhc == nullptr) return;
+  if (!p.use_dh || c.dense || c.g.dhc == nullptr || p.n_chg < 97) return;   // short rows (<= 3 words): the walk is cheap, few warps hide the loads
   const int G = p.dh_group;
   uint16_t *lst0 = c.g.dhc + (size_t)c.r * p.dhc_cap * p.dhc_stride;
   for (int idx = c.tid; idx < G * p.n_chg; idx += c.nt) {
