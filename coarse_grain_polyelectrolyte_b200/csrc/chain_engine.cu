@@ -760,10 +760,45 @@ __device__ __forceinline__ float warp_min(float v) {
 // the ion's Debye-Hueckel energy with every particle and its distance to the nearest one
 // (exclusion range, M.py:202-206) come from one lane-parallel pass over all particles.  The ion
 // carries no WCA energy because cgpe_create insists on exclusion_range >= its largest WCA cutoff.
+//
+// An accepted flip changes the cached potential of every listed partner of the site: up to one
+// 32-lane pass per word of its row, a chain of dependent shared-memory accesses and MUFU calls each.
+// Warp 0 posts the flip as an order (site, dq, position) and the other warps, parked at a named
+// barrier while the trial loop runs, take one word each.
+__device__ __forceinline__ void mc_bar(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
+
+__device__ __forceinline__ void mc_phi_word(Ctx &c, int ci, int w, float dq, float4 pi4) {
+  const uint32_t mw = c.s.dbits[(size_t)ci * c.p.dw + w];
+  if ((mw >> c.lane) & 1u) {
+    const int ck = w * 32 + c.lane;
+    V3 d;
+    const float4 pk4 = c.s.cpos[ck];
+    const float r2 = c.wrap ? dist2<true>(c, pi4, pk4, &d) : dist2<false>(c, pi4, pk4, &d);
+    if (r2 < c.rc2) {
+      float fr;
+      c.s.phi[ck] = fmaf(dq, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), c.s.phi[ck]);
+    }
+  }
+}
+
 template <bool IONS>
 __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_ctr, long long &accepted,
                          cgpe_trial_record *trace) {
   const DevParams &p = c.p;
+  const bool helpers = p.use_dh && c.nt > 32;   // same for every thread
+  float *ord = reinterpret_cast<float *>(c.s.red);   // {x, y, z, -, dq, ci, op}: the reduction scratch is idle here
+  if (c.warp != 0 && n_trials > 0 && helpers) {
+    const int nw = (p.n_chg + 31) >> 5, n_help = (c.nt >> 5) - 1;
+    for (;;) {
+      mc_bar(c.nt);   // an order is posted
+      if (__float_as_int(ord[6]) == 0) break;
+      const int ci = __float_as_int(ord[5]);
+      const float dq = ord[4];
+      const float4 pi4 = make_float4(ord[0], ord[1], ord[2], 0.f);
+      for (int w = c.warp - 1; w < nw; w += n_help) mc_phi_word(c, ci, w, dq, pi4);
+      mc_bar(c.nt);   // the potentials are current
+    }
+  }
   if (c.warp == 0 && n_trials > 0) {
     const DevReaction rx = p.rx[m];
     constexpr bool ions = IONS;   // compile-time: the implicit-ion kernels carry none of the ion code
@@ -876,21 +911,20 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
           acc += 1;
           if (p.use_dh && dq != 0.f) {
             // phi of every listed partner inside r_cut changes by dq e(r): lane b handles bit b of
-            // each non-empty word
-            uint32_t live = __ballot_sync(0xffffffffu, row != 0u);
-            while (live) {
-              const int w = __ffs(live) - 1;
-              live &= live - 1;
-              const uint32_t mw = __shfl_sync(0xffffffffu, row, w);
-              if ((mw >> c.lane) & 1u) {
-                const int ck = w * 32 + c.lane;
-                V3 d;
-                const float4 pk4 = c.s.cpos[ck];
-                const float r2 = c.wrap ? dist2<true>(c, pi4, pk4, &d) : dist2<false>(c, pi4, pk4, &d);
-                if (r2 < c.rc2) {
-                  float fr;
-                  c.s.phi[ck] = fmaf(dq, dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr), c.s.phi[ck]);
-                }
+            // each non-empty word (the helpers one word each, see above)
+            if (helpers) {
+              if (c.lane == 0) {
+                ord[0] = pi4.x; ord[1] = pi4.y; ord[2] = pi4.z; ord[4] = dq;
+                ord[5] = __int_as_float(ci); ord[6] = __int_as_float(1);
+              }
+              mc_bar(c.nt);
+              mc_bar(c.nt);
+            } else {
+              uint32_t live = __ballot_sync(0xffffffffu, row != 0u);
+              while (live) {
+                const int w = __ffs(live) - 1;
+                live &= live - 1;
+                mc_phi_word(c, ci, w, dq, pi4);
               }
             }
           }
@@ -967,6 +1001,10 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
           }
         }
       }
+    }
+    if (helpers) {   // release the helpers
+      if (c.lane == 0) ord[6] = __int_as_float(0);
+      mc_bar(c.nt);
     }
     if (c.lane == 0) {
       c.s.cnt[m * 2] = n_p; c.s.cnt[m * 2 + 1] = n_d;
