@@ -173,6 +173,21 @@ __device__ __forceinline__ float dh_energy_unit(float r2, float kappa, float neg
   return e;
 }
 
+// F/r of the same term times q_j, written for the inner loop of the MD force phase: the only constant
+// is u's factor (1 + kappa r = 1 - u ln 2 with u = -kappa log2(e) r), the two MUFU results meet late.
+__device__ __forceinline__ float dh_force_unit_q(float r2, float neg_kappa_log2e, float qj) {
+  const float rinv = rsqrtf(r2), r = r2 * rinv, u = neg_kappa_log2e * r;
+  const float w = fast_ex2(u) * ((rinv * qj) * (rinv * rinv));
+  return fmaf(w * u, -0.693147180559945f, w);
+}
+
+// 16-byte shared-memory load from a 32-bit shared-space address
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------
 // bonded terms (unfolded coordinates).  Each returns the energy; forces by reference.
 // ------------------------------------------------------------------------------------------------

@@ -58,7 +58,7 @@ size_t chain_smem_bytes(DevParams &p) {
   f.phi = take(sizeof(float) * n_chg, 4);
   f.wc = take(sizeof(float) * n_chg, 4);
   f.rxof = take(n_chg, 1);
-  f.cpos = take(sizeof(float4) * n_chg, 16);
+  f.cpos = take(sizeof(float4) * (n_chg + 1), 16);   // +1: far-away, uncharged dummy that pads the compact partner lists
   f.wrange = take(2 * n_chg, 1);
   f.wflag = take(n_chg, 1);
   f.ratio = take(sizeof(float) * n_rx * (n_chg + 1), 4);
@@ -156,6 +156,7 @@ __device__ void load_state(Ctx &c, Thr<ITEMS> &t, bool f_valid) {
     c.s.cpos[i] = c.s.pos[c.s.chg[i]];
     c.s.wrange[2 * i] = 0; c.s.wrange[2 * i + 1] = 0;
   }
+  if (c.tid == 0) c.s.cpos[p.n_chg] = make_float4(1e10f, 1e10f, 1e10f, 0.0f);   // list padding (build_dh_compact)
   // live mask of the chargeable particles that carry charge right now (the MC warp keeps it current)
   for (int w = c.tid; w < p.dw; w += c.nt) {
     uint32_t m = 0;
@@ -396,12 +397,13 @@ __device__ void build_dh_compact(Ctx &c) {
         while (m) {
           const int b = __ffs(m) - 1;
           m &= m - 1;
-          lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)(w * 32 + b);
+          lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)((w * 32 + b) * 16);
           ++n;
         }
       }
     }
     c.s.dhn[idx] = (uint16_t)n;
+    for (; n & 7; ++n) lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)(p.n_chg * 16);
   }
   c.compact = true;   // every list is read only by the thread that wrote it: no barrier
 }
@@ -518,30 +520,36 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
           }
         }
       } else if (pi4.w != 0.0f && c.compact) {
-        const float qi = p.dh_pref * pi4.w;
+        // entries are byte offsets into cpos, groups of eight padded with the far-away uncharged dummy:
+        // no per-entry bounds test (WRAP keeps it: a folded dummy may land anywhere), no branch on the
+        // cutoff (91 % of the listed pairs are inside it; the rest select a zero), the shared address of
+        // cpos and the two loop constants pinned in registers instead of re-derived per pair
         const int n = c.s.dhn[idx];
         const uint4 *lst = reinterpret_cast<const uint4 *>(c.g.dhc + (size_t)c.r * p.dhc_cap * p.dhc_stride) + idx;
+        uint32_t cpos_sa = (uint32_t)__cvta_generic_to_shared(c.s.cpos);
+        float nk = c.neg_kappa_log2e, rc2 = c.rc2;
+        asm volatile("" : "+r"(cpos_sa), "+f"(nk), "+f"(rc2));
         uint4 cur = n > 0 ? __ldcg(lst) : make_uint4(0u, 0u, 0u, 0u);
         for (int k0 = 0; k0 < n; k0 += 8) {
-          const uint4 nxt = k0 + 8 < n ? __ldcg(lst + (size_t)((k0 >> 3) + 1) * p.dhc_stride) : make_uint4(0u, 0u, 0u, 0u);
+          lst += p.dhc_stride;
+          const uint4 nxt = k0 + 8 < n ? __ldcg(lst) : make_uint4(0u, 0u, 0u, 0u);
           const uint32_t pk[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            if (k0 + e < n) {
-              const int cj = (e & 1) ? (int)(pk[e >> 1] >> 16) : (int)(pk[e >> 1] & 0xFFFFu);
-              const float4 pj4 = c.s.cpos[cj];
-              V3 d;
-              const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
-              if (r2 < c.rc2) {
-                float fr;
-                dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr);
-                fr *= qi * pj4.w;
-                f.x = fmaf(fr, d.x, f.x); f.y = fmaf(fr, d.y, f.y); f.z = fmaf(fr, d.z, f.z);
-              }
-            }
+            const uint32_t off = (e & 1) ? (pk[e >> 1] >> 16) : (pk[e >> 1] & 0xFFFFu);
+            const float4 pj4 = lds_f4(cpos_sa + off);
+            V3 d;
+            const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
+            bool ok = r2 < rc2;
+            if (WRAP) ok = ok && (k0 + e < n);
+            float fr = dh_force_unit_q(r2, nk, pj4.w);
+            fr = ok ? fr : 0.0f;
+            f.x = fmaf(fr, d.x, f.x); f.y = fmaf(fr, d.y, f.y); f.z = fmaf(fr, d.z, f.z);
           }
           cur = nxt;
         }
+        const float qi = p.dh_pref * pi4.w;
+        f.x *= qi; f.y *= qi; f.z *= qi;
       } else if (pi4.w != 0.0f) {
         const float qi = p.dh_pref * pi4.w;
         const int w_end = c.s.wrange[2 * ci + 1];
