@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_TYPES = 16
 MAX_REACTIONS = 4
 MAX_MC_BLOCKS = 4
@@ -38,7 +38,7 @@ class Config(C.Structure):
         ("n_types", C.c_int32), ("bond_kind", C.c_int32), ("use_angle", C.c_int32),
         ("use_dihedral", C.c_int32), ("dihedral_mult", C.c_int32), ("use_wca", C.c_int32),
         ("use_dh", C.c_int32), ("n_reactions", C.c_int32), ("cap_wca", C.c_int32),
-        ("cap_dh", C.c_int32), ("device", C.c_int32), ("reserved0", C.c_int32),
+        ("cap_dh", C.c_int32), ("device", C.c_int32), ("fixed_type_mask", C.c_int32),
         ("bond_k", C.c_double), ("bond_r0", C.c_double), ("fene_drmax", C.c_double),
         ("angle_k", C.c_double), ("angle_phi0", C.c_double),
         ("dihedral_k", C.c_double), ("dihedral_phase", C.c_double),

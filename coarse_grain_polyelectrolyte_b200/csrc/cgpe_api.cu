@@ -24,6 +24,7 @@ struct cgpe_handle {
   std::vector<int> chg_host;   // [R][n_chg] chargeable particle ids (host copy)
   WideGraphCache wgraph;       // captured block of MD steps of the global-memory engine
   void *dhc_alloc = nullptr;   // DevState::dhc
+  bool two_radii = false;      // see upload_wca
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
   int device;
@@ -79,6 +80,8 @@ int validate(const cgpe_config *c) {
   if (c->n_replicas < 1 || c->n_chains < 1 || c->n_beads < 1 || c->n_ion_slots < 0)
     return fail(nullptr, CGPE_ERR_INVALID, "n_replicas, n_chains, n_beads must be >= 1");
   if (c->n_types < 1 || c->n_types > CGPE_MAX_TYPES) return fail(nullptr, CGPE_ERR_INVALID, "n_types out of range");
+  if (c->fixed_type_mask < 0 || (c->fixed_type_mask >> c->n_types) != 0)
+    return fail(nullptr, CGPE_ERR_INVALID, "fixed_type_mask names a type >= n_types");
   if (c->n_reactions < 0 || c->n_reactions > CGPE_MAX_REACTIONS)
     return fail(nullptr, CGPE_ERR_INVALID, "n_reactions out of range");
   if (!(c->box_l > 0.0) || !(c->time_step > 0.0))
@@ -110,7 +113,8 @@ int validate(const cgpe_config *c) {
 int upload_wca(cgpe_handle *h) {
   const int T = h->cfg.n_types, S = T + 1;
   std::vector<float4> tab((size_t)S * S, make_float4(0.f, 0.f, 0.f, 0.f));
-  double rc_max = 0.0;
+  double rc_max = 0.0, rc_free = 0.0;   // over all type pairs / over pairs of types that move
+  const unsigned fixed = (unsigned)h->cfg.fixed_type_mask;
   for (int a = 0; a < T; ++a)
     for (int b = 0; b < T; ++b) {
       const double eps = h->cfg.wca_eps[a * CGPE_MAX_TYPES + b], sig = h->cfg.wca_sig[a * CGPE_MAX_TYPES + b];
@@ -119,12 +123,18 @@ int upload_wca(cgpe_handle *h) {
       const double rc2 = 1.2599210498948731648 * sig * sig;
       tab[(size_t)a * S + b] = make_float4((float)(24.0 * eps), (float)(sig * sig), (float)rc2, (float)eps);
       rc_max = std::fmax(rc_max, std::sqrt(rc2));
+      if (!((fixed >> a) & 1u) && !((fixed >> b) & 1u)) rc_free = std::fmax(rc_free, std::sqrt(rc2));
     }
   CU(cudaMemcpyAsync(h->g.wca_tab, tab.data(), sizeof(float4) * tab.size(), cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   const double rl = rc_max + h->p.skin;
   if (h->cfg.use_wca && rl > 0.5 * h->cfg.box_l) return fail(h, CGPE_ERR_INVALID, "WCA cutoff + skin exceeds box_l/2");
-  h->p.rlist_w2 = (float)(rl * rl);
+  h->p.rlist_wf2 = (float)(rl * rl);
+  // one big fixed sphere must not lengthen every row: when the fixed particles all sit in slots and the
+  // shared-memory engine serves the handle (set_state decides both), the rows take free partners within
+  // the free-pair radius and fixed ones within the full radius (chain_engine.cu::build_rows)
+  const double rl_free = h->two_radii ? rc_free + h->p.skin : rl;
+  h->p.rlist_w2 = (float)(rl_free * rl_free);
   h->p.rc_w_max2 = (float)(rc_max * rc_max * (1.0 + 1e-6));
   return CGPE_OK;
 }
@@ -301,12 +311,22 @@ int cgpe_abi_version(void) { return CGPE_ABI_VERSION; }
 
 const char *cgpe_last_error(const cgpe_handle *h) { return h ? h->err : g_err; }
 
+// Slots behind the chains hold explicit ions that the reactions create and destroy (M.py:173-198) --
+// unless every reaction names no ion type (type_ion < 0): then the reactions are the implicit-ion
+// ones and the slots hold spectator particles (a charged nanoparticle, BASELINE config 4).
+static bool explicit_ions(const cgpe_config *c) {
+  if (c->n_ion_slots <= 0) return false;
+  for (int m = 0; m < c->n_reactions; ++m)
+    if (c->reactions[m].type_ion >= 0) return true;
+  return c->n_reactions == 0;
+}
+
 int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   if (!out) return fail(nullptr, CGPE_ERR_INVALID, "out is NULL");
   *out = nullptr;
   int rc = validate(cfg);
   if (rc) return rc;
-  if (cfg->n_ion_slots > 0) {
+  if (explicit_ions(cfg)) {
     double rc_ion = 0.0;   // largest WCA cutoff of the ion type
     const int tb = cfg->n_reactions > 0 ? cfg->reactions[0].type_ion : 0;
     for (int m = 0; m < cfg->n_reactions; ++m) {
@@ -344,7 +364,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   DevParams &p = h->p;
   std::memset(&p, 0, sizeof(p));
   p.R = cfg->n_replicas; p.N = cfg->n_beads; p.NC = cfg->n_chains * cfg->n_beads;
-  p.P = p.NC + cfg->n_ion_slots; p.T = cfg->n_types; p.n_rx = cfg->n_reactions; p.n_ions = cfg->n_ion_slots;
+  p.P = p.NC + cfg->n_ion_slots; p.T = cfg->n_types; p.n_rx = cfg->n_reactions; p.n_ions = explicit_ions(cfg) ? cfg->n_ion_slots : 0;
   p.bond_kind = cfg->bond_kind; p.use_angle = cfg->use_angle; p.use_dih = cfg->use_dihedral;
   p.dih_mult = cfg->dihedral_mult; p.use_wca = cfg->use_wca; p.use_dh = cfg->use_dh;
   p.replica_offset = cfg->replica_offset;
@@ -364,6 +384,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   const double skin = cfg->skin > 0.0 ? cfg->skin : 0.8;
   p.skin = (float)skin; p.half_skin2 = (float)(0.25 * skin * skin);
   p.force_cap = 0.f;
+  p.fixed_mask = (uint32_t)cfg->fixed_type_mask;
   p.thermostat_seed = 0u;
   if (const char *dp = std::getenv("CGPE_DENSE_POLICY")) p.dense_policy = std::atoi(dp);   // diagnostics only
   for (int m = 0; m < p.n_rx; ++m) {
@@ -374,7 +395,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
     d.q_prot = (float)r.q_prot; d.q_deprot = (float)r.q_deprot; d.q_ion = (float)r.q_ion;
     d.inv_kT = (float)(1.0 / r.kT); d.pK = r.pK;
     d.excl2 = (float)(r.exclusion_range * r.exclusion_range); d.sqrt_kT = (float)std::sqrt(r.kT);
-    if (cfg->n_ion_slots > 0) p.grid_w_min = std::fmax(p.grid_w_min, (float)(r.exclusion_range * 1.001));
+    if (p.n_ions > 0) p.grid_w_min = std::fmax(p.grid_w_min, (float)(r.exclusion_range * 1.001));
   }
   // chargeable particles are fixed at set_state; size the lists for "every third bead" + ions
   p.n_chg = 0;
@@ -519,6 +540,8 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
   if (h->dhc_alloc) { cudaFree(h->dhc_alloc); h->dhc_alloc = nullptr; }
   h->g.dhc = nullptr; p.dhc_cap = 0; p.dhc_stride = 0;
   if (h->launch.items == 0) {
+    if (p.P > p.NC && p.n_ions == 0)
+      return fail(h, CGPE_ERR_UNSUPPORTED, "spectator particles (slots without an ion reaction) are served by the shared-memory engine only (<= 2048 particles per replica)");
     int rc_w = ensure_wide(h, chg_packed);
     if (rc_w) return rc_w;
   } else {
@@ -529,6 +552,18 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
       p.dhc_cap = (((32 + G - 1) / G) * ((n_chg + 31) / 32) + 7) / 8 * 8;   // whole 16-byte groups of eight entries
       CU(cudaMalloc(&h->dhc_alloc, sizeof(uint16_t) * (size_t)p.R * p.dhc_cap * p.dhc_stride));
       h->g.dhc = static_cast<uint16_t *>(h->dhc_alloc);
+    }
+  }
+  {   // list radii: see upload_wca
+    bool fixed_in_chain = false;
+    for (int r = 0; r < p.R && !fixed_in_chain; ++r)
+      for (int i = 0; i < p.NC; ++i)
+        if ((p.fixed_mask >> type[(size_t)r * p.P + i]) & 1u) { fixed_in_chain = true; break; }
+    const bool two = p.fixed_mask != 0u && !fixed_in_chain && h->launch.items != 0;
+    if (two != h->two_radii) {
+      h->two_radii = two;
+      int rc_r = upload_wca(h);
+      if (rc_r) return rc_r;
     }
   }
   // bookkeeping lists in particle-id order
@@ -569,6 +604,13 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     CU(cudaMemcpyAsync(h->g.ion_free, fre.data(), sizeof(int) * fre.size(), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->g.ion_cnt, icnt.data(), sizeof(int) * icnt.size(), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+  }
+  std::vector<float> vel_still;
+  if (p.fixed_mask != 0u && vel) {   // fixed particles (fix=[True]*3) hold no velocity
+    vel_still.assign(vel, vel + RP * 4);
+    for (size_t k = 0; k < RP; ++k)
+      if ((p.fixed_mask >> type[k]) & 1u) vel_still[4 * k] = vel_still[4 * k + 1] = vel_still[4 * k + 2] = 0.f;
+    vel = vel_still.data();
   }
   CU(cudaMemcpyAsync(h->g.pos, xyzq, sizeof(float4) * RP, cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->g.vel, vel ? vel : zero.data(), sizeof(float4) * RP, cudaMemcpyHostToDevice, h->stream));

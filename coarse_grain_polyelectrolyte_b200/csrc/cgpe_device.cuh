@@ -54,11 +54,14 @@ struct DevParams {
   float dt, half_dt;
   double dt_d;                  // time step in double for the clock (system.time)
   float skin, half_skin2;       // Verlet skin, (skin/2)^2
-  float rlist_w2;               // (max WCA cutoff + skin)^2
+  float rlist_w2;               // (max WCA cutoff + skin)^2; with fixed particles in slots only (rlist_wf2 > rlist_w2):
+                                // over the pairs of free types
+  float rlist_wf2;              // (max WCA cutoff + skin)^2 over all type pairs: list radius towards a fixed particle
   float rc_w_max2;              // (max WCA cutoff)^2
   int dhc_cap, dhc_stride;      // compact Debye-Hueckel partner lists: entries per sub-thread, sub-threads per replica (padded)
   float grid_w_min;             // smallest cell edge of the all-particle grid (explicit ions: the largest exclusion range)
   float force_cap;              // 0 = off
+  uint32_t fixed_mask;          // bit t: particles of type t never move (cgpe_config::fixed_type_mask)
   SmemOff off;
   DevReaction rx[kMaxRx];
 };

@@ -250,8 +250,8 @@ __device__ void build_rows(Ctx &c, Thr<ITEMS> &t) {
     const int i = c.tid + k * c.nt;
     if (i < p.P) {
       t.ref[k][0] = t.x[k][0]; t.ref[k][1] = t.x[k][1]; t.ref[k][2] = t.x[k][2];
-      if (p.use_wca && c.s.type[i] >= p.T) {
-        c.s.wn[i] = 0;   // hidden slot: not a particle (it gets rows when a trial move revives it)
+      if (p.use_wca && (c.s.type[i] >= p.T || ((p.fixed_mask >> c.s.type[i]) & 1u))) {
+        c.s.wn[i] = 0;   // hidden slot: not a particle (it gets rows when a trial move revives it); fixed particle: its force is discarded
       } else if (p.use_wca) {
         const float4 pi = c.s.pos[i];
         // same-chain partners handled by the bonded owner (also excludes j == i)
@@ -266,6 +266,16 @@ __device__ void build_rows(Ctx &c, Thr<ITEMS> &t) {
             ++n;
           }
         }
+        if (p.rlist_wf2 > p.rlist_w2)   // fixed particles sit in slots and may be large: their own list radius
+          for (int j = p.NC; j < p.P; ++j) {
+            if (!((p.fixed_mask >> c.s.type[j]) & 1u) || j == i) continue;
+            V3 d;
+            const float r2 = dist2<WRAP>(c, pi, c.s.pos[j], &d);
+            if (r2 >= p.rlist_w2 && r2 < p.rlist_wf2) {
+              if (n < p.cap_w) c.s.wl[(size_t)n * p.P + i] = (uint16_t)j;
+              ++n;
+            }
+          }
         if (n > p.cap_w) { c.err |= kErrWcaCap; n = p.cap_w; }
         c.s.wn[i] = (unsigned char)n;
       }
@@ -607,6 +617,7 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
           fx *= sc_; fy *= sc_; fz *= sc_;
         }
       }
+      if (p.fixed_mask != 0u && ((p.fixed_mask >> c.s.type[i]) & 1u)) fx = fy = fz = 0.0f;   // fix=[True]*3
       t.f[k][0] = fx; t.f[k][1] = fy; t.f[k][2] = fz;
     }
   }
@@ -1063,7 +1074,7 @@ __device__ void init_ctx(Ctx &c) {
   c.rc2 = rc * rc;
   c.neg_kappa_log2e = -c.kappa * kLog2e;
   c.rlist_d2 = (rc + p.skin) * (rc + p.skin);
-  c.rlist_max = fmaxf(p.use_dh ? rc + p.skin : 0.f, p.use_wca ? sqrtf(p.rlist_w2) : 0.f);
+  c.rlist_max = fmaxf(p.use_dh ? rc + p.skin : 0.f, p.use_wca ? sqrtf(p.rlist_wf2) : 0.f);
   c.wrap = true;
   c.dense = false;
   c.compact = false;

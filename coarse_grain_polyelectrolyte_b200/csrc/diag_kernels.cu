@@ -136,6 +136,7 @@ k_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
         if (fr != 0.f) { fx += (double)(fr * d.x); fy += (double)(fr * d.y); fz += (double)(fr * d.z); }
       }
     }
+    if ((p.fixed_mask >> ti) & 1u) fx = fy = fz = 0;   // fix=[True]*3
     out[(size_t)r * p.P + i] = make_float4((float)fx, (float)fy, (float)fz, 0.f);
   }
   if (err) atomicOr(&g.err[r], err);

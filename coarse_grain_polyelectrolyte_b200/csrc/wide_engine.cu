@@ -448,6 +448,7 @@ wk_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState 
     const float n2 = dot(f, f);
     if (n2 > p.force_cap * p.force_cap) f = (p.force_cap * rsqrtf(n2)) * f;
   }
+  if (p.fixed_mask != 0u && ((p.fixed_mask >> ti) & 1u)) f = V3{0.f, 0.f, 0.f};   // fix=[True]*3
   if (out) { out[base + i] = make_float4(f.x, f.y, f.z, 0.f); }
   else {
     g.frc[base + i] = make_float4(f.x, f.y, f.z, 0.f);

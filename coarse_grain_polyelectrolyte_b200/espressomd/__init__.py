@@ -205,8 +205,9 @@ class _ParticleList:
             return s._n_part
         return int((s._state()[2][0] < s._hidden_type).sum())     # hidden ion slots are not particles
 
-    def add(self, id=None, pos=None, type=0, q=0.0, v=None, **unsupported):
-        """Scalar form (M.py:130-155) and vectorised form (M.py:175-198)."""
+    def add(self, id=None, pos=None, type=0, q=0.0, v=None, fix=None, **unsupported):
+        """Scalar form (M.py:130-155) and vectorised form (M.py:175-198).  fix=[True]*3 pins the
+        particle(s) in space (all three axes or none; the engine fixes whole particle types)."""
         if unsupported:
             raise NotImplementedError(f"particle properties not supported: {sorted(unsupported)}")
         if pos is None:
@@ -229,7 +230,14 @@ class _ParticleList:
             raise NotImplementedError("particle ids must be consecutive, starting at len(system.part)")
         if np.any(types < 0) or np.any(types >= _abi.MAX_TYPES):
             raise ValueError("particle type out of range")
+        fixed = False
+        if fix is not None:
+            fx = np.asarray(fix, dtype=bool).reshape(-1)
+            if fx.size != 3 or (fx.any() and not fx.all()):
+                raise NotImplementedError("fix: all three axes or none")
+            fixed = bool(fx.all())
         s._append_particles(pos, vs, types, qs)
+        s._fixed = np.concatenate([s._fixed, np.full(n, fixed)])
         if single:
             return _ParticleHandle(s, ids[0])
         return _ParticleSlice(s, ids)
@@ -404,6 +412,7 @@ class System:
         self._reactions = []                    # reaction_methods._Registered
         self._engine = None
         self._engine_particles = 0
+        self._fixed = np.zeros(0, dtype=bool)   # per particle: fix=[True]*3
         self._hidden_type = None               # type index of hidden (non-interacting) ion slots once they exist
         self._state_cache = None
         _current_system = self
@@ -548,7 +557,16 @@ class System:
         # free particles (explicit ions, M.py:173-198) live in ion slots behind the chain; one spare
         # hidden slot per titratable site lets every site release its H+ (ESPResSo creates particles
         # on demand; here the pool is sized up front)
-        if self._n_part > n_chain:
+        # fixed particles (fix=[True]*3): the engine pins whole types
+        fixed = np.concatenate([self._fixed, np.zeros(self._n_part - len(self._fixed), dtype=bool)])
+        fixed_types = sorted({int(t) for t in self._type[fixed]})
+        if any(not f and int(t) in fixed_types for f, t in zip(fixed, self._type)):
+            raise NotImplementedError("a particle type is either fixed (fix=[True]*3 on all its particles) or free")
+        fixed_mask = sum(1 << t for t in fixed_types)
+        # free particles that are all fixed are spectators (a charged nanoparticle): the reactions stay
+        # the implicit-ion ones and need no H+ pool
+        spectators = self._n_part > n_chain and bool(np.all(fixed[n_chain:]))
+        if self._n_part > n_chain and not spectators:
             reactive = {t for r in self._reactions for t in (r.type_prot, r.type_deprot)}
             n_sites = int(sum(int(t) in reactive for t in self._type[:n_chain]))
             n_hidden = 0 if self._hidden_type is None else int((self._type == self._hidden_type).sum())
@@ -567,7 +585,7 @@ class System:
             n_ion_slots=n_ion_slots, n_types=T, device=self._device, skin=self._engine_skin,
             box_l=float(self.box_l[0]), time_step=float(self.time_step),
             bond_kind=_abi.BOND_NONE, use_angle=0, use_dihedral=0, use_wca=int(self._use_wca), use_dh=0,
-            wca_eps=self._wca_eps, wca_sig=self._wca_sig,
+            wca_eps=self._wca_eps, wca_sig=self._wca_sig, fixed_type_mask=fixed_mask,
         )
         if isinstance(bond_t, interactions.HarmonicBond):
             kw.update(bond_kind=_abi.BOND_HARMONIC, bond_k=bond_t.k, bond_r0=bond_t.r_0)
@@ -581,6 +599,9 @@ class System:
             kw.update(use_dh=1, dh_prefactor=self._dh.prefactor,
                       kappa=float(np.atleast_1d(self._dh.kappa)[0]), r_cut=float(np.max(self._dh.r_cut)))
         kw["reactions"] = [r.as_dict() for r in self._reactions]
+        if spectators:
+            for rx in kw["reactions"]:
+                rx["type_ion"] = -1
         return _abi.make_config(**kw)
 
     def _ensure_engine(self):

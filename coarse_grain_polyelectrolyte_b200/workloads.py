@@ -87,7 +87,10 @@ class Workload:
     "Number of polymers" chains (+ explicit ions on request)."""
 
     def __init__(self, params, pH, c_salt=None, replica_offset=0, seed=12, device=-1, deprotonated=True,
-                 explicit_ions=False, ion_seed=10, min_distance=None):
+                 explicit_ions=False, ion_seed=10, min_distance=None, nanoparticle=None):
+        """nanoparticle: dict(charge=, sigma=[Angstrom, as in the particle table; 34.8 = 10 sim_length],
+        epsilon=[kJ/mol], offset=(dx,dy,dz) [sim_length]) puts one fixed sphere of type "NP" at box centre +
+        offset (BASELINE config 4; README.md:14-15 of the reference)."""
         self.params = params
         sp = params["System properties"]
         sc = params["Simulation configuration"]
@@ -98,6 +101,14 @@ class Workload:
         tix = ru.type_index
         c_salt_r = np.full(R, sp["Concentration salt particles"]) if c_salt is None else np.broadcast_to(
             np.asarray(c_salt, np.float64), (R,)).copy()
+        if nanoparticle is not None:   # an extra row of the particle table, in the table's own units (Angstrom)
+            params = copy.deepcopy(params)
+            pp = params["Particles properties"]
+            pp["NP"] = {"index": max(v["index"] for v in pp.values()) + 1, "charge": nanoparticle["charge"],
+                        "sigma": nanoparticle.get("sigma", 34.8), "epsilon": nanoparticle.get("epsilon", 0.3)}
+            self.params = params
+            self.ru = ru = reduced_units(params)
+            tix = ru.type_index
         self.pH = pH
         self.kappa = np.array([units.kappa_per_nm(c) for c in c_salt_r]) * ru.sim_length_nm
         self.r_cut = 1.0 / self.kappa                                   # M.py:106
@@ -117,7 +128,13 @@ class Workload:
         n_acid = n_poly * (sp["NH monomers"] + sp["NH2 monomers"])
         ion_names = (["B"] * n_acid + ["Cl"] * n_acid + ["Na"] * ru.n_salt + ["Cl"] * ru.n_salt) if explicit_ions else []
         n_spare = n_acid if explicit_ions else 0
-        self.n_ion_slots = len(ion_names) + n_spare
+        if nanoparticle is not None:
+            if explicit_ions:
+                raise NotImplementedError("nanoparticle workload: implicit ions (an inserted H+ would need the "
+                                          "sphere's WCA energy, which the explicit-ion move does not evaluate)")
+            for rx in reactions:
+                rx["type_ion"] = -1          # implicit-ion reactions; the slot holds a spectator
+        self.n_ion_slots = len(ion_names) + n_spare + (1 if nanoparticle is not None else 0)
         self.cfg = _abi.make_config(
             n_replicas=R, replica_offset=replica_offset, n_chains=n_poly, n_beads=n_mon, n_ion_slots=self.n_ion_slots,
             n_types=len(tix), bond_kind=_abi.BOND_FENE if sc["USE_FENE"] else _abi.BOND_HARMONIC,
@@ -128,7 +145,8 @@ class Workload:
             dihedral_k=ru.k_dihedral, dihedral_phase=math.pi,
             dh_prefactor=ru.coulomb_prefactor, box_l=ru.box_length, time_step=sc["time step"],
             pH=float(pH[0]), kappa=float(self.kappa[0]), r_cut=float(self.r_cut[0]), kT=1.0, gamma=1.0,
-            wca_eps=eps, wca_sig=sig, reactions=reactions, device=device)
+            wca_eps=eps, wca_sig=sig, reactions=reactions, device=device,
+            fixed_type_mask=(1 << tix["NP"]) if nanoparticle is not None else 0)
         # topology + start state: every site starts deprotonated (M.py:130-147)
         role = np.tile(topology.chain_site_pattern(n_mon), n_poly)
         if deprotonated:
@@ -154,6 +172,17 @@ class Workload:
             self.xyzq = np.concatenate([self.xyzq, np.concatenate([ion_pos, ion_q[:, None]], axis=1).astype(np.float32)])
             self.type = np.concatenate([self.type, ion_type])
             self.q = np.concatenate([self.q, ion_q])
+        if nanoparticle is not None:
+            if "offset" in nanoparticle:
+                np_pos = 0.5 * ru.box_length + np.asarray(nanoparticle["offset"], np.float64)
+            else:   # beside the chain: the nearest point along +x that clears every bead's WCA core
+                clear = nanoparticle.get("clearance", 1.3) * 0.25 * (ru.sigma["NP"] + max(ru.sigma.values()))
+                np_pos = np.full(3, 0.5 * ru.box_length)
+                while np.min(np.linalg.norm(self.xyzq[:, :3] - np_pos, axis=1)) < clear:
+                    np_pos[0] += 0.25
+            self.xyzq = np.concatenate([self.xyzq, np.array([[*np_pos, ru.charge["NP"]]], np.float32)])
+            self.type = np.concatenate([self.type, np.array([tix["NP"]], np.uint8)])
+            self.q = np.concatenate([self.q, np.array([ru.charge["NP"]], np.float32)])
         self.n_sites = (int(np.sum(role == 1)), int(np.sum(role == 2)))   # all chains
         ns, nsi = num_samples(params)
         p = params["Montecarlo properties"]["PROB_REACTION"]
@@ -192,6 +221,13 @@ def config_c2(**kw):
 
 
 C3_SALT_MOLAR = (1e-3, 2e-3, 5e-3, 1e-2, 2e-2, 5e-2, 1e-1, 2e-1)
+
+
+def config_c4(charge=-20.0, n_ph=64, **kw):
+    """C4: the C2 chain next to one fixed charged sphere (sigma = 10 sim_length) that interacts with
+    every bead through WCA and Debye-Hueckel; the chain starts beside the sphere."""
+    return Workload(example_parameters(100, c_salt=2e-2), pH=np.linspace(4.0, 12.0, n_ph),
+                    nanoparticle=dict(charge=charge, sigma=34.8, epsilon=0.3), **kw)
 
 
 def config_c3_shard(rank=0, world=8, n_ph=128, n_mon=1000, **kw):

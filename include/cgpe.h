@@ -37,7 +37,7 @@ extern "C" {
 #define CGPE_API
 #endif
 
-#define CGPE_ABI_VERSION 4
+#define CGPE_ABI_VERSION 5
 #define CGPE_MAX_TYPES 16     /* interacting particle types (the reference uses 8, M.py:58-76) */
 #define CGPE_MAX_REACTIONS 4  /* reaction objects (the reference uses 2, M.py:211-233)         */
 #define CGPE_MAX_MC_BLOCKS 4  /* MC blocks per sample (the reference uses 2, E.py:94-95)       */
@@ -62,7 +62,7 @@ enum { CGPE_BOND_NONE = 0, CGPE_BOND_HARMONIC = 1, CGPE_BOND_FENE = 2 };
 typedef struct cgpe_reaction {
   int32_t type_prot;      /* reactant_types[0], "NH"  (M.py:237)                               */
   int32_t type_deprot;    /* product_types[0],  "N"   (M.py:238)                               */
-  int32_t type_ion;       /* product_types[1],  "B"   (M.py:238); unused with implicit ions    */
+  int32_t type_ion;       /* product_types[1],  "B"   (M.py:238); < 0 = implicit ions          */
   int32_t seed;           /* seed=77 (M.py:214)                                                */
   double q_prot;          /* default_charges (M.py:239-243)                                    */
   double q_deprot;
@@ -80,7 +80,10 @@ typedef struct cgpe_config {
                              index so results do not depend on how replicas shard over GPUs   */
   int32_t n_chains;       /* "Number of polymers" (P.py:384)                                   */
   int32_t n_beads;        /* "Number of monomers" per chain (P.py:390)                         */
-  int32_t n_ion_slots;    /* explicit-ion capacity per replica; 0 = implicit ions              */
+  int32_t n_ion_slots;    /* particles per replica behind the chains.  With reactions that name an ion
+                             type (type_ion >= 0): the explicit-ion pool (free H+, salt, hidden spares).
+                             With type_ion < 0 in every reaction: implicit-ion reactions, the slots hold
+                             spectator particles (e.g. one fixed charged nanoparticle); 0 = none      */
   int32_t n_types;        /* T interacting types; type index T is the non-interacting type
                              (M.py:256-261)                                                    */
   int32_t bond_kind;      /* HarmonicBond / FeneBond (M.py:34-40)                              */
@@ -94,7 +97,9 @@ typedef struct cgpe_config {
   int32_t cap_dh;         /* Debye-Hueckel row capacity of the large-replica engine (P > 2048);
                              the shared-memory engine keeps a fixed-size bit matrix instead    */
   int32_t device;         /* CUDA ordinal, -1 = current device                                 */
-  int32_t reserved0;
+  int32_t fixed_type_mask; /* bit t set: particles of type t never move (ESPResSo's `fix=[True]*3`): zero
+                             force and velocity, no thermostat noise.  They still act on every other
+                             particle: a charged nanoparticle among the chains (BASELINE config 4)     */
   double bond_k, bond_r0, fene_drmax;   /* M.py:35-39                                          */
   double angle_k, angle_phi0;           /* M.py:43-45                                          */
   double dihedral_k, dihedral_phase;    /* M.py:49-53                                          */

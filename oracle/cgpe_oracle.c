@@ -428,10 +428,20 @@ static int check_config(const cgpe_config *c, char *err) {
   return CGPE_OK;
 }
 
+/* Slots behind the chains hold explicit ions that the reactions create and destroy (M.py:173-198) --
+   unless every reaction names no ion type (type_ion < 0): then the reactions are the implicit-ion
+   ones and the slots hold spectator particles (a charged nanoparticle, BASELINE config 4). */
+static int explicit_ions(const cgpe_config *c) {
+  if (c->n_ion_slots <= 0) return 0;
+  for (int m = 0; m < c->n_reactions; ++m)
+    if (c->reactions[m].type_ion >= 0) return 1;
+  return c->n_reactions == 0;
+}
+
 int orc_create(const cgpe_config *cfg, orc_handle **out) {
   int rc = check_config(cfg, g_err);
   if (rc) return rc;
-  if (cfg->n_ion_slots > 0) {
+  if (explicit_ions(cfg)) {
     for (int m = 0; m < cfg->n_reactions; ++m)
       if (cfg->reactions[m].type_ion != cfg->reactions[0].type_ion || cfg->reactions[m].q_ion != cfg->reactions[0].q_ion ||
           cfg->reactions[m].type_ion < 0 || cfg->reactions[m].type_ion >= cfg->n_types) {
@@ -507,7 +517,7 @@ int orc_synchronize(orc_handle *h) { (void)h; return CGPE_OK; }
 
 static void rebuild_lists(orc_handle *h) {
   /* bookkeeping lists in particle-id order (set_state contract) */
-  if (h->cfg.n_ion_slots > 0 && h->cfg.n_reactions > 0)
+  if (explicit_ions(&h->cfg) && h->cfg.n_reactions > 0)
     for (int r = 0; r < h->R; ++r) {
       const int ni = h->cfg.n_ion_slots, tb = h->cfg.reactions[0].type_ion;
       h->n_active[r] = h->n_free[r] = 0;
@@ -542,6 +552,7 @@ int orc_set_state(orc_handle *h, const float *xyzq, const float *vel, const uint
     if (type[k] > h->T) return fail(h, CGPE_ERR_INVALID, "type index out of range");
     h->type[k] = type[k];
     if (type[k] >= h->T) { h->v[k * 3] = h->v[k * 3 + 1] = h->v[k * 3 + 2] = 0.0; h->q[k] = 0.0; }
+    else if (((unsigned)h->cfg.fixed_type_mask >> type[k]) & 1u) h->v[k * 3] = h->v[k * 3 + 1] = h->v[k * 3 + 2] = 0.0;
   }
   rebuild_lists(h);
   {
@@ -645,6 +656,15 @@ int orc_get_time(orc_handle *h, double *t) { memcpy(t, h->time, sizeof(double) *
 /* ------------------------------------------------------------------------------------------- */
 /* R2: velocity Verlet + Langevin thermostat (E.py:61-63; integrator.run E.py:90)               */
 /* ------------------------------------------------------------------------------------------- */
+/* fix=[True]*3 (cgpe_config::fixed_type_mask): particles of a fixed type feel no force, hold no
+   velocity, get no thermostat noise; they still act on everything else. */
+static void release_fixed(const orc_handle *h, int r, double *f) {
+  const unsigned mask = (unsigned)h->cfg.fixed_type_mask;
+  if (!mask) return;
+  for (int i = 0; i < h->P; ++i)
+    if ((mask >> h->type[(size_t)r * h->P + i]) & 1u) f[i * 3] = f[i * 3 + 1] = f[i * 3 + 2] = 0.0;
+}
+
 static void total_force(orc_handle *h, int r, int with_thermostat) {
   /* f = F_interactions + ( -gamma v + sqrt(24 gamma kT / dt) (U - 1/2) ), then the force cap */
   double e[3];
@@ -672,6 +692,7 @@ static void total_force(orc_handle *h, int r, int with_thermostat) {
       }
     }
   }
+  release_fixed(h, r, f);
 }
 
 static void md_run_replica(orc_handle *h, int r, int n_steps) {
@@ -824,13 +845,13 @@ static void mc_run_replica_follow(orc_handle *h, int r, int m, int n_trials, cgp
     int32_t *src = forward ? l->prot : l->deprot, *dst = forward ? l->deprot : l->prot;
     int32_t *n_src = forward ? &l->n_prot : &l->n_deprot, *n_dst = forward ? &l->n_deprot : &l->n_prot;
     cgpe_trial_record rec = {-1, -1, (int8_t)(forward ? 1 : -1), 0, 0, 0, 0.f, 0.f, (float)u24(o[2])};
-    const int explicit_ions = h->cfg.n_ion_slots > 0;
-    const int ni = explicit_ions ? h->cfg.n_ion_slots : 1;
+    const int explicit_ions_ = explicit_ions(&h->cfg);
+    const int ni = explicit_ions_ ? h->cfg.n_ion_slots : 1;
     int32_t *ion_active = h->ion_active + (size_t)r * ni, *ion_free = h->ion_free + (size_t)r * ni;
     /* all reactant particles must exist (backward also needs a free H+ to take; forward a spare slot) */
     int possible = *n_src > 0;
-    if (explicit_ions && !forward && h->n_active[r] == 0) possible = 0;
-    if (explicit_ions && forward && h->n_free[r] == 0) possible = 0;
+    if (explicit_ions_ && !forward && h->n_active[r] == 0) possible = 0;
+    if (explicit_ions_ && forward && h->n_free[r] == 0) possible = 0;
     if (possible) {
       const uint32_t k = mulhi32(o[1], (uint32_t)*n_src);
       const int i = src[k];
@@ -839,7 +860,7 @@ static void mc_run_replica_follow(orc_handle *h, int r, int m, int n_trials, cgp
       double de = site_delta_e(h, r, i, t_old, t_new, q_old, q_new);
       int b = -1, kb = 0, excluded = 0;
       double xb[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
-      if (explicit_ions) {
+      if (explicit_ions_) {
         double dmin2;
         if (forward) { /* insert one B at a uniform position with a Maxwell-Boltzmann velocity */
           uint32_t c1[4] = {ctr[0], ctr[1], 1u, ctr[3]}, c2[4] = {ctr[0], ctr[1], 2u, ctr[3]}, o1[4], o2[4];
@@ -875,7 +896,7 @@ static void mc_run_replica_follow(orc_handle *h, int r, int m, int n_trials, cgp
         ty[i] = (uint8_t)t_new; q[i] = q_new;
         src[k] = src[*n_src - 1]; *n_src -= 1; /* swap-remove */
         dst[*n_dst] = i; *n_dst += 1;
-        if (explicit_ions) {
+        if (explicit_ions_) {
           double *xs = h->x + ((size_t)r * h->P + b) * 3, *vs = h->v + ((size_t)r * h->P + b) * 3;
           if (forward) {
             ty[b] = (uint8_t)rx->type_ion; q[b] = rx->q_ion;
@@ -949,7 +970,7 @@ static void observables_replica(const orc_handle *h, int r, double *rg, double *
   counts[0] = counts[1] = counts[2] = 0;
   for (int m = 0; m < h->cfg.n_reactions && m < 2; ++m)
     counts[m] = h->lists[(size_t)r * h->cfg.n_reactions + m].n_deprot;
-  if (h->cfg.n_ion_slots > 0) counts[2] = h->n_active[r]; /* number_of_particles(type=B), E.py:99 */
+  if (explicit_ions(&h->cfg)) counts[2] = h->n_active[r]; /* number_of_particles(type=B), E.py:99 */
   else /* implicit ions: every deprotonated site has released one (virtual) H+ : N_B = N_N + N_N2 */
     for (int m = 0; m < h->cfg.n_reactions; ++m)
       counts[2] += h->lists[(size_t)r * h->cfg.n_reactions + m].n_deprot;
@@ -984,7 +1005,7 @@ int orc_energy(orc_handle *h, double *out) {
 int orc_forces_f64(orc_handle *h, double *out /*[R][P][3]*/) {
   if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
   double e[3];
-  for (int r = 0; r < h->R; ++r) interactions(h, r, out + (size_t)r * h->P * 3, e);
+  for (int r = 0; r < h->R; ++r) { interactions(h, r, out + (size_t)r * h->P * 3, e); release_fixed(h, r, out + (size_t)r * h->P * 3); }
   return CGPE_OK;
 }
 
@@ -993,6 +1014,7 @@ int orc_forces(orc_handle *h, float *out /*[R][P][4]*/) {
   double *tmp = malloc(sizeof(double) * 3 * h->P), e[3];
   for (int r = 0; r < h->R; ++r) {
     interactions(h, r, tmp, e);
+    release_fixed(h, r, tmp);
     for (int i = 0; i < h->P; ++i) {
       float *o = out + ((size_t)r * h->P + i) * 4;
       o[0] = (float)tmp[i * 3]; o[1] = (float)tmp[i * 3 + 1]; o[2] = (float)tmp[i * 3 + 2]; o[3] = 0.f;

@@ -8,12 +8,13 @@ from coarse_grain_polyelectrolyte_b200 import workloads
 
 
 def make_workload(n_mon, pH, c_salt=2e-2, flags=None, replica_offset=0, seed=12, explicit_ions=False, n_poly=1,
-                  **cfg_overrides):
+                  nanoparticle=None, **cfg_overrides):
     params = workloads.example_parameters(n_mon, c_salt=c_salt, n_poly=n_poly)
     if flags:
         params = copy.deepcopy(params)
         params["Simulation configuration"].update(flags)
-    w = workloads.Workload(params, pH=pH, replica_offset=replica_offset, seed=seed, explicit_ions=explicit_ions)
+    w = workloads.Workload(params, pH=pH, replica_offset=replica_offset, seed=seed, explicit_ions=explicit_ions,
+                           nanoparticle=nanoparticle)
     for k, v in cfg_overrides.items():
         setattr(w.cfg, k, v)
     return w

@@ -162,3 +162,24 @@ def test_model_dictionary_to_topology():
     assert (role == 1).sum() == 16 and (role == 2).sum() == 1
     role = topology.chain_site_pattern(1000)
     assert (role == 1).sum() == 332 and (role == 2).sum() == 2
+
+
+def test_fixed_nanoparticle_becomes_a_spectator_slot():
+    """part.add(..., fix=[True]*3) behind the chain (BASELINE config 4): a spectator slot of a fixed
+    type; the reactions stay the implicit-ion ones (no H+ pool is created)."""
+    s = build_chain(9, dihedral=False)
+    s.non_bonded_inter[1, 5].wca.set_params(epsilon=0.2, sigma=3.0)
+    s.non_bonded_inter[3, 5].wca.set_params(epsilon=0.2, sigma=3.1)
+    s.actors.add(electrostatics.DH(prefactor=2.0, kappa=0.16, r_cut=6.0))
+    rx = reaction_methods.ConstantpHEnsemble(kT=1.0, exclusion_range=1.4, seed=77, constant_pH=8.0)
+    rx.add_reaction(gamma=10 ** -8.18, reactant_types=[0], product_types=[1, 2], default_charges={0: 1.0, 1: 0.0, 2: 1.0})
+    with pytest.raises(NotImplementedError):
+        s.part.add(pos=[1.0, 2.0, 3.0], type=5, q=-20.0, fix=[True, False, True])
+    s.part.add(pos=[15.0, 15.0, 15.0], type=5, q=-20.0, fix=[True, True, True])
+    cfg = s._build_config()
+    assert cfg.n_ion_slots == 1 and cfg.fixed_type_mask == 1 << 5 and cfg.n_types >= 6
+    assert cfg.reactions[0].type_ion == -1
+    # a free particle of the same type contradicts the type-wide pin
+    s.part.add(pos=[5.0, 5.0, 5.0], type=5, q=-20.0)
+    with pytest.raises(NotImplementedError):
+        s._build_config()

@@ -613,3 +613,64 @@ def test_compact_partner_lists_follow_charges_and_rebuilds(Engine, oracle_mod):
             fo = o.forces_f64()
             assert np.abs(g.md_forces() - fo).max() < REL_TOL * np.abs(fo).max()
         assert g.counters()["list_rebuilds"].min() >= 4
+
+
+@pytest.mark.parametrize("charge,n_mon", [(-20.0, 100), (20.0, 100), (-20.0, 1000)])
+def test_charged_nanoparticle_config_c4(Engine, oracle_mod, charge, n_mon):
+    """BASELINE config 4: the chain next to one fixed charged sphere (type "NP", sigma = 10 sim_length,
+    fixed_type_mask) in a spectator slot, implicit-ion reactions.  Energies, forces (all-pairs and
+    list path), trial moves, MD steps and the fused loop against the oracle; the sphere never moves."""
+    w = make_workload(n_mon, pH=[6.0, 8.18, 10.0], nanoparticle=dict(charge=charge, clearance=0.9))
+    state = random_state(w, seed=n_mon + int(charge), jitter=0.03, protonated_fraction=0.6)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    i_np = n_mon
+    x_np = g.get_state()[0][:, i_np, :3].copy()
+    d = np.linalg.norm(state[0][0, :n_mon, :3] - state[0][0, i_np, :3], axis=1)
+    assert (d < w.r_cut[0]).sum() >= 3
+    eg, eo = g.energy(), o.energy()
+    scale = np.maximum(np.abs(eo), 1e-3 * np.abs(eo).max(axis=1, keepdims=True))
+    assert np.max(np.abs(eg - eo) / scale) < REL_TOL, (eg, eo)
+    fo = o.forces_f64()
+    fmax = np.abs(fo).max()
+    for name, fg in (("all-pairs", g.forces()), ("md-lists", g.md_forces())):
+        assert np.abs(fg[..., :3] - fo).max() / fmax < REL_TOL, name
+        assert np.all(fg[:, i_np, :3] == 0.0), name
+    # trial moves: same stream, same decisions, Delta-E with the sphere's potential in it
+    for rx in (0, 1, 0):
+        tg = g.mc_run(rx, 3000, trace=True)
+        to, ties = o.mc_run_follow(rx, tg, tie_tol=1e-4)
+        assert ties <= 4
+        for k in ("particle", "direction", "accepted", "u"):
+            np.testing.assert_array_equal(tg[k], to[k])
+        tried = to["particle"] >= 0
+        err = np.abs(tg["delta_e"][tried] - to["delta_e"][tried]) / np.maximum(np.abs(to["delta_e"][tried]), 1.0)
+        assert err.max() < REL_TOL
+        assert tg["accepted"].sum() > 0
+    np.testing.assert_array_equal(g.get_state()[2], o.get_state()[2])
+    # MD steps (the state now carries the flipped charges)
+    ulp = float(np.spacing(np.float32(np.abs(state[0][..., :3]).max())))
+    for n_steps, tol in ((1, 0.75 * ulp), (9, 8 * ulp)):
+        g.md_run(n_steps); o.md_run(n_steps)
+        xg, vg, _ = g.get_state()
+        xo, vo, _ = o.state_f64()
+        assert np.abs(xg[..., :3] - xo).max() < tol and np.abs(vg[..., :3] - vo).max() < tol * 1e3
+    # the fused loop, with steepest descent in between
+    g.steepest_descent(3, 0.0, 0.01, 0.01); o.steepest_descent(3, 0.0, 0.01, 0.01)
+    sp = g.sample_params(20, md_steps_per_burst=5, use_md=True, mc_blocks=((0, 31), (1, 11)),
+                         q_snapshot_every=0, q_snapshot_rows=0, schedule_seed=10, p_burst1=0.7, p_burst2=0.3)
+    og, _ = g.sample_loop(sp)
+    oo, _ = o.sample_loop(sp)
+    np.testing.assert_array_equal(og[..., :3], oo[..., :3])
+    np.testing.assert_allclose(og[..., 3:5], oo[..., 3:5], rtol=2e-4)
+    np.testing.assert_array_equal(og[..., 2], og[..., 0] + og[..., 1])      # implicit ions: N_B = N_N + N_N2
+    xg, vg, _ = g.get_state()
+    np.testing.assert_array_equal(xg[:, i_np, :3], x_np)
+    assert np.all(vg[:, i_np, :3] == 0.0)
+
+
+def test_spectator_particles_beyond_the_shared_memory_engine_are_refused(Engine):
+    w = make_workload(2500, pH=[8.0], nanoparticle=dict(charge=-20.0))
+    e = Engine(w.cfg)
+    with pytest.raises(Exception) as ei:
+        e.set_state(w.xyzq, None, w.type)
+    assert "spectator" in str(ei.value)

@@ -221,3 +221,66 @@ def test_dihedral_gradient_is_bounded_near_straight_bond_angles(oracle_mod):
     assert np.abs(tame).max() < 1.2e3                    # regularised
     np.testing.assert_allclose(tame.sum(axis=0), 0.0, atol=1e-9)
     np.testing.assert_allclose(forces(0.3, -1.0), forces(0.3, 0.0), rtol=1e-13)   # outside the cone: identical
+
+
+@pytest.mark.parametrize("charge", [-20.0, 20.0])
+def test_fixed_charged_nanoparticle(oracle_mod, charge):
+    """BASELINE config 4: one fixed charged sphere (type "NP", fixed_type_mask) in a spectator slot next
+    to the chain, implicit-ion reactions.  The sphere acts on the beads (forces = -grad E with the
+    sphere held), feels nothing itself, never moves, and shifts the protonation equilibrium."""
+    w = make_workload(40, pH=[8.0], nanoparticle=dict(charge=charge, clearance=0.9))
+    assert w.cfg.n_ion_slots == 1 and w.cfg.fixed_type_mask == 1 << w.ru.type_index["NP"]
+    assert all(w.cfg.reactions[m].type_ion < 0 for m in range(w.cfg.n_reactions))
+    state = random_state(w, seed=4, jitter=0.03, protonated_fraction=0.7)
+    o = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    i_np = 40
+    x0 = o.state_f64()[0][0].copy()
+    d = np.linalg.norm(x0[:40] - x0[i_np], axis=1)
+    assert (d < w.r_cut[0]).sum() >= 3                       # the sphere is felt
+    F = o.forces_f64()[0]
+    assert np.all(F[i_np] == 0.0) and np.all(o.state_f64()[1][0, i_np] == 0.0)
+    near = np.argsort(d)[:6]
+    h, worst = 1e-5, 0.0
+    for i in near:
+        for k in range(3):
+            xp, xm = x0.copy(), x0.copy()
+            xp[i, k] += h
+            xm[i, k] -= h
+            o.set_positions_f64(xp[None]); ep = o.energy()[0, 0]
+            o.set_positions_f64(xm[None]); em = o.energy()[0, 0]
+            worst = max(worst, abs(-(ep - em) / (2 * h) - F[i, k]) / max(1.0, abs(F[i, k])))
+    assert worst < 1e-6
+    o.set_positions_f64(x0[None])
+    # the same chain without the sphere: energies differ (it interacts), bead forces differ
+    w0 = make_workload(40, pH=[8.0])
+    s0 = tuple(a[:, :40] for a in state)
+    o0 = load(oracle_mod.OracleEngine(w0.cfg), w0, s0)
+    assert abs(o.energy()[0, 0] - o0.energy()[0, 0]) > 1e-3
+    assert np.abs(F[:40] - o0.forces_f64()[0]).max() > 1e-3
+    # dynamics and trial moves: the sphere stays put, implicit-ion bookkeeping (N_B = N_N + N_N2)
+    o.md_run(300); o.mc_run(0, 400); o.mc_run(1, 40); o.steepest_descent(5, 0.0, 0.1, 0.1); o.md_run(50)
+    x1, v1, _ = o.state_f64()
+    assert np.all(x1[0, i_np] == x0[i_np]) and np.all(v1[0, i_np] == 0.0)
+    assert np.abs(x1[0, :40] - x0[:40]).max() > 1e-2
+    cnt = o.observables()[2][0]
+    assert cnt[2] == cnt[0] + cnt[1]
+    # list mode agrees with all pairs with the large sphere in the rows
+    b = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    b.set_list_mode(True, 0.6)
+    a = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    np.testing.assert_allclose(a.energy(), b.energy(), rtol=1e-12)
+    np.testing.assert_allclose(a.forces_f64(), b.forces_f64(), rtol=1e-10, atol=1e-10)
+
+
+def test_nanoparticle_shifts_the_titration_curve(oracle_mod):
+    """Sites are cationic when protonated (NH+ <-> N): a negative sphere in contact stabilises the
+    protonated state (alpha, the deprotonated fraction, drops), a positive one destabilises it."""
+    alpha = {}
+    for q in (-20.0, 0.0, 20.0):
+        w = make_workload(40, pH=[8.18] * 4, flags={"USE_DIHEDRAL_POT": False},
+                          nanoparticle=dict(charge=q, clearance=0.9))
+        o = w.init_engine(oracle_mod.OracleEngine(w.cfg))
+        sp = o.sample_params(260, md_steps_per_burst=20, use_md=True, mc_blocks=((0, 66), (1, 6)), p_burst1=0.7, p_burst2=0.3)
+        obs, _ = o.sample_loop(sp)
+        alpha[q] = obs[:, 60:, 0].mean() / w.n_sites[0]
+    assert alpha[-20.0] < alpha[0.0] - 0.01 < alpha[20.0] - 0.02, alpha
