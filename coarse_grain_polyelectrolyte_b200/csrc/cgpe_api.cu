@@ -24,6 +24,7 @@ struct cgpe_handle {
   std::vector<int> chg_host;   // [R][n_chg] chargeable particle ids (host copy)
   WideGraphCache wgraph;       // captured block of MD steps of the global-memory engine
   void *dhc_alloc = nullptr;   // DevState::dhc
+  size_t dhc_bytes = 0;
   bool two_radii = false;      // see upload_wca
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
@@ -537,7 +538,6 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     CU(cudaGetDeviceProperties(&prop, h->device));
     if (h->launch.smem > (size_t)prop.sharedMemPerBlockOptin) h->launch.items = 0;   // -> global-memory engine
   }
-  if (h->dhc_alloc) { cudaFree(h->dhc_alloc); h->dhc_alloc = nullptr; }
   h->g.dhc = nullptr; p.dhc_cap = 0; p.dhc_stride = 0;
   if (h->launch.items == 0) {
     if (p.P > p.NC && p.n_ions == 0)
@@ -550,7 +550,12 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
       const int G = p.dh_group > 0 ? p.dh_group : 1;
       p.dhc_stride = (G * n_chg + 31) / 32 * 32;
       p.dhc_cap = (((32 + G - 1) / G) * ((n_chg + 31) / 32) + 7) / 8 * 8;   // whole 16-byte groups of eight entries
-      CU(cudaMalloc(&h->dhc_alloc, sizeof(uint16_t) * (size_t)p.R * p.dhc_cap * p.dhc_stride));
+      const size_t need = sizeof(uint16_t) * (size_t)p.R * p.dhc_cap * p.dhc_stride;
+      if (need > h->dhc_bytes) {   // kept across set_state calls: cudaFree/cudaMalloc synchronise the device
+        if (h->dhc_alloc) { cudaFree(h->dhc_alloc); h->dhc_alloc = nullptr; h->dhc_bytes = 0; }
+        CU(cudaMalloc(&h->dhc_alloc, need));
+        h->dhc_bytes = need;
+      }
       h->g.dhc = static_cast<uint16_t *>(h->dhc_alloc);
     }
   }
