@@ -413,7 +413,7 @@ __device__ void build_dh_compact(Ctx &c) {
       }
     }
     c.s.dhn[idx] = (uint16_t)n;
-    for (; n & 7; ++n) lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)(p.n_chg * 16);
+    for (; n & 3; ++n) lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)(p.n_chg * 16);   // whole half groups
   }
   c.compact = true;   // every list is read only by the thread that wrote it: no barrier
 }
@@ -531,7 +531,7 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
         }
       } else if (pi4.w != 0.0f && c.compact) {
         // entries are byte offsets into cpos, groups of eight padded with the far-away uncharged dummy:
-        // no per-entry bounds test (WRAP keeps it: a folded dummy may land anywhere), no branch on the
+        // no per-entry bounds test, one per half group (WRAP keeps it: a folded dummy may land anywhere), no branch on the
         // cutoff (91 % of the listed pairs are inside it; the rest select a zero), the shared address of
         // cpos and the two loop constants pinned in registers instead of re-derived per pair
         const int n = c.s.dhn[idx];
@@ -545,16 +545,20 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
           const uint4 nxt = k0 + 8 < n ? __ldcg(lst) : make_uint4(0u, 0u, 0u, 0u);
           const uint32_t pk[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const uint32_t off = (e & 1) ? (pk[e >> 1] >> 16) : (pk[e >> 1] & 0xFFFFu);
-            const float4 pj4 = lds_f4(cpos_sa + off);
-            V3 d;
-            const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
-            bool ok = r2 < rc2;
-            if (WRAP) ok = ok && (k0 + e < n);
-            float fr = dh_force_unit_q(r2, nk, pj4.w);
-            fr = ok ? fr : 0.0f;
-            f.x = fmaf(fr, d.x, f.x); f.y = fmaf(fr, d.y, f.y); f.z = fmaf(fr, d.z, f.z);
+          for (int half = 0; half < 2; ++half) {
+            if (half == 1 && k0 + 4 >= n) break;   // short rows (high salt): the padding stops at the half group
+#pragma unroll
+            for (int e = 4 * half; e < 4 * half + 4; ++e) {
+              const uint32_t off = (e & 1) ? (pk[e >> 1] >> 16) : (pk[e >> 1] & 0xFFFFu);
+              const float4 pj4 = lds_f4(cpos_sa + off);
+              V3 d;
+              const float r2 = dist2<WRAP>(c, pi4, pj4, &d);
+              bool ok = r2 < rc2;
+              if (WRAP) ok = ok && (k0 + e < n);
+              float fr = dh_force_unit_q(r2, nk, pj4.w);
+              fr = ok ? fr : 0.0f;
+              f.x = fmaf(fr, d.x, f.x); f.y = fmaf(fr, d.y, f.y); f.z = fmaf(fr, d.z, f.z);
+            }
           }
           cur = nxt;
         }
@@ -931,7 +935,9 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
           if (p.use_dh && dq != 0.f) {
             // phi of every listed partner inside r_cut changes by dq e(r): lane b handles bit b of
             // each non-empty word (the helpers one word each, see above)
-            if (helpers) {
+            // (a row of one or two words -- high salt -- costs this warp less than the two barriers)
+            uint32_t live = __ballot_sync(0xffffffffu, row != 0u);
+            if (helpers && __popc(live) > 2) {
               if (c.lane == 0) {
                 ord[0] = pi4.x; ord[1] = pi4.y; ord[2] = pi4.z; ord[4] = dq;
                 ord[5] = __int_as_float(ci); ord[6] = __int_as_float(1);
@@ -939,7 +945,6 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
               mc_bar(c.nt);
               mc_bar(c.nt);
             } else {
-              uint32_t live = __ballot_sync(0xffffffffu, row != 0u);
               while (live) {
                 const int w = __ffs(live) - 1;
                 live &= live - 1;

@@ -62,12 +62,14 @@ def test_energy_and_forces_match_oracle(Engine, oracle_mod, n_mon, flags):
     np.testing.assert_array_equal(cnt_g, cnt_o)
 
 
-@pytest.mark.parametrize("n_mon,n_trials", [(50, 4000), (100, 6000), (1000, 20000), (2500, 6000)])
-def test_mc_bookkeeping_bit_exact(Engine, oracle_mod, n_mon, n_trials):
+@pytest.mark.parametrize("n_mon,n_trials,c_salt", [(50, 4000, 2e-2), (100, 6000, 2e-2), (1000, 20000, 2e-2),
+                                                   (1000, 12000, 1e-3),   # long Debye-Hueckel rows: helper warps update the potentials
+                                                   (2500, 6000, 2e-2)])
+def test_mc_bookkeeping_bit_exact(Engine, oracle_mod, n_mon, n_trials, c_salt):
     """Same Philox proposal stream on both sides -> identical sites, directions, decisions,
     types and charges; Delta-E within 1e-5 of the FP64 value.  A decision may differ only on a
     near-tie |u - bf| <= 1e-4 bf, which the oracle then follows and the test counts."""
-    w = make_workload(n_mon, pH=[7.0, 8.18, 9.0, 10.5])
+    w = make_workload(n_mon, pH=[7.0, 8.18, 9.0, 10.5], c_salt=c_salt)
     state = random_state(w, seed=7 + n_mon, jitter=0.03)
     g, o = _pair(Engine, oracle_mod, w, state)
     for rx in (0, 1, 0):
