@@ -194,11 +194,33 @@ def main_reference(args, rank, world):
         "mc_sweeps_per_s": trials / sum(sub.n_sites) / dt,
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Everything any library writes to fd 1 (NCCL prints its version banner there at every debug level)
+    goes to stderr from here on; emit() alone writes to the real stdout: ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -356,7 +378,7 @@ def main():
             except Exception as exc:  # the GPU line must still print
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {exc!r}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
