@@ -364,7 +364,8 @@ def main():
                          "(all kernels); the force kernel is bound by L2 gathers of partner positions, the trial loop by its "
                          "chain of dependent reads" if wide else
                          "Verlet-list algorithm: work counted on the pairs the lists hold (SURVEY 8d formula); the kernel is "
-                         "barrier/latency-bound at one CTA per replica, not pipe-bound"),
+                         "bound by instruction issue on the one SM of the slowest replica (63 % issue-slot utilisation, "
+                         "25 SASS instructions per listed Debye-Hueckel pair against 32 counted flop), not by a pipe"),
                 "allpairs_equivalent_tflops": allpairs_equiv,
             },
             "observables_check": {"alpha_mean": float(obs[..., 0].mean() / max(w.n_sites[0], 1)),
