@@ -935,9 +935,10 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
           if (p.use_dh && dq != 0.f) {
             // phi of every listed partner inside r_cut changes by dq e(r): lane b handles bit b of
             // each non-empty word (the helpers one word each, see above)
-            // (a row of one or two words -- high salt -- costs this warp less than the two barriers)
+            // (a row of one or two words -- high salt -- costs this warp less than two barriers of 32 warps;
+            // barriers of a small CTA are cheap: measured at N = 100, 8 CTAs per SM)
             uint32_t live = __ballot_sync(0xffffffffu, row != 0u);
-            if (helpers && __popc(live) > 2) {
+            if (helpers && __popc(live) > (c.nt > 256 ? 2 : 1)) {
               if (c.lane == 0) {
                 ord[0] = pi4.x; ord[1] = pi4.y; ord[2] = pi4.z; ord[4] = dq;
                 ord[5] = __int_as_float(ci); ord[6] = __int_as_float(1);
