@@ -11,8 +11,13 @@ Beyond the reference:
   * "Simulation configuration" may carry "ION_MODEL": "implicit" (default here: the chain alone,
     small ions only through the Debye-Hueckel screening, as BASELINE.json's north star describes)
     or "explicit" (the reference's B+/Na+/Cl- particles with H+ insertion / deletion,
-    M.py:173-198).
+    M.py:173-198);
+  * an optional section "Nanoparticle properties": {"charge": q, "sigma": [Angstrom], "epsilon": [kJ/mol],
+    "clearance": 1.3} places one fixed charged sphere (type "NP", `fix=[True]*3`) beside the first chain
+    (BASELINE config 4; the reference only announces it, README.md:14-15).  Implicit ions only.
 """
+import copy
+
 import numpy as np
 
 from coarse_grain_polyelectrolyte_b200 import espressomd, units
@@ -32,12 +37,19 @@ espressomd.assert_features(["WCA", "ELECTROSTATICS"])
 class Model(Properties):
     def __init__(self, input_dict, replicas=None, replica_offset=0, device=-1):
         self.replica_pH, self.replica_c_salt = self._replica_axes(input_dict, replicas)
+        self.nanoparticle = input_dict.get("Nanoparticle properties")
+        if self.nanoparticle is not None:   # one more row of the particle table, reduced like the others (P.py:307-311)
+            input_dict = copy.deepcopy(input_dict)
+            table = input_dict["Particles properties"]
+            table["NP"] = {"index": max(v["index"] for v in table.values()) + 1, "charge": self.nanoparticle["charge"],
+                           "sigma": self.nanoparticle.get("sigma", 34.8), "epsilon": self.nanoparticle.get("epsilon", 0.3)}
         super().__init__(input_dict, n_replicas=len(self.replica_pH), replica_offset=replica_offset, device=device)
         self.ion_model = input_dict["Simulation configuration"].get("ION_MODEL", "implicit")
         if self.ion_model not in ("implicit", "explicit"):
             raise ValueError("ION_MODEL must be 'implicit' or 'explicit'")
         self._bonded_interactions()
         self._create_polymer()
+        self._add_nanoparticle()
         self._add_salt_ions()
         self._non_bonded_interactions()
         self._long_range_interactions()
@@ -92,6 +104,20 @@ class Model(Properties):
                         me.add_bond((self.bend, pid - 1, pid + 1))
                     if self.USE_DIHEDRAL_POT and index < last - 1:
                         me.add_bond((self.dihedral, pid - 1, pid + 1, pid + 2))
+
+    def _add_nanoparticle(self):
+        if self.nanoparticle is None:
+            return
+        if self.ion_model != "implicit":
+            raise NotImplementedError("the nanoparticle needs ION_MODEL 'implicit' (an inserted H+ would carry its WCA energy)")
+        beads = np.asarray(self.polymers[0], dtype=np.float64)
+        clear = self.nanoparticle.get("clearance", 1.3) * 0.25 * (self.sigma_reduced_units["NP"] + max(self.sigma_reduced_units.values()))
+        pos = beads.mean(axis=0)
+        while np.min(np.linalg.norm(np.asarray(self.polymers).reshape(-1, 3) - pos, axis=1)) < clear:
+            pos[0] += 0.25
+        self.nanoparticle_id = len(self.system.part)
+        self.system.part.add(id=self.nanoparticle_id, pos=pos, type=self.type_particles["NP"],
+                             q=self.charge_reduced_units["NP"], fix=[True, True, True])
 
     # -- M.py:173-198 --------------------------------------------------------------------------------
     def _add_salt_ions(self):

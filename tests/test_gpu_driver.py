@@ -133,3 +133,31 @@ def test_explicit_ion_model_beyond_shared_memory():
         n_b = m.system.number_of_particles(type=tp["B"])
         assert n_b == m.system.number_of_particles(type=tp["N"]) + m.system.number_of_particles(type=tp["N2"])
         assert n_b < m.n_acid and np.isfinite(m.system.analysis.energy()["total"])
+
+
+def test_nanoparticle_through_the_driver():
+    """"Nanoparticle properties" in the dictionary (BASELINE config 4): Model adds one fixed sphere with
+    part.add(..., fix=[True]*3); the facade makes it a spectator slot; equilibration, warm-up and the fused
+    sampling loop run as usual, the sphere never moves, a negative one lowers the degree of deprotonation."""
+    from modules.EnsembleDynamics import EnsembleDynamics
+    alpha = {}
+    for q in (-20.0, 20.0):
+        p = small_run_parameters(n_mon=40, n_blocks=4, block=60)
+        p["Simulation configuration"]["USE_DIHEDRAL_POT"] = False
+        p["Nanoparticle properties"] = {"charge": q, "sigma": 34.8, "epsilon": 0.3, "clearance": 1.0}
+        ens = EnsembleDynamics(p, replicas=dict(pH=[8.18] * 8))
+        i_np = ens.nanoparticle_id
+        assert i_np == 40 and len(ens.system.part) == 41
+        cfg = ens.system._build_config()
+        assert cfg.n_ion_slots == 1 and cfg.fixed_type_mask == 1 << ens.type_particles["NP"] and cfg.reactions[0].type_ion == -1
+        ens.system._ensure_engine()
+        x0 = ens.system._engine.get_state()[0][:, i_np, :3].copy()
+        ens.equilibrate_pH()
+        ens.perform_sampling()
+        x1, v1, _ = ens.system._engine.get_state()
+        np.testing.assert_array_equal(x1[:, i_np, :3], x0)
+        assert np.all(v1[:, i_np, :3] == 0.0)
+        np.testing.assert_array_equal(ens.num_B, ens.num_As + ens.num_As2)
+        assert np.all(np.isfinite(ens.rad_gyr))
+        alpha[q] = ens.num_As[:, ens.num_As.shape[1] // 4:].mean() / ens.n_nh
+    assert alpha[-20.0] < alpha[20.0] - 0.03, alpha
