@@ -115,6 +115,23 @@ def ncu_traffic():
         return None
 
 
+def ncu_issue():
+    """Instruction-issue figures of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_sample_loop_ncu_summary.json): the roof that actually binds this kernel.  Measured under the
+    profiler on the same command, reported beside the live flop count, never instead of it."""
+    path = os.path.join(ROOT, "profiles", "r1_sample_loop_ncu_summary.json")
+    try:
+        with open(path) as f:
+            m = json.load(f)["metrics"]
+        ipc = float(m["sm__inst_executed.avg.per_cycle_elapsed"][0])
+        return {"warp_inst_per_cycle_per_sm": ipc, "peak": 4.0, "frac": ipc / 4.0,
+                "issue_slots_busy_of_active_cycles": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]) / 100.0,
+                "sm_active_of_elapsed_cycles": float(m["sm__cycles_active.avg"][0]) / float(m["sm__cycles_elapsed.avg"][0]),
+                "source": "ncu --set full capture profiles/r1_sample_loop_ncu_summary.json (40-step launch, under the profiler)"}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def algorithmic_flops(n_mon, md_steps, trials, stats):
     """SURVEY §8d convention on the work the kernel's algorithm performs (unique listed pairs)."""
     w_all, w_in, d_all, d_in = (float(x) / 2.0 for x in stats)   # directed -> unique
@@ -367,6 +384,7 @@ def main():
                          "bound by instruction issue on the one SM of the slowest replica (63 % issue-slot utilisation, "
                          "25 SASS instructions per listed Debye-Hueckel pair against 32 counted flop), not by a pipe"),
                 "allpairs_equivalent_tflops": allpairs_equiv,
+                "instruction_issue": None if wide else ncu_issue(),
             },
             "observables_check": {"alpha_mean": float(obs[..., 0].mean() / max(w.n_sites[0], 1)),
                                   "rg_mean": float(obs[..., 3].mean()), "ree_mean": float(obs[..., 4].mean())},
