@@ -309,11 +309,17 @@ def main():
     barrier()
     t0 = time.perf_counter()
     eng.set_state(*pin)
+    t_a = time.perf_counter()
     eng.set_replica_params(pH=w.pH, kappa=w.kappa, r_cut=w.r_cut)
+    t_b = time.perf_counter()
     obs2, _ = eng.sample_loop(sp)
+    t_c = time.perf_counter()
     out_state = eng.get_state()
+    t_d = time.perf_counter()
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_parts = {"set_state": t_a - t0, "set_replica_params": t_b - t_a, "sample_loop": t_c - t_b,
+                 "get_state": t_d - t_c, "barrier": e2e_s - (t_d - t0), "kernel_ms": eng.last_call_ms()[0]}
     ce = eng.counters()
     md_steps_e2e = int((ce["md_steps"] - c1["md_steps"]).sum())
     h2d = sum(a.nbytes for a in pin) + 3 * 8 * w.R
@@ -361,6 +367,7 @@ def main():
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(args.steps, 1),
                     "d2h_bytes_per_step": d2h / max(args.steps, 1), "seconds": t_e2e,
+                    "rank0_parts_s": {k: round(v, 4) for k, v in e2e_parts.items()},
                     "call": "Engine.set_state + set_replica_params + sample_loop + get_state on host (pinned) buffers"},
             "gpu_launches": launches,
             "clocks": clocks,
