@@ -25,6 +25,8 @@ struct cgpe_handle {
   WideGraphCache wgraph;       // captured block of MD steps of the global-memory engine
   void *dhc_alloc = nullptr;   // DevState::dhc
   size_t dhc_bytes = 0;
+  size_t smem_optin = 0;       // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once (cudaGetDeviceProperties is slow,
+                               // and slower still when eight processes ask at once)
   bool two_radii = false;      // see upload_wca
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
@@ -156,10 +158,8 @@ int choose_capacities(cgpe_handle *h) {
   }
   if (h->cfg.cap_wca > 0) p.cap_w = h->cfg.cap_wca;
   else {
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, h->device));
     p.cap_w = 0;
-    const size_t fixed = chain_smem_bytes(p), budget = (size_t)prop.sharedMemPerBlockOptin;
+    const size_t fixed = chain_smem_bytes(p), budget = h->smem_optin;
     long cap = budget > fixed + 64 ? (long)((budget - fixed - 64) / (2 * (size_t)p.P)) : 0;
     if (cap > 64) cap = 64;
     if (cap < 4) cap = 4;   // too little: chain_launch_shape / the smem check will refuse
@@ -362,6 +362,14 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   h->err[0] = 0;
   DeviceGuard guard(dev);
 
+  {
+    int optin = 0;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || optin <= 0) {
+      delete h;
+      return fail(nullptr, CGPE_ERR_CUDA, "cannot read the shared-memory limit of device %d", dev);
+    }
+    h->smem_optin = (size_t)optin;
+  }
   DevParams &p = h->p;
   std::memset(&p, 0, sizeof(p));
   p.R = cfg->n_replicas; p.N = cfg->n_beads; p.NC = cfg->n_chains * cfg->n_beads;
@@ -533,11 +541,7 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     int rc_cap = choose_capacities(h);
     if (rc_cap) return rc_cap;
   }
-  if (h->launch.items != 0) {
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, h->device));
-    if (h->launch.smem > (size_t)prop.sharedMemPerBlockOptin) h->launch.items = 0;   // -> global-memory engine
-  }
+  if (h->launch.items != 0 && h->launch.smem > h->smem_optin) h->launch.items = 0;   // -> global-memory engine
   h->g.dhc = nullptr; p.dhc_cap = 0; p.dhc_stride = 0;
   if (h->launch.items == 0) {
     if (p.P > p.NC && p.n_ions == 0)
