@@ -284,3 +284,30 @@ def test_nanoparticle_shifts_the_titration_curve(oracle_mod):
         obs, _ = o.sample_loop(sp)
         alpha[q] = obs[:, 60:, 0].mean() / w.n_sites[0]
     assert alpha[-20.0] < alpha[0.0] - 0.01 < alpha[20.0] - 0.02, alpha
+
+
+def test_oracle_invariances_hold_for_random_states(oracle_mod):
+    """Size-independent properties of the restatement itself (hypothesis-driven seeds): rigid translations leave every
+    energy component unchanged, total = kinetic + coulomb + bonded + non_bonded, forces sum to zero, and replicas do
+    not see each other (permuting them permutes the results)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=8, deadline=None)
+    @given(seed=st.integers(0, 10_000), shift=st.tuples(*[st.floats(-3.0, 3.0)] * 3), frac=st.floats(0.0, 1.0))
+    def check(seed, shift, frac):
+        w = make_workload(30, pH=[7.0, 9.0, 11.0])
+        state = random_state(w, seed=seed, jitter=0.03, protonated_fraction=frac)
+        o = load(oracle_mod.OracleEngine(w.cfg), w, state)
+        e0, f0 = o.energy(), o.forces_f64()
+        np.testing.assert_allclose(e0[:, 0], e0[:, 1:].sum(axis=1), rtol=1e-12)
+        assert np.abs(f0.sum(axis=1)).max() < 1e-9 * max(1.0, np.abs(f0).max()) * 30
+        x = o.state_f64()[0]
+        o.set_positions_f64(x + np.asarray(shift))
+        np.testing.assert_allclose(o.energy()[:, [2, 3, 4]], e0[:, [2, 3, 4]], rtol=1e-9, atol=1e-9)
+        perm = [2, 0, 1]
+        w2 = make_workload(30, pH=[11.0, 7.0, 9.0])
+        o2 = load(oracle_mod.OracleEngine(w2.cfg), w2, tuple(a[perm] for a in state))
+        np.testing.assert_allclose(o2.energy(), e0[perm], rtol=1e-12)
+        np.testing.assert_allclose(o2.forces_f64(), f0[perm], rtol=1e-12, atol=1e-12)
+
+    check()
