@@ -7,6 +7,7 @@ cannot be run here), so these are the vectors SURVEY.md §8c asks the build to c
                     expressions written here (independent of oracle/cgpe_oracle.c)
   chain_n52.npz     frozen N=52 chain (the notebook's size): FP64 oracle energy breakdown + forces
   chain_n100.npz    frozen N=100 chain (examples/run_test.py size): same
+  chain_n100_np.npz the N=100 chain next to a fixed sphere of charge -20 (BASELINE config 4): same
   trials_n100.npz   10^4-trial proposal log of reaction 1 (site, direction, u, Delta-E, decision)
   titration.npz     ideal titration curve at 64 pH points (utils.py:15-16 closed form)
 
@@ -81,12 +82,17 @@ def few_body():
     return out
 
 
-def chain(n_mon, seed):
-    w = make_workload(n_mon, pH=[8.0])
+def chain(n_mon, seed, np_charge=None):
+    """np_charge: BASELINE config 4, one fixed sphere (sigma = 10 sim_length) of that charge in contact with the chain."""
+    kw = {} if np_charge is None else dict(nanoparticle=dict(charge=np_charge, clearance=0.9))
+    w = make_workload(n_mon, pH=[8.0], **kw)
     state = random_state(w, seed=seed, jitter=0.03)
     o = load(OracleEngine(w.cfg), w, state)
-    return dict(n_mon=n_mon, seed=seed, xyzq=state[0], vel=state[1], type=state[2], energy=o.energy(),
-                forces=o.forces_f64(), min_dist=o.min_dist(), rg=o.observables()[0], ree=o.observables()[1])
+    out = dict(n_mon=n_mon, seed=seed, xyzq=state[0], vel=state[1], type=state[2], energy=o.energy(),
+               forces=o.forces_f64(), min_dist=o.min_dist(), rg=o.observables()[0], ree=o.observables()[1])
+    if np_charge is not None:
+        out["np_charge"] = np_charge
+    return out
 
 
 def trials(n_mon=100, n_trials=10000, seed=17):
@@ -108,6 +114,7 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "few_body.npz"), **few_body())
     np.savez_compressed(os.path.join(HERE, "chain_n52.npz"), **chain(52, 52))
     np.savez_compressed(os.path.join(HERE, "chain_n100.npz"), **chain(100, 100))
+    np.savez_compressed(os.path.join(HERE, "chain_n100_np.npz"), **chain(100, 101, np_charge=-20.0))
     np.savez_compressed(os.path.join(HERE, "trials_n100.npz"), **trials())
     np.savez_compressed(os.path.join(HERE, "titration.npz"), **titration())
     for f in sorted(os.listdir(HERE)):

@@ -18,11 +18,12 @@ def small_run_parameters(n_mon=40, n_blocks=2, block=40):
     return workloads.example_parameters(n_mon, **{"Montecarlo properties": {"N_BLOCKS": n_blocks, "DESIRED_BLOCK_SIZE": block, "PROB_REACTION": 0.7}})
 
 
-@pytest.mark.parametrize("name", ["chain_n52.npz", "chain_n100.npz"])
+@pytest.mark.parametrize("name", ["chain_n52.npz", "chain_n100.npz", "chain_n100_np.npz"])
 def test_golden_chain_through_the_c_abi(name):
     from coarse_grain_polyelectrolyte_b200.engine import Engine
     g = np.load(os.path.join(GOLD, name))
-    w = make_workload(int(g["n_mon"]), pH=[8.0])
+    kw = dict(nanoparticle=dict(charge=float(g["np_charge"]), clearance=0.9)) if "np_charge" in g else {}
+    w = make_workload(int(g["n_mon"]), pH=[8.0], **kw)
     e = load(Engine(w.cfg), w, (g["xyzq"], g["vel"], g["type"]))
     np.testing.assert_allclose(e.energy(), g["energy"], rtol=1e-5, atol=1e-4)
     fmax = np.abs(g["forces"]).max()

@@ -100,10 +100,11 @@ def test_forces_are_minus_grad_energy(oracle_mod, flags):
     assert np.abs(F.sum(axis=0)).max() < 1e-9 * np.abs(F).max() * 40
 
 
-@pytest.mark.parametrize("name", ["chain_n52.npz", "chain_n100.npz"])
+@pytest.mark.parametrize("name", ["chain_n52.npz", "chain_n100.npz", "chain_n100_np.npz"])
 def test_golden_chain(oracle_mod, name):
     g = np.load(os.path.join(GOLD, name))
-    w = make_workload(int(g["n_mon"]), pH=[8.0])
+    kw = dict(nanoparticle=dict(charge=float(g["np_charge"]), clearance=0.9)) if "np_charge" in g else {}
+    w = make_workload(int(g["n_mon"]), pH=[8.0], **kw)
     o = load(oracle_mod.OracleEngine(w.cfg), w, (g["xyzq"], g["vel"], g["type"]))
     np.testing.assert_allclose(o.energy(), g["energy"], rtol=1e-12)
     np.testing.assert_allclose(o.forces_f64(), g["forces"], rtol=1e-10, atol=1e-10)
