@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_TYPES = 16
 MAX_REACTIONS = 4
 MAX_MC_BLOCKS = 4
@@ -112,6 +112,8 @@ SIGNATURES = {
     "min_dist": (C.c_int, [_p, _p]),
     "get_counters": (C.c_int, [_p, _p, _p, _p, _p]),
     "list_stats": (C.c_int, [_p, _p]),
+    "set_engine": (C.c_int, [_p, C.c_int32]),
+    "engine_info": (C.c_int, [_p, _i32p, _p]),
     "last_call_ms": (C.c_int, [_p, _fp, _i32p]),
 }
 
@@ -346,6 +348,18 @@ class EngineBase:
         out = np.empty((self.R, 4), np.float64)
         self._check(self._b.list_stats(self._h, _ptr(out)), "list_stats")
         return out
+
+    ENGINES = {"auto": -1, "solo": 0, "duo": 1}
+
+    def set_engine(self, engine):
+        """'solo' (one CTA per replica), 'duo' (cluster of two CTAs per replica) or 'auto'."""
+        self._check(self._b.set_engine(self._h, int(self.ENGINES.get(engine, engine))), "set_engine")
+
+    def engine_info(self):
+        eng = C.c_int32()
+        cb = np.zeros(self.R, np.int64)
+        self._check(self._b.engine_info(self._h, C.byref(eng), _ptr(cb)), "engine_info")
+        return {"engine": ("solo", "duo", "wide")[eng.value] if 0 <= eng.value <= 2 else "oracle", "compact_builds": cb}
 
     def last_call_ms(self):
         ms, n = C.c_float(), C.c_int32()

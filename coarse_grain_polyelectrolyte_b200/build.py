@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcgpe.so")
-SOURCES = ["cgpe_api.cu", "chain_engine.cu", "wide_engine.cu", "diag_kernels.cu"]
-HEADERS = ["cgpe_device.cuh", "chain_engine.cuh", "wide_engine.cuh", os.path.join("..", "..", "include", "cgpe.h")]
+SOURCES = ["cgpe_api.cu", "chain_engine.cu", "duo_engine.cu", "wide_engine.cu", "diag_kernels.cu"]
+HEADERS = ["cgpe_device.cuh", "chain_engine.cuh", "duo_engine.cuh", "wide_engine.cuh", os.path.join("..", "..", "include", "cgpe.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--ftz=true",

@@ -9,6 +9,7 @@
 #include <new>
 #include <vector>
 
+#include "duo_engine.cuh"
 #include "wide_engine.cuh"
 
 using namespace cgpe;
@@ -28,6 +29,10 @@ struct cgpe_handle {
   size_t smem_optin = 0;       // cudaDevAttrMaxSharedMemoryPerBlockOptin, read once (cudaGetDeviceProperties is slow,
                                // and slower still when eight processes ask at once)
   bool two_radii = false;      // see upload_wca
+  DuoShape duo;                // cluster engine (two CTAs per replica): shape, or duo.ok == 0
+  int engine_pref = -1;        // cgpe_set_engine: -1 = choose, 0 = one CTA per replica, 1 = cluster engine
+  int n_sm = 0;
+  size_t dhc_need_solo = 0;
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
   int device;
@@ -196,6 +201,40 @@ int require_engine(cgpe_handle *h) {
   if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
   if (h->launch.items == 0 && !h->wide)
     return fail(h, CGPE_ERR_UNSUPPORTED, "P=%d particles per replica: no engine available", h->p.P);
+  return CGPE_OK;
+}
+
+// The cluster engine serves implicit-ion replicas without spectator particles; chosen unless the caller
+// (cgpe_set_engine) or CGPE_ENGINE=solo says otherwise.
+bool use_duo(const cgpe_handle *h) {
+  if (h->wide || !h->duo.ok || h->launch.items == 0) return false;
+  if (h->engine_pref >= 0) return h->engine_pref == 1;
+  return h->p.P >= 64;
+}
+
+// shape of the cluster engine for the current state (after choose_capacities)
+int plan_duo(cgpe_handle *h) {
+  DevParams &p = h->p;
+  h->duo.ok = 0;
+  if (p.n_ions != 0 || p.P != p.NC || p.fixed_mask != 0u || p.P < 8 || p.P > 2048 || h->launch.items == 0) return CGPE_OK;
+  const int half = (p.P + 1) / 2;
+  int n_loc = 0;
+  for (int r = 0; r < p.R; ++r) {
+    int a = 0;
+    for (int i = 0; i < p.n_chg; ++i) a += h->chg_host[(size_t)r * p.n_chg + i] < half ? 1 : 0;
+    n_loc = std::max(n_loc, std::max(a, p.n_chg - a));
+  }
+  // two CTAs of up to 512 threads share an SM: each may take half of its shared memory (minus 1 KB the system keeps per CTA)
+  const int nt = std::max(32, (half + 31) / 32 * 32);
+  const size_t budget = nt <= 512 ? std::min(h->smem_optin, (size_t)(233472 / 2 - 1024)) : h->smem_optin;
+  int *order = h->duo.order;
+  duo_layout(p, n_loc, budget, h->cfg.cap_wca, &h->duo);
+  h->duo.order = order;
+  h->duo.n_sm = h->n_sm;
+  if (h->duo.ok && !h->duo.order) {
+    CU(cudaMalloc((void **)&h->duo.order, sizeof(int) * p.R));
+    h->allocs.push_back((void *)h->duo.order);
+  }
   return CGPE_OK;
 }
 
@@ -369,6 +408,10 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
       return fail(nullptr, CGPE_ERR_CUDA, "cannot read the shared-memory limit of device %d", dev);
     }
     h->smem_optin = (size_t)optin;
+    int n_sm = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    h->n_sm = n_sm > 0 ? n_sm : 148;
+    std::memset(&h->duo, 0, sizeof(h->duo));
   }
   DevParams &p = h->p;
   std::memset(&p, 0, sizeof(p));
@@ -396,6 +439,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   p.fixed_mask = (uint32_t)cfg->fixed_type_mask;
   p.thermostat_seed = 0u;
   if (const char *dp = std::getenv("CGPE_DENSE_POLICY")) p.dense_policy = std::atoi(dp);   // diagnostics only
+  if (const char *en = std::getenv("CGPE_ENGINE")) h->engine_pref = std::strcmp(en, "solo") == 0 ? 0 : std::strcmp(en, "duo") == 0 ? 1 : -1;
   for (int m = 0; m < p.n_rx; ++m) {
     const cgpe_reaction &r = cfg->reactions[m];
     DevReaction &d = p.rx[m];
@@ -433,7 +477,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   ALLOC(g.ion_cnt, (size_t)p.R * 2);
   ALLOC(g.kappa, p.R); ALLOC(g.rcut, p.R); ALLOC(g.kT, p.R); ALLOC(g.gamma, p.R); ALLOC(g.pH, p.R);
   ALLOC(g.time, p.R); ALLOC(g.md_counter, p.R); ALLOC(g.md_steps, p.R); ALLOC(g.samples_done, p.R);
-  ALLOC(g.rebuilds, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
+  ALLOC(g.rebuilds, p.R); ALLOC(g.compact_builds, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
   ALLOC(g.f_valid, p.R); ALLOC(g.err, p.R);
   ALLOC(h->d_tmp_d, (size_t)p.R * 8); ALLOC(h->d_tmp_i, (size_t)p.R * 3); ALLOC(h->d_tmp_f4, RP);
 #undef ALLOC
@@ -543,6 +587,7 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
   }
   if (h->launch.items != 0 && h->launch.smem > h->smem_optin) h->launch.items = 0;   // -> global-memory engine
   h->g.dhc = nullptr; p.dhc_cap = 0; p.dhc_stride = 0;
+  h->duo.ok = 0;
   if (h->launch.items == 0) {
     if (p.P > p.NC && p.n_ions == 0)
       return fail(h, CGPE_ERR_UNSUPPORTED, "spectator particles (slots without an ion reaction) are served by the shared-memory engine only (<= 2048 particles per replica)");
@@ -554,13 +599,21 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
       const int G = p.dh_group > 0 ? p.dh_group : 1;
       p.dhc_stride = (G * n_chg + 31) / 32 * 32;
       p.dhc_cap = (((32 + G - 1) / G) * ((n_chg + 31) / 32) + 7) / 8 * 8;   // whole 16-byte groups of eight entries
-      const size_t need = sizeof(uint16_t) * (size_t)p.R * p.dhc_cap * p.dhc_stride;
+      size_t need = sizeof(uint16_t) * (size_t)p.R * p.dhc_cap * p.dhc_stride;
+      {
+        int rc_duo = plan_duo(h);
+        if (rc_duo) return rc_duo;
+        if (h->duo.ok) need = std::max(need, sizeof(uint16_t) * (size_t)p.R * 2 * h->duo.dhc_cap * h->duo.dhc_stride);
+      }
       if (need > h->dhc_bytes) {   // kept across set_state calls: cudaFree/cudaMalloc synchronise the device
         if (h->dhc_alloc) { cudaFree(h->dhc_alloc); h->dhc_alloc = nullptr; h->dhc_bytes = 0; }
         CU(cudaMalloc(&h->dhc_alloc, need));
         h->dhc_bytes = need;
       }
       h->g.dhc = static_cast<uint16_t *>(h->dhc_alloc);
+    } else {
+      int rc_duo = plan_duo(h);
+      if (rc_duo) return rc_duo;
     }
   }
   {   // list radii: see upload_wca
@@ -755,6 +808,7 @@ int cgpe_md_run(cgpe_handle *h, int32_t n_steps) {
   begin_timing(h);
   int launches = 1;
   if (h->wide) { launches = 0; CU(wide_md_run(h->p, h->g, h->w, n_steps, h->stream, &launches, &h->wgraph)); }
+  else if (use_duo(h)) { launches = 2; CU(duo_md_run(h->p, h->g, h->duo, n_steps, h->stream)); }
   else CU(launch_md_run(h->p, h->g, h->launch, n_steps, h->stream));
   end_timing(h, launches);
   return CGPE_OK;
@@ -796,6 +850,7 @@ int cgpe_mc_run(cgpe_handle *h, int32_t reaction_id, int32_t n_trials, cgpe_tria
   begin_timing(h);
   int launches = 1;
   if (h->wide) { launches = 0; CU(wide_mc_run(h->p, h->g, h->w, reaction_id, n_trials, d_trace, h->stream, &launches)); }
+  else if (use_duo(h)) { launches = 2; CU(duo_mc_run(h->p, h->g, h->duo, reaction_id, n_trials, d_trace, h->stream)); }
   else CU(launch_mc_run(h->p, h->g, h->launch, reaction_id, n_trials, d_trace, h->stream));
   end_timing(h, launches);
   if (d_trace) {
@@ -840,6 +895,10 @@ int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp) {
     launches = 0;
     CU(wide_sample_loop(h->p, h->g, h->w, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                         h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->d_tmp_d, h->d_tmp_i, h->stream, &launches, &h->wgraph));
+  } else if (use_duo(h)) {
+    launches = 2;   // the placement plan (k_duo_plan) + the loop itself
+    CU(duo_sample_loop(h->p, h->g, h->duo, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
+                       h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
   } else {
     CU(launch_sample_loop(h->p, h->g, h->launch, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                           h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
@@ -895,6 +954,7 @@ int cgpe_md_forces(cgpe_handle *h, float *out) {
   if (rc) return rc;
   DeviceGuard guard(h->device);
   if (h->wide) CU(wide_md_forces(h->p, h->g, h->w, h->d_tmp_f4, h->stream));
+  else if (use_duo(h)) CU(duo_md_forces(h->p, h->g, h->duo, h->d_tmp_f4, h->stream));
   else CU(launch_md_forces(h->p, h->g, h->launch, h->d_tmp_f4, h->stream));
   CU(cudaMemcpyAsync(out, h->d_tmp_f4, sizeof(float4) * (size_t)h->p.R * h->p.P, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -949,6 +1009,27 @@ int cgpe_list_stats(cgpe_handle *h, double *out) {
   CU(cudaMemcpyAsync(out, h->d_tmp_d, sizeof(double) * h->p.R * 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return check_device_errors(h);
+}
+
+int cgpe_set_engine(cgpe_handle *h, int32_t engine) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (engine < -1 || engine > 1) return fail(h, CGPE_ERR_INVALID, "engine must be -1 (choose), 0 (one CTA per replica) or 1 (cluster of two CTAs)");
+  if (engine == 1 && h->have_state && (!h->duo.ok || h->wide))
+    return fail(h, CGPE_ERR_UNSUPPORTED, "the cluster engine serves implicit-ion replicas of 8..2048 chain beads without spectator particles");
+  h->engine_pref = engine;
+  return CGPE_OK;
+}
+
+int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
+  DeviceGuard guard(h->device);
+  if (engine) *engine = h->wide ? 2 : use_duo(h) ? 1 : 0;
+  if (compact_builds) {
+    CU(cudaMemcpyAsync(compact_builds, h->g.compact_builds, sizeof(int64_t) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return CGPE_OK;
 }
 
 int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches) {

@@ -85,6 +85,7 @@ struct DevState {
   double *pH;         // [R]
   double *time;       // [R]
   long long *md_counter, *md_steps, *samples_done, *rebuilds;   // [R]
+  long long *compact_builds;   // [R] times the compact Debye-Hueckel partner lists were written (cgpe_engine_info)
   long long *trials, *accepted;                                  // [R][n_rx]
   int *f_valid;       // [R]
   int *err;           // [R]

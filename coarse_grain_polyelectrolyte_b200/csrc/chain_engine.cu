@@ -416,6 +416,7 @@ __device__ void build_dh_compact(Ctx &c) {
     for (; n & 3; ++n) lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)(p.n_chg * 16);   // whole half groups
   }
   c.compact = true;   // every list is read only by the thread that wrote it: no barrier
+  if (c.tid == 0) c.g.compact_builds[c.r] += 1;
 }
 
 // ---- forces ------------------------------------------------------------------------------------
@@ -1229,6 +1230,7 @@ k_md_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
   load_state(c, t, false);
   build_lists(c, t);
   if (p.use_dh) { build_qlist(c); __syncthreads(); }
+  build_dh_compact(c);   // the partner lists the MD loop walks (md_steps)
   compute_forces(c, t, false, 0ull);
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {

@@ -37,7 +37,7 @@ extern "C" {
 #define CGPE_API
 #endif
 
-#define CGPE_ABI_VERSION 5
+#define CGPE_ABI_VERSION 6
 #define CGPE_MAX_TYPES 16     /* interacting particle types (the reference uses 8, M.py:58-76) */
 #define CGPE_MAX_REACTIONS 4  /* reaction objects (the reference uses 2, M.py:211-233)         */
 #define CGPE_MAX_MC_BLOCKS 4  /* MC blocks per sample (the reference uses 2, E.py:94-95)       */
@@ -229,6 +229,16 @@ CGPE_API int cgpe_get_counters(cgpe_handle *h, int64_t *md_steps, int64_t *trial
  * those inside their cutoff, directed Debye-Hueckel list entries, those between two charged
  * particles inside r_cut.  (Unique pairs = directed / 2.)  Feeds the roofline arithmetic. */
 CGPE_API int cgpe_list_stats(cgpe_handle *h, double *out);
+/* Which kernels serve integrator.run / reaction.reaction / the fused sampling loop (E.py:88-95) of this handle:
+ *   0 = one persistent CTA per replica (shared-memory engine), 1 = one thread-block cluster of two CTAs per
+ *   replica (implicit-ion replicas of 8..2048 chain beads without spectator particles), -1 = the library
+ *   chooses (default: the cluster engine wherever it applies).  Replicas beyond 2048 particles always run on
+ *   the global-memory engine.  State between calls is engine-agnostic; the Markov chain is the same. */
+CGPE_API int cgpe_set_engine(cgpe_handle *h, int32_t engine);
+/* engine: the one in force (0, 1 as above, 2 = global-memory engine); compact_builds [R] (may be NULL): how
+ * often each replica wrote the compact Debye-Hueckel partner lists its MD force loop walks -- lets a test
+ * assert that it measured the code path the benchmark times. */
+CGPE_API int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds);
 /* device time of the last hot-path call in milliseconds (CUDA events on the handle's stream) and
  * the number of kernels it launched */
 CGPE_API int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches);

@@ -1084,6 +1084,13 @@ int orc_list_stats(orc_handle *h, double *out) {
   return CGPE_OK;
 }
 
+/* the oracle has one engine; the entry points exist so that the same binding drives both libraries */
+int orc_set_engine(orc_handle *h, int32_t engine) { (void)h; (void)engine; return CGPE_OK; }
+int orc_engine_info(orc_handle *h, int32_t *engine, int64_t *compact_builds) {
+  if (engine) *engine = -1;
+  if (compact_builds) for (int r = 0; r < h->cfg.n_replicas; ++r) compact_builds[r] = 0;
+  return CGPE_OK;
+}
 int orc_last_call_ms(orc_handle *h, float *ms, int32_t *n) { (void)h; if (ms) *ms = 0.f; if (n) *n = 0; return CGPE_OK; }
 
 /* ------------------------------------------------------------------------------------------- */

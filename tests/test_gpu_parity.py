@@ -19,10 +19,20 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5
 
 
-@pytest.fixture(scope="module")
-def Engine():
-    from coarse_grain_polyelectrolyte_b200.engine import Engine
-    return Engine
+@pytest.fixture(scope="module", params=["auto", "solo"])
+def Engine(request):
+    """Every test of this module runs twice: with the engine the library chooses (the cluster engine of
+    two CTAs per replica wherever it applies, i.e. what bench.py times) and pinned to the one-CTA-per-replica
+    engine."""
+    from coarse_grain_polyelectrolyte_b200.engine import Engine as E
+    if request.param == "auto":
+        return E
+
+    def make(cfg):
+        e = E(cfg)
+        e.set_engine("solo")
+        return e
+    return make
 
 
 def _pair(Engine, oracle_mod, w, state):
