@@ -113,7 +113,7 @@ SIGNATURES = {
     "get_counters": (C.c_int, [_p, _p, _p, _p, _p]),
     "list_stats": (C.c_int, [_p, _p]),
     "set_engine": (C.c_int, [_p, C.c_int32]),
-    "engine_info": (C.c_int, [_p, _i32p, _p]),
+    "engine_info": (C.c_int, [_p, _i32p, _p, _p]),
     "last_call_ms": (C.c_int, [_p, _fp, _i32p]),
 }
 
@@ -358,8 +358,10 @@ class EngineBase:
     def engine_info(self):
         eng = C.c_int32()
         cb = np.zeros(self.R, np.int64)
-        self._check(self._b.engine_info(self._h, C.byref(eng), _ptr(cb)), "engine_info")
-        return {"engine": ("solo", "duo", "wide")[eng.value] if 0 <= eng.value <= 2 else "oracle", "compact_builds": cb}
+        ns = np.zeros((self.R, 2, 2), np.int64)
+        self._check(self._b.engine_info(self._h, C.byref(eng), _ptr(cb), _ptr(ns)), "engine_info")
+        return {"engine": ("solo", "duo", "wide")[eng.value] if 0 <= eng.value <= 2 else "oracle", "compact_builds": cb,
+                "cta_ns": ns}
 
     def last_call_ms(self):
         ms, n = C.c_float(), C.c_int32()

@@ -477,7 +477,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   ALLOC(g.ion_cnt, (size_t)p.R * 2);
   ALLOC(g.kappa, p.R); ALLOC(g.rcut, p.R); ALLOC(g.kT, p.R); ALLOC(g.gamma, p.R); ALLOC(g.pH, p.R);
   ALLOC(g.time, p.R); ALLOC(g.md_counter, p.R); ALLOC(g.md_steps, p.R); ALLOC(g.samples_done, p.R);
-  ALLOC(g.rebuilds, p.R); ALLOC(g.compact_builds, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
+  ALLOC(g.rebuilds, p.R); ALLOC(g.compact_builds, p.R); ALLOC(g.cta_ns, (size_t)p.R * 4); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
   ALLOC(g.f_valid, p.R); ALLOC(g.err, p.R);
   ALLOC(h->d_tmp_d, (size_t)p.R * 8); ALLOC(h->d_tmp_i, (size_t)p.R * 3); ALLOC(h->d_tmp_f4, RP);
 #undef ALLOC
@@ -1020,15 +1020,14 @@ int cgpe_set_engine(cgpe_handle *h, int32_t engine) {
   return CGPE_OK;
 }
 
-int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds) {
+int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds, int64_t *cta_ns) {
   if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
   if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
   DeviceGuard guard(h->device);
   if (engine) *engine = h->wide ? 2 : use_duo(h) ? 1 : 0;
-  if (compact_builds) {
-    CU(cudaMemcpyAsync(compact_builds, h->g.compact_builds, sizeof(int64_t) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-  }
+  if (compact_builds) CU(cudaMemcpyAsync(compact_builds, h->g.compact_builds, sizeof(int64_t) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
+  if (cta_ns) CU(cudaMemcpyAsync(cta_ns, h->g.cta_ns, sizeof(int64_t) * h->p.R * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return CGPE_OK;
 }
 

@@ -85,6 +85,7 @@ struct DevState {
   double *pH;         // [R]
   double *time;       // [R]
   long long *md_counter, *md_steps, *samples_done, *rebuilds;   // [R]
+  long long *cta_ns;           // [R][2][2] start / end (GPU global timer, ns) of the CTA(s) of each replica in the last fused sampling launch
   long long *compact_builds;   // [R] times the compact Debye-Hueckel partner lists were written (cgpe_engine_info)
   long long *trials, *accepted;                                  // [R][n_rx]
   int *f_valid;       // [R]
@@ -258,6 +259,12 @@ __device__ __forceinline__ float dihedral_term(const DevParams &p, V3 p1, V3 p2,
   const V3 g3 = s12 * g1 + (-1.0f - s32) * g4;
   *f1 = (-dedphi) * g1; *f2 = (-dedphi) * g2; *f3 = (-dedphi) * g3; *f4 = (-dedphi) * g4;
   return p.dih_k * (1.0f - cos_arg);
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 // warp / block reductions

@@ -1312,6 +1312,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
   bind_smem(p, &c.s);
   init_ctx(c);
   Thr<ITEMS> t;
+  if (c.tid == 0) { g.cta_ns[c.r * 4] = (long long)global_timer_ns(); g.cta_ns[c.r * 4 + 2] = 0; g.cta_ns[c.r * 4 + 3] = 0; }
   bool f_valid = g.f_valid[c.r] != 0, lists_valid = false;
   unsigned long long counter = (unsigned long long)g.md_counter[c.r];
   unsigned long long sample_ctr = (unsigned long long)g.samples_done[c.r];
@@ -1374,6 +1375,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
     g.md_counter[c.r] = (long long)counter;
     g.md_steps[c.r] += steps;
     g.samples_done[c.r] = (long long)sample_ctr;
+    g.cta_ns[c.r * 4 + 1] = (long long)global_timer_ns();
     g.time[c.r] = t0 + (double)steps * p.dt_d;
     g.f_valid[c.r] = f_valid ? 1 : 0;
     for (int m = 0; m < p.n_rx; ++m) {

@@ -1084,6 +1084,7 @@ k_duo_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ D
   Ctx c{p, g, d};
   prologue(c);
   Thr t;
+  if (c.tid == 0) g.cta_ns[c.r * 4 + c.rank * 2] = (long long)global_timer_ns();
   bool f_valid = g.f_valid[c.r] != 0, lists_valid = false;
   unsigned long long counter = (unsigned long long)g.md_counter[c.r];
   unsigned long long sample_ctr = (unsigned long long)g.samples_done[c.r];
@@ -1146,6 +1147,7 @@ k_duo_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ D
     cl_sync();   // flips mirrored into the peer; the leader is done with its copy of the positions
   }
   store_state(c, t, true);
+  if (c.tid == 0) g.cta_ns[c.r * 4 + c.rank * 2 + 1] = (long long)global_timer_ns();
   if (c.rank == 0 && c.tid == 0) {
     g.md_counter[c.r] = (long long)counter;
     g.md_steps[c.r] += steps;

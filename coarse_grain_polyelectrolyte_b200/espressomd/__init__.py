@@ -372,6 +372,10 @@ class _Analysis:
 class System:
     """espressomd.System(box_l=[L, L, L]) (P.py:372) with an optional replica axis."""
 
+    # Class that drives the C-ABI handle; None = the product's `Engine` over libcgpe.so (CUDA; raises without a
+    # device).  A test may point it at another implementation of the same ABI to run the driver code elsewhere.
+    engine_factory = None
+
     def __init__(self, box_l, n_replicas=1, replica_offset=0, device=-1, skin=0.0):
         global _current_system
         box_l = np.atleast_1d(np.asarray(box_l, dtype=np.float64))
@@ -606,7 +610,9 @@ class System:
 
     def _ensure_engine(self):
         if self._engine is None:
-            from ..engine import Engine
+            Engine = type(self).engine_factory
+            if Engine is None:
+                from ..engine import Engine
             if self._n_part == 0:
                 raise RuntimeError("the system holds no particles")
             cfg = self._build_config()

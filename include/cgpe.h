@@ -237,8 +237,10 @@ CGPE_API int cgpe_list_stats(cgpe_handle *h, double *out);
 CGPE_API int cgpe_set_engine(cgpe_handle *h, int32_t engine);
 /* engine: the one in force (0, 1 as above, 2 = global-memory engine); compact_builds [R] (may be NULL): how
  * often each replica wrote the compact Debye-Hueckel partner lists its MD force loop walks -- lets a test
- * assert that it measured the code path the benchmark times. */
-CGPE_API int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds);
+ * assert that it measured the code path the benchmark times.  cta_ns [R][2][2] (may be NULL): start and end,
+ * in ns of the GPU's global timer, of the CTA(s) that ran each replica in the last fused sampling launch
+ * (second CTA zero for the one-CTA engines): the load-balance picture of a launch. */
+CGPE_API int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds, int64_t *cta_ns);
 /* device time of the last hot-path call in milliseconds (CUDA events on the handle's stream) and
  * the number of kernels it launched */
 CGPE_API int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches);

@@ -1086,7 +1086,8 @@ int orc_list_stats(orc_handle *h, double *out) {
 
 /* the oracle has one engine; the entry points exist so that the same binding drives both libraries */
 int orc_set_engine(orc_handle *h, int32_t engine) { (void)h; (void)engine; return CGPE_OK; }
-int orc_engine_info(orc_handle *h, int32_t *engine, int64_t *compact_builds) {
+int orc_engine_info(orc_handle *h, int32_t *engine, int64_t *compact_builds, int64_t *cta_ns) {
+  if (cta_ns) for (int r = 0; r < 4 * h->cfg.n_replicas; ++r) cta_ns[r] = 0;
   if (engine) *engine = -1;
   if (compact_builds) for (int r = 0; r < h->cfg.n_replicas; ++r) compact_builds[r] = 0;
   return CGPE_OK;

@@ -312,3 +312,45 @@ def test_oracle_invariances_hold_for_random_states(oracle_mod):
         np.testing.assert_allclose(o2.forces_f64(), f0[perm], rtol=1e-12, atol=1e-12)
 
     check()
+
+
+@pytest.mark.parametrize("explicit_ions", [False, True])
+def test_local_delta_e_equals_the_whole_system_energy_difference(oracle_mod, explicit_ions):
+    """ESPResSo's reaction engine accepts on E_pot(whole system, after) - E_pot(whole system, before)
+    (E.py:70-71,94-95 call it).  The oracle -- like the CUDA kernels -- evaluates only the terms a
+    trial changes.  One trial per call, the full potential energy around it: for every accepted trial the
+    difference of the totals equals the trace's delta_e; a rejected trial leaves the total unchanged."""
+    w = make_workload(50, pH=[8.18], c_salt=1e-2, explicit_ions=explicit_ions)   # C1's chain and salt
+    state = random_state(w, seed=23, jitter=0.03)
+    if explicit_ions:   # random_state flips site types without touching the H+ pool: keep the workload's own protonation
+        xyzq, vel, types = state
+        n = w.cfg.n_chains * w.cfg.n_beads
+        types[:, :n] = w.type[:n]; xyzq[:, :n, 3] = w.q[:n]
+        types[:, n:] = w.type[n:]; xyzq[:, n:, 3] = w.q[n:]
+        state = (xyzq, vel, types)
+    o = load(oracle_mod.OracleEngine(w.cfg), w, state)
+    o.md_run(50)                                       # off the synthetic start
+
+    def e_pot():
+        e = o.energy()[0]
+        return e[2] + e[3] + e[4]                      # coulomb + bonded + non_bonded (an inserted H+ brings kinetic energy)
+
+    n_acc = n_rej = n_excl = 0
+    worst = 0.0
+    for k in range(400):
+        rx = k % 2
+        before = e_pot()
+        tr = o.mc_run(rx, 1, trace=True)[0, 0]
+        after = e_pot()
+        if tr["accepted"]:
+            n_acc += 1
+            err = abs((after - before) - tr["delta_e"]) / max(abs(tr["delta_e"]), 1.0)
+            worst = max(worst, err)
+        else:
+            n_rej += 1
+            n_excl += int(tr["excluded"])
+            assert after == before
+    assert n_acc > 40 and n_rej > 40, (n_acc, n_rej)
+    assert worst < 2e-6, worst                          # delta_e travels through the trace as float32
+    if explicit_ions:
+        assert n_excl >= 0

@@ -133,6 +133,89 @@ __global__ void __launch_bounds__(1024, 1) k_pair_packed(float *out, int iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// MUFU throughput: 8 independent chains of rsqrt / ex2 per thread
+__global__ void __launch_bounds__(1024, 1) k_mufu(float *out, int iters, int which) {
+  float x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = 1.0f + threadIdx.x * 1e-3f + k;
+  if (which == 0) {
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x[k]));
+    }
+  } else {
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[k]));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// pair body with exp(-kappa r) as a degree-6 polynomial on the FMA pipe (one MUFU per pair: the rsqrt)
+#define EXP_POLY(t) fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(0.00083676545f, (t), -0.0076200562f), (t), 0.041187618f), (t), -0.16649818f), (t), 0.49997148f), (t), -0.99999815f), (t), 1.0f)
+__global__ void __launch_bounds__(1024, 1) k_pair_scalar_poly(float *out, int iters, float kappa, float rc2) {
+  __shared__ float4 pos[1024];
+  pos[threadIdx.x] = make_float4(threadIdx.x * 0.37f, threadIdx.x * 0.11f, threadIdx.x * 0.23f, 1.0f);
+  __syncthreads();
+  const float4 pi = pos[threadIdx.x];
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll 8
+    for (int j = 0; j < 64; ++j) {
+      const float4 pj = pos[(threadIdx.x + 1 + j + i) & 1023];
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+      const float rinv = rsqrtf(r2), t = kappa * (r2 * rinv);
+      const float e = EXP_POLY(t);
+      const float w = e * ((rinv * pj.w) * (rinv * rinv));
+      float fr = fmaf(w, t, w);
+      fr = r2 < rc2 ? fr : 0.f;
+      fx = fmaf(fr, dx, fx); fy = fmaf(fr, dy, fy); fz = fmaf(fr, dz, fz);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = fx + fy + fz;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_pair_packed_poly(float *out, int iters, float kappa, float rc2) {
+  __shared__ float4 pos[1024];
+  pos[threadIdx.x] = make_float4(threadIdx.x * 0.37f, threadIdx.x * 0.11f, threadIdx.x * 0.23f, 1.0f);
+  __syncthreads();
+  const float4 pi = pos[threadIdx.x];
+  const unsigned long long pix = pack2(pi.x, pi.x), piy = pack2(pi.y, pi.y), piz = pack2(pi.z, pi.z);
+  const unsigned long long k2 = pack2(kappa, kappa);
+  const unsigned long long c6 = pack2(0.00083676545f, 0.00083676545f), c5 = pack2(-0.0076200562f, -0.0076200562f),
+                           c4 = pack2(0.041187618f, 0.041187618f), c3 = pack2(-0.16649818f, -0.16649818f),
+                           c2 = pack2(0.49997148f, 0.49997148f), c1 = pack2(-0.99999815f, -0.99999815f), c0 = pack2(1.0f, 1.0f);
+  unsigned long long fx = 0ull, fy = 0ull, fz = 0ull;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll 4
+    for (int j = 0; j < 64; j += 2) {
+      const float4 pa = pos[(threadIdx.x + 1 + j + i) & 1023], pb = pos[(threadIdx.x + 2 + j + i) & 1023];
+      const unsigned long long dx = sub2(pix, pack2(pa.x, pb.x)), dy = sub2(piy, pack2(pa.y, pb.y)), dz = sub2(piz, pack2(pa.z, pb.z));
+      const unsigned long long r2 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
+      float r2a, r2b;
+      unpack2(r2, r2a, r2b);
+      const unsigned long long rinv = pack2(rsqrtf(r2a), rsqrtf(r2b));
+      const unsigned long long t = mul2(k2, mul2(r2, rinv));
+      const unsigned long long e = fma2(fma2(fma2(fma2(fma2(fma2(c6, t, c5), t, c4), t, c3), t, c2), t, c1), t, c0);
+      const unsigned long long w = mul2(e, mul2(mul2(rinv, pack2(pa.w, pb.w)), mul2(rinv, rinv)));
+      unsigned long long fr = fma2(w, t, w);
+      float fa, fb;
+      unpack2(fr, fa, fb);
+      fa = r2a < rc2 ? fa : 0.f; fb = r2b < rc2 ? fb : 0.f;
+      fr = pack2(fa, fb);
+      fx = fma2(fr, dx, fx); fy = fma2(fr, dy, fy); fz = fma2(fr, dz, fz);
+    }
+  }
+  float a, b, s = 0.f;
+  unpack2(fx, a, b); s += a + b; unpack2(fy, a, b); s += a + b; unpack2(fz, a, b); s += a + b;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // placement of 2-CTA clusters: every CTA records its SM, cluster rank and the time it started
 __global__ void __launch_bounds__(512, 2) k_where(int *smid, long long *t0, int spin) {
   extern __shared__ unsigned char dummy[];
@@ -191,6 +274,20 @@ int main() {
     const double pairs = (double)it * 64 * 1024;
     printf("pair body: scalar %.3f ms -> %.2f pairs/clk/SM | packed %.3f ms -> %.2f pairs/clk/SM\n", ms1,
            pairs / (ms1 * 1e-3 * clk_khz * 1e3), ms2, pairs / (ms2 * 1e-3 * clk_khz * 1e3));
+  }
+  {
+    const int it = 400;
+    const double ms3 = time_kernel([&] { k_pair_scalar_poly<<<sms, 1024>>>(out, it, 0.0362f, 700.f); }, 5);
+    const double ms4 = time_kernel([&] { k_pair_packed_poly<<<sms, 1024>>>(out, it, 0.0362f, 700.f); }, 5);
+    const double ms5 = time_kernel([&] { k_pair_packed_poly<<<sms, 512>>>(out, it, 0.0362f, 700.f); }, 5);
+    const double pairs = (double)it * 64 * 1024;
+    printf("pair body, exp as a degree-6 polynomial: scalar %.3f ms -> %.2f pairs/clk/SM | packed %.3f ms -> %.2f pairs/clk/SM | packed, 512 threads %.3f ms -> %.2f pairs/clk/SM\n",
+           ms3, pairs / (ms3 * 1e-3 * clk_khz * 1e3), ms4, pairs / (ms4 * 1e-3 * clk_khz * 1e3), ms5, 0.5 * pairs / (ms5 * 1e-3 * clk_khz * 1e3));
+    for (int which = 0; which < 2; ++which) {
+      const int itm = 4000;
+      const double ms = time_kernel([&] { k_mufu<<<sms, 1024>>>(out, itm, which); }, 5);
+      printf("MUFU.%s: %.3f ms -> %.2f op/clk/SM\n", which == 0 ? "RSQ" : "EX2", ms, (double)itm * 8 * 1024 / (ms * 1e-3 * clk_khz * 1e3));
+    }
   }
   // cluster placement
   for (size_t smem : {(size_t)60 * 1024, (size_t)100 * 1024}) {
