@@ -204,12 +204,19 @@ int require_engine(cgpe_handle *h) {
   return CGPE_OK;
 }
 
-// The cluster engine serves implicit-ion replicas without spectator particles; chosen unless the caller
-// (cgpe_set_engine) or CGPE_ENGINE=solo says otherwise.
+// The cluster engine serves implicit-ion replicas without spectator particles.  Its step carries two cluster barriers
+// and the mirrored position stores (~1.2 us), which it earns back only where the step is long and the launch leaves SMs
+// idle (measured, tools/prof_engines.py -> profiles/r2_engines.txt: 128 x N=1000 at 1 mM 1.03x, 64 x N=1000 1.05x; but
+// 0.78x at 20 mM, 0.65x at N=100, 0.81x with 256 replicas).  So the library picks it for long Debye-Hueckel rows (list
+// radius >= 0.6 of the ideal-chain extent), chains of >= 512 beads and no more replicas than SMs; cgpe_set_engine or
+// CGPE_ENGINE=solo|duo overrides.
 bool use_duo(const cgpe_handle *h) {
   if (h->wide || !h->duo.ok || h->launch.items == 0) return false;
   if (h->engine_pref >= 0) return h->engine_pref == 1;
-  return h->p.P >= 64;
+  const DevParams &p = h->p;
+  const double b = h->cfg.bond_r0 > 0.0 ? h->cfg.bond_r0 : 1.0;
+  const bool long_rows = p.use_dh && h->cfg.r_cut + p.skin >= 0.6 * b * std::sqrt((double)p.N);
+  return p.P >= 512 && p.R <= h->n_sm && long_rows;
 }
 
 // shape of the cluster engine for the current state (after choose_capacities)

@@ -598,7 +598,8 @@ class System:
         if ang_t is not None:
             kw.update(use_angle=1, angle_k=ang_t.bend, angle_phi0=ang_t.phi0)
         if dih_t is not None:
-            kw.update(use_dihedral=1, dihedral_k=dih_t.bend, dihedral_mult=dih_t.mult, dihedral_phase=dih_t.phase)
+            kw.update(use_dihedral=1, dihedral_k=dih_t.bend, dihedral_mult=dih_t.mult, dihedral_phase=dih_t.phase,
+                      dihedral_sin_min=getattr(dih_t, "sin_min", 0.0))
         if self._dh is not None:
             kw.update(use_dh=1, dh_prefactor=self._dh.prefactor,
                       kappa=float(np.atleast_1d(self._dh.kappa)[0]), r_cut=float(np.max(self._dh.r_cut)))

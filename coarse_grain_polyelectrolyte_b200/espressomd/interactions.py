@@ -48,8 +48,11 @@ class Dihedral(BondedInteraction):
     """Dihedral(bend=, mult=, phase=): U = bend [1 - cos(mult phi - phase)] (M.py:49-53)."""
     n_partners = 3
 
-    def __init__(self, bend, mult, phase):
+    def __init__(self, bend, mult, phase, sin_min=0.0):
+        """sin_min is not an ESPResSo argument: the engine evaluates the torsion gradient with sin(bond angle) >= sin_min
+        (cgpe.h, dihedral_sin_min).  0 = the library's default safeguard (0.02), negative = ESPResSo's own guard only
+        (the term is dropped for |b1 x b2| <= 1e-4, nothing else)."""
         super().__init__()
         if int(mult) != mult or not 0 <= int(mult) <= 12:
             raise ValueError("mult must be an integer in [0, 12]")
-        self.bend, self.mult, self.phase = float(bend), int(mult), float(phase)
+        self.bend, self.mult, self.phase, self.sin_min = float(bend), int(mult), float(phase), float(sin_min)

@@ -230,12 +230,13 @@ def config_c4(charge=-20.0, n_ph=64, **kw):
                     nanoparticle=dict(charge=charge, sigma=34.8, epsilon=0.3), **kw)
 
 
-def config_c3_shard(rank=0, world=8, n_ph=128, n_mon=1000, **kw):
+def config_c3_shard(rank=0, world=8, n_ph=128, n_mon=1000, all_salts=False, **kw):
     """C3: 128 pH x 8 ionic strengths of N=1000 chains; rank `rank` of `world` holds the
     contiguous block of replicas [rank*R/world, (rank+1)*R/world) of the pH-major grid, i.e. with
     world=8 one ionic strength per GPU.  With world < 8 the grid shrinks to `world` ionic
-    strengths (weak scaling: 128 replicas per GPU)."""
-    salts = C3_SALT_MOLAR[:world] if world <= 8 else C3_SALT_MOLAR
+    strengths (weak scaling: 128 replicas per GPU) unless all_salts (strong scaling: the whole
+    grid of 8 x n_ph replicas whatever the number of GPUs)."""
+    salts = C3_SALT_MOLAR if (all_salts or world > 8) else C3_SALT_MOLAR[:world]
     n_total = n_ph * len(salts)
     per = n_total // world
     lo = rank * per

@@ -37,12 +37,16 @@ class EnsembleDynamics(Model):
         # for N <= 100 but pinches strands of long chains (min_dist then never recovers and the loop, which is
         # unbounded in the reference, cannot end).  A contracting steepest descent (gamma k_bond = 0.1, steps of
         # at most 0.02) first takes the bond strain out gently; it is a no-op for an already relaxed chain.
-        k_bond = self.k_bond_reduced_units.magnitude
-        stretch = abs(1.5 - self.bond_length_reduced_units.magnitude)
-        n_relax = int(min(60000, max(500, 30 * self.n_mon * stretch)))
-        system.integrator.set_steepest_descent(f_max=0, gamma=0.1 / k_bond, max_displacement=0.02)
-        system.integrator.run(n_relax)
-        system.integrator.set_vv()
+        # "REFERENCE_FAITHFUL": True skips it and lifts the bound on the rounds below: the reference's loop as written.
+        if not self.reference_faithful:
+            k_bond = self.k_bond_reduced_units.magnitude
+            stretch = abs(1.5 - self.bond_length_reduced_units.magnitude)
+            n_relax = int(min(60000, max(500, 30 * self.n_mon * stretch)))
+            system.integrator.set_steepest_descent(f_max=0, gamma=0.1 / k_bond, max_displacement=0.02)
+            system.integrator.run(n_relax)
+            system.integrator.set_vv()
+        else:
+            max_rounds = None
         wca_cap = 5
         system.force_cap = wca_cap
         act_min_dist = np.min(system.analysis.min_dist())
@@ -56,7 +60,7 @@ class EnsembleDynamics(Model):
             wca_cap += 1
             system.force_cap = wca_cap
             rounds += 1
-            if rounds >= max_rounds:
+            if max_rounds is not None and rounds >= max_rounds:
                 # The reference loops here without bound.  Long chains start with bonds of 1.5 against
                 # r_0 ~ 1.1 (M.py:119): while they contract, a pair of strands can end up pinched below
                 # the threshold at T = 0 for good.  The temperature ramp below anneals such contacts.

@@ -8,10 +8,14 @@ here configure the B200 engine.
 Beyond the reference:
   * `replicas=dict(pH=[...], c_salt=[...])` batches R independent copies of the system over the
     pH x ionic-strength grid (the reference loops over pH values serially, notebook cell 4);
-  * "Simulation configuration" may carry "ION_MODEL": "implicit" (default here: the chain alone,
-    small ions only through the Debye-Hueckel screening, as BASELINE.json's north star describes)
-    or "explicit" (the reference's B+/Na+/Cl- particles with H+ insertion / deletion,
-    M.py:173-198);
+  * "Simulation configuration" may carry "ION_MODEL": "explicit" (default, as in the reference: B+/Na+/Cl-
+    particles, a reaction inserts or deletes an H+, M.py:173-198) or "implicit" (the chain alone, small ions only
+    through the Debye-Hueckel screening: the move BASELINE.json's north star describes and bench.py times; N_B is
+    then reported through the identity N_B = N_N + N_N2).  The choice is recorded in `ion_model`;
+  * "Simulation configuration" may carry "REFERENCE_FAITHFUL": True -- the two places where the defaults depart from
+    what the reference computes are switched back: the torsion gradient keeps ESPResSo's guard only (no sin-theta
+    floor, cgpe.h dihedral_sin_min < 0) and the warm-up is the reference's own loop (E.py:39-48: no contracting
+    pre-relaxation, no bound on the rounds).  "DIHEDRAL_SIN_MIN": x sets the floor alone;
   * an optional section "Nanoparticle properties": {"charge": q, "sigma": [Angstrom], "epsilon": [kJ/mol],
     "clearance": 1.3} places one fixed charged sphere (type "NP", `fix=[True]*3`) beside the first chain
     (BASELINE config 4; the reference only announces it, README.md:14-15).  Implicit ions only.
@@ -44,9 +48,14 @@ class Model(Properties):
             table["NP"] = {"index": max(v["index"] for v in table.values()) + 1, "charge": self.nanoparticle["charge"],
                            "sigma": self.nanoparticle.get("sigma", 34.8), "epsilon": self.nanoparticle.get("epsilon", 0.3)}
         super().__init__(input_dict, n_replicas=len(self.replica_pH), replica_offset=replica_offset, device=device)
-        self.ion_model = input_dict["Simulation configuration"].get("ION_MODEL", "implicit")
+        sim = input_dict["Simulation configuration"]
+        self.ion_model = sim.get("ION_MODEL", "explicit")
         if self.ion_model not in ("implicit", "explicit"):
             raise ValueError("ION_MODEL must be 'implicit' or 'explicit'")
+        if self.nanoparticle is not None and "ION_MODEL" not in sim:
+            self.ion_model = "implicit"     # the only model the fixed sphere is served with (see _add_nanoparticle)
+        self.reference_faithful = bool(sim.get("REFERENCE_FAITHFUL", False))
+        self.dihedral_sin_min = float(sim.get("DIHEDRAL_SIN_MIN", -1.0 if self.reference_faithful else 0.0))
         self._bonded_interactions()
         self._create_polymer()
         self._add_nanoparticle()
@@ -78,7 +87,8 @@ class Model(Properties):
             self.bend = AngleHarmonic(bend=self.k_bending_reduced_units.magnitude, phi0=np.pi * (2.0 / 3.0))
             self.system.bonded_inter.add(self.bend)
         if self.USE_DIHEDRAL_POT:
-            self.dihedral = Dihedral(bend=self.k_dihedral_reduced_units.magnitude, mult=3, phase=np.pi)
+            self.dihedral = Dihedral(bend=self.k_dihedral_reduced_units.magnitude, mult=3, phase=np.pi,
+                                     sin_min=self.dihedral_sin_min)
             self.system.bonded_inter.add(self.dihedral)
 
     # -- M.py:114-170 --------------------------------------------------------------------------------
@@ -170,7 +180,11 @@ class Model(Properties):
         made = []
         for prot, deprot, pK in (("NH", "N", self.pK), ("NH2", "N2", self.pK2)):
             excl = combination_rule_sigma("Berthelot", self.sigma_reduced_units[deprot], self.sigma_reduced_units["B"])
-            rx = reaction_methods.ConstantpHEnsemble(kT=kT, exclusion_range=excl, seed=77, constant_pH=4.0)
+            # the reference starts every reaction object at pH 4 (M.py:215,232); with a replica axis the replicas' own
+            # pH values are in force from the start, so perform_sampling without equilibrate_pH cannot sample pH 4 by accident
+            pH0 = self.replica_pH if np.all(np.isfinite(self.replica_pH)) else 4.0
+            rx = reaction_methods.ConstantpHEnsemble(kT=kT, exclusion_range=excl, seed=77,
+                                                     constant_pH=pH0 if np.size(pH0) > 1 else float(np.atleast_1d(pH0)[0]))
             rx.add_reaction(gamma=10 ** (-pK), reactant_types=[tp[prot]], product_types=[tp[deprot], tp["B"]],
                             default_charges={tp[prot]: q[prot], tp[deprot]: q[deprot], tp["B"]: q["B"]})
             rx.set_non_interacting_type(type=len(tp))

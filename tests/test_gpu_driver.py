@@ -15,7 +15,8 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def small_run_parameters(n_mon=40, n_blocks=2, block=40):
-    return workloads.example_parameters(n_mon, **{"Montecarlo properties": {"N_BLOCKS": n_blocks, "DESIRED_BLOCK_SIZE": block, "PROB_REACTION": 0.7}})
+    return workloads.example_parameters(n_mon, **{"Montecarlo properties": {"N_BLOCKS": n_blocks, "DESIRED_BLOCK_SIZE": block, "PROB_REACTION": 0.7},
+                                                   "Simulation configuration": {"ION_MODEL": "implicit"}})
 
 
 @pytest.mark.parametrize("name", ["chain_n52.npz", "chain_n100.npz", "chain_n100_np.npz"])
@@ -43,14 +44,19 @@ def test_golden_trial_log_through_the_c_abi():
     rec = e.mc_run(0, g["trace"].shape[1], trace=True)
     gold = g["trace"]
     same = rec["accepted"] == gold["accepted"]
-    if not same.all():       # a decision may differ only on a near-tie; everything after it then differs too
-        k = int(np.argmin(same[0]))
+    n = gold.shape[1]
+    k = n if same.all() else int(np.argmin(same[0]))
+    if k < n:
+        # A decision may differ from the FP64 golden log only on a near-tie |u - bf| <= 1e-4 bf; the two Markov chains
+        # legitimately part there, so the log is compared up to that trial (never skipped: a tie in the first tenth of
+        # the log would mean the fixture needs regenerating and fails here).
         assert abs(gold["u"][0, k] - gold["bf"][0, k]) <= 1e-4 * gold["bf"][0, k], (k, gold[0, k], rec[0, k])
-        pytest.skip(f"near-tie at trial {k}: the two Markov chains legitimately part there")
-    for f in ("particle", "direction", "u"):
-        np.testing.assert_array_equal(rec[f], gold[f])
-    np.testing.assert_allclose(rec["delta_e"], gold["delta_e"], rtol=2e-5, atol=1e-5)
-    np.testing.assert_array_equal(e.get_state()[2], g["final_type"])
+        assert k > n // 10, f"near-tie already at trial {k} of {n}: regenerate tests/golden/trials_n100.npz"
+    for f in ("particle", "direction", "u", "accepted"):
+        np.testing.assert_array_equal(rec[f][:, :k], gold[f][:, :k])
+    np.testing.assert_allclose(rec["delta_e"][:, :k], gold["delta_e"][:, :k], rtol=2e-5, atol=1e-5)
+    if k == n:
+        np.testing.assert_array_equal(e.get_state()[2], g["final_type"])
 
 
 def test_ensemble_dynamics_drop_in_single_replica():

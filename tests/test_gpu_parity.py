@@ -19,20 +19,22 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5
 
 
-@pytest.fixture(scope="module", params=["auto", "solo"])
+@pytest.fixture(scope="module", params=["duo", "solo"])
 def Engine(request):
-    """Every test of this module runs twice: with the engine the library chooses (the cluster engine of
-    two CTAs per replica wherever it applies, i.e. what bench.py times) and pinned to the one-CTA-per-replica
-    engine."""
+    """Every test of this module runs twice: on the cluster engine (two CTAs per replica) wherever it can serve the
+    configuration -- otherwise on whatever the library chooses, e.g. the global-memory engine -- and pinned to the
+    one-CTA-per-replica engine.  bench.py's headline (128 x N=1000 at 1 mM) runs on the cluster engine."""
     from coarse_grain_polyelectrolyte_b200.engine import Engine as E
-    if request.param == "auto":
-        return E
+    from coarse_grain_polyelectrolyte_b200._abi import CgpeError
 
-    def make(cfg):
-        e = E(cfg)
-        e.set_engine("solo")
-        return e
-    return make
+    class Pinned(E):
+        def set_state(self, *a, **k):
+            super().set_state(*a, **k)
+            try:
+                self.set_engine(request.param)
+            except CgpeError:            # the cluster engine does not serve this configuration (ions, spectators, size)
+                self.set_engine("auto")
+    return Pinned
 
 
 def _pair(Engine, oracle_mod, w, state):
@@ -610,11 +612,14 @@ def test_compact_partner_lists_follow_charges_and_rebuilds(Engine, oracle_mod):
     written out at the start of a burst and after every list build.  Interleave bursts long enough to rebuild
     the lists with reaction blocks that change which sites are charged, at weak screening (long rows) and with
     explicit ions (every ion is a partner), and compare with the oracle step by step."""
-    for n_mon, ions, c_salt in ((150, False, 1e-3), (60, True, 2e-2)):
+    # n_mon = 300: 100 chargeable particles -- the one-CTA engine keeps the bit walk below 97 (chain_engine.cu,
+    # build_dh_compact); the cluster engine always takes the compact lists
+    for n_mon, ions, c_salt in ((300, False, 1e-3), (60, True, 2e-2)):
         w = make_workload(n_mon, pH=[6.0, 8.5, 11.0], c_salt=c_salt, explicit_ions=ions)
         state = _ion_state(w, seed=9) if ions else random_state(w, seed=9, jitter=0.02)
         g, o = _pair(Engine, oracle_mod, w, state)
         o.set_list_mode(True, 0.8)
+        builds0 = g.engine_info()["compact_builds"].copy()
         for burst in range(4):
             g.md_run(60); o.md_run(60)
             xg = g.get_state()[0]
@@ -627,6 +632,88 @@ def test_compact_partner_lists_follow_charges_and_rebuilds(Engine, oracle_mod):
             fo = o.forces_f64()
             assert np.abs(g.md_forces() - fo).max() < REL_TOL * np.abs(fo).max()
         assert g.counters()["list_rebuilds"].min() >= 4
+        # the compact partner lists were really the path taken: written at every burst start, list build and md_forces call
+        assert (g.engine_info()["compact_builds"] - builds0).min() >= 8, g.engine_info()
+
+
+@pytest.mark.parametrize("wrap", [False, True])
+def test_md_of_the_headline_regime_matches_oracle_across_list_rebuilds(Engine, oracle_mod, wrap):
+    """The code bench.py times: N = 1000 at 1 mM (r_cut 27.6: Debye-Hueckel rows of ~150 partners per site, compact
+    partner lists), pH 2 / 4 / 8, i.e. every site charged down to a third of them.  Bursts of 40 steps from a hot
+    start so that at least one Verlet-list rebuild falls inside; the oracle is re-seated on the device positions
+    between bursts (the gap of a 40-step burst is what is compared).  wrap = True shrinks the box until the chain
+    reaches through the periodic boundary, which switches the kernels to their minimum-image instantiation."""
+    w = make_workload(1000, pH=[2.0, 4.0, 8.0], c_salt=1e-3)
+    if wrap:
+        ext = float(np.ptp(w.xyzq[:, :3], axis=0).max())
+        w.cfg.box_l = max(2.0 * (float(w.r_cut.max()) + 0.8) + 1.0, 0.9 * ext)   # r_cut + skin <= L/2, extent + list radius > L
+    state = random_state(w, seed=41, jitter=0.02, vel_sigma=3.0)     # hot: a particle leaves its skin/2 sphere within ~40 steps
+    xyzq, vel, types = state
+    tix, ru = w.ru.type_index, w.ru
+    for r, frac in enumerate((1.0, 1.0, 0.35)):                     # protonation as the titration has it at 1 mM
+        sites = np.isin(types[r], [tix["N"], tix["NH"]])
+        ends = np.isin(types[r], [tix["N2"], tix["NH2"]])
+        rng = np.random.default_rng(100 + r)
+        prot = rng.random(types.shape[1]) < frac
+        types[r, sites] = np.where(prot[sites], tix["NH"], tix["N"])
+        types[r, ends] = np.where(prot[ends], tix["NH2"], tix["N2"])
+    q_of = np.zeros(len(tix) + 1, np.float32)
+    for name, t in tix.items():
+        q_of[t] = ru.charge[name]
+    xyzq[..., 3] = q_of[types]
+    g, o = _pair(Engine, oracle_mod, w, (xyzq, vel, types))
+    o.set_list_mode(True, 0.8)
+    ulp = float(np.spacing(np.float32(np.abs(xyzq[..., :3]).max())))
+    builds0 = g.engine_info()["compact_builds"].copy()
+    for burst in range(3):
+        g.md_run(40); o.md_run(40)
+        xg, vg, _ = g.get_state()
+        xo, vo, _ = o.state_f64()
+        dx, dv = np.abs(xg[..., :3] - xo).max(), np.abs(vg[..., :3] - vo).max()
+        assert dx < 400 * ulp and dv < 0.4, f"burst {burst}: dx={dx:.3g} ({dx / ulp:.0f} ulp) dv={dv:.3g}"
+        o.set_positions_f64(np.asarray(xg[..., :3], np.float64))
+        fo = o.forces_f64()
+        assert np.abs(g.md_forces() - fo).max() < REL_TOL * np.abs(fo).max()
+    reb = g.counters()["list_rebuilds"]
+    assert reb.min() >= 4, reb                    # one build per md_run / md_forces call + at least one inside a burst
+    assert (g.engine_info()["compact_builds"] - builds0).min() >= reb.min(), g.engine_info()
+    stats = g.list_stats()
+    assert stats[0, 2] / 334 > 100                 # the fully charged replica really has the long rows (directed entries per site)
+    np.testing.assert_array_equal(g.counters()["md_steps"], o.counters()["md_steps"])
+
+
+@pytest.mark.parametrize("explicit_ions", [False, True])
+def test_config_c1_as_specified(Engine, oracle_mod, explicit_ions):
+    """BASELINE configs[0] exactly as SURVEY 8d states it: N = 50 (16 N + 1 N2 sites), Debye-Hueckel at 10 mM
+    (kappa 0.11452, r_cut 8.732), pH = pK1 = 8.18, one replica, implicit ions and the reference's explicit ions."""
+    w = make_workload(50, pH=[8.18], c_salt=1e-2, explicit_ions=explicit_ions)
+    assert w.n_sites == (16, 1) and abs(w.kappa[0] - 0.11452) < 2e-5 and abs(w.r_cut[0] - 8.732) < 2e-3
+    state = _ion_state(w, seed=5) if explicit_ions else random_state(w, seed=5, jitter=0.03)
+    g, o = _pair(Engine, oracle_mod, w, state)
+    eg, eo = g.energy(), o.energy()
+    scale = np.maximum(np.abs(eo), 1e-3 * np.abs(eo).max(axis=1, keepdims=True))
+    assert np.max(np.abs(eg - eo) / scale) < REL_TOL, (eg, eo)
+    fo = o.forces_f64()
+    for fg in (g.forces(), g.md_forces()):
+        assert np.abs(fg - fo).max() < REL_TOL * np.abs(fo).max()
+    for rx, n in ((0, 2000), (1, 400)):
+        tg = g.mc_run(rx, n, trace=True)
+        to, ties = o.mc_run_follow(rx, tg, tie_tol=1e-4)
+        assert ties <= 2
+        for col in ("particle", "direction", "accepted", "u"):
+            np.testing.assert_array_equal(tg[col], to[col])
+        tried = to["particle"] >= 0
+        err = np.abs(tg["delta_e"][tried] - to["delta_e"][tried]) / np.maximum(np.abs(to["delta_e"][tried]), 1.0)
+        assert err.max() < REL_TOL
+        assert 0.05 < tg["accepted"].mean() < 0.95          # pH = pK: both directions are taken
+    np.testing.assert_array_equal(g.get_state()[2], o.get_state()[2])
+    g.md_run(20); o.md_run(20)
+    assert _ion_dx(g.get_state()[0][..., :3], o.state_f64()[0], w) < 2e-4
+    sp = g.sample_params(6, md_steps_per_burst=20, use_md=True, mc_blocks=((0, 81), (1, 6)), p_burst1=0.7, p_burst2=0.05)
+    og, _ = g.sample_loop(sp)
+    oo, _ = o.sample_loop(sp)
+    np.testing.assert_array_equal(og[..., :3], oo[..., :3])
+    np.testing.assert_allclose(og[..., 3:5], oo[..., 3:5], rtol=2e-3)
 
 
 @pytest.mark.parametrize("charge,n_mon", [(-20.0, 100), (20.0, 100), (-20.0, 1000)])

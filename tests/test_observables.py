@@ -157,7 +157,8 @@ def test_registry_mirrors_the_reference_interface():
 def test_accumulators_follow_integrator_run():
     from coarse_grain_polyelectrolyte_b200 import workloads
     from modules.EnsembleDynamics import EnsembleDynamics
-    params = workloads.example_parameters(40, **{"Montecarlo properties": {"N_BLOCKS": 1, "DESIRED_BLOCK_SIZE": 14}})
+    params = workloads.example_parameters(40, **{"Montecarlo properties": {"N_BLOCKS": 1, "DESIRED_BLOCK_SIZE": 14},
+                                                 "Simulation configuration": {"ION_MODEL": "implicit"}})
     ens = EnsembleDynamics(params, replicas=dict(pH=[7.0, 9.0], c_salt=[2e-2, 2e-2]))
     s = ens.system
     reg = Observables()

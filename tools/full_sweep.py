@@ -15,6 +15,7 @@ def sem(x, nb=16):
 
 def run(label, n_mon, pH, c_salt):
     params = workloads.example_parameters(n_mon, c_salt=c_salt)
+    params["Simulation configuration"]["ION_MODEL"] = "implicit"
     t0 = time.time()
     ens = EnsembleDynamics(params, replicas=dict(pH=pH, c_salt=[c_salt] * len(pH)))
     t1 = time.time()
