@@ -643,11 +643,11 @@ def test_md_of_the_headline_regime_matches_oracle_across_list_rebuilds(Engine, o
     start so that at least one Verlet-list rebuild falls inside; the oracle is re-seated on the device positions
     between bursts (the gap of a 40-step burst is what is compared).  wrap = True shrinks the box until the chain
     reaches through the periodic boundary, which switches the kernels to their minimum-image instantiation."""
-    w = make_workload(1000, pH=[2.0, 4.0, 8.0], c_salt=1e-3)
+    w = make_workload(1000, pH=[2.0, 4.0, 8.0], c_salt=1e-3, skin=0.2)   # thin skin: a rebuild every ~40 thermal steps
     if wrap:
         ext = float(np.ptp(w.xyzq[:, :3], axis=0).max())
-        w.cfg.box_l = max(2.0 * (float(w.r_cut.max()) + 0.8) + 1.0, 0.9 * ext)   # r_cut + skin <= L/2, extent + list radius > L
-    state = random_state(w, seed=41, jitter=0.02, vel_sigma=3.0)     # hot: a particle leaves its skin/2 sphere within ~40 steps
+        w.cfg.box_l = max(2.0 * (float(w.r_cut.max()) + 0.2) + 1.0, 0.9 * ext)   # r_cut + skin <= L/2, extent + list radius > L
+    state = random_state(w, seed=41, jitter=0.02)
     xyzq, vel, types = state
     tix, ru = w.ru.type_index, w.ru
     for r, frac in enumerate((1.0, 1.0, 0.35)):                     # protonation as the titration has it at 1 mM
@@ -662,21 +662,23 @@ def test_md_of_the_headline_regime_matches_oracle_across_list_rebuilds(Engine, o
         q_of[t] = ru.charge[name]
     xyzq[..., 3] = q_of[types]
     g, o = _pair(Engine, oracle_mod, w, (xyzq, vel, types))
-    o.set_list_mode(True, 0.8)
+    o.set_list_mode(True, 0.2)
     ulp = float(np.spacing(np.float32(np.abs(xyzq[..., :3]).max())))
     builds0 = g.engine_info()["compact_builds"].copy()
+    in_burst = np.zeros(w.R, np.int64)
     for burst in range(3):
-        g.md_run(40); o.md_run(40)
+        r0 = g.counters()["list_rebuilds"].copy()
+        g.md_run(60); o.md_run(60)
+        in_burst += g.counters()["list_rebuilds"] - r0 - 1          # one build opens the call, the rest fell inside the burst
         xg, vg, _ = g.get_state()
         xo, vo, _ = o.state_f64()
         dx, dv = np.abs(xg[..., :3] - xo).max(), np.abs(vg[..., :3] - vo).max()
-        assert dx < 400 * ulp and dv < 0.4, f"burst {burst}: dx={dx:.3g} ({dx / ulp:.0f} ulp) dv={dv:.3g}"
+        assert dx < 600 * ulp and dv < 0.5, f"burst {burst}: dx={dx:.3g} ({dx / ulp:.0f} ulp) dv={dv:.3g}"
         o.set_positions_f64(np.asarray(xg[..., :3], np.float64))
         fo = o.forces_f64()
         assert np.abs(g.md_forces() - fo).max() < REL_TOL * np.abs(fo).max()
-    reb = g.counters()["list_rebuilds"]
-    assert reb.min() >= 4, reb                    # one build per md_run / md_forces call + at least one inside a burst
-    assert (g.engine_info()["compact_builds"] - builds0).min() >= reb.min(), g.engine_info()
+    assert in_burst.min() >= 1, in_burst                           # every replica rebuilt its lists inside a burst
+    assert (g.engine_info()["compact_builds"] - builds0).min() >= 6 + in_burst.min(), g.engine_info()
     stats = g.list_stats()
     assert stats[0, 2] / 334 > 100                 # the fully charged replica really has the long rows (directed entries per site)
     np.testing.assert_array_equal(g.counters()["md_steps"], o.counters()["md_steps"])
@@ -705,7 +707,8 @@ def test_config_c1_as_specified(Engine, oracle_mod, explicit_ions):
         tried = to["particle"] >= 0
         err = np.abs(tg["delta_e"][tried] - to["delta_e"][tried]) / np.maximum(np.abs(to["delta_e"][tried]), 1.0)
         assert err.max() < REL_TOL
-        assert 0.05 < tg["accepted"].mean() < 0.95          # pH = pK: both directions are taken
+        if rx == 0:
+            assert 0.05 < tg["accepted"].mean() < 0.95      # pH = pK1: both directions are taken
     np.testing.assert_array_equal(g.get_state()[2], o.get_state()[2])
     g.md_run(20); o.md_run(20)
     assert _ion_dx(g.get_state()[0][..., :3], o.state_f64()[0], w) < 2e-4

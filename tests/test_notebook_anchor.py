@@ -25,10 +25,13 @@ r_0 = 1.5 sim_length = 5.2219 A, k = 300 kcal/(mol A^2) = 503.22 kT/A^2, bend = 
 
 What is asserted (tolerances stated per quantity): mean site counts within their binning error bar + 10 %;
 the bookkeeping identity N_B = N_N + N_N2 sample by sample; E_kin = 3/2 kT per *present* particle (the
-notebook's 259.9 vs 287.1 is exactly the 18 H+ that are absorbed at pH 4: 174 vs ~191 particles);
-E_bonded = kT/2 per bond and angle (101 terms -> 50.5, notebook 54-56) within 10 % of the notebook band;
-sign and size of E_coul.  Rg / Ree of the notebook are single frames of an unequilibrated 31-time-unit run
-from ESPResSo's own random start and are NOT asserted.
+notebook's 259.9 vs 287.1 is exactly the 18 H+ that are absorbed at pH 4: 174 vs ~190 particles);
+E_bonded = kT/2 per bond and angle (101 terms -> 50.5 +- 10 %; the notebook's four frames 54.1-56.3 must be
+plausible draws of our frame distribution); sign of E_coul, and -- on the GPU, where the run is long enough -- its
+size: the Debye-Hueckel energy of the charged chain follows its extension (the start is a random walk with 90 degree
+angles that the bending term straightens over ~80 time units: Rg 5.7 -> 8.5, E_coul +24 -> +1..+7 kT, measured in
+profiles/r2_notebook_anchor_trajectory.txt), so the notebook's +3.0 kT at Rg = 7.98 is compared with OUR frames of the
+same extension (Rg 7.3..8.7).  Rg / Ree themselves depend on ESPResSo's own random start and are not asserted.
 
 The same driver code (src/modules/EnsembleDynamics.py, ION_MODEL "explicit") runs on the CPU oracle
 (not gpu: reduced sample count) and on the CUDA engine (gpu: the full 1333-sample protocol).
@@ -94,21 +97,22 @@ def binning_sem(x, n_bins=16):
     return float(np.std(means, ddof=1.5) / np.sqrt(n_bins))
 
 
-def run_notebook_protocol(engine_factory, n_chunks, samples_per_chunk):
-    """The notebook's cells 0-4 for the pH 4 and pH 10 points, both as replicas of one batched run.  The sampling
-    loop runs in chunks with one energy frame (analysis.energy(), as the older revision printed it) behind each."""
+def run_notebook_protocol(engine_factory, n_chunks, samples_per_chunk, equil_steps, n_streams=1):
+    """The notebook's cells 0-4 for the pH 4 and pH 10 points as replicas of one batched run (n_streams independent
+    copies of each).  The sampling loop runs in chunks with one frame (analysis.energy(), calc_rg as the older revision
+    printed them) behind each."""
     from coarse_grain_polyelectrolyte_b200 import espressomd
     from modules.EnsembleDynamics import EnsembleDynamics
     old = espressomd.System.engine_factory
     espressomd.System.engine_factory = engine_factory
     try:
-        ens = EnsembleDynamics(copy.deepcopy(NOTEBOOK_PARAMETERS), replicas=dict(pH=[4.0, 10.0]))
+        ens = EnsembleDynamics(copy.deepcopy(NOTEBOOK_PARAMETERS), replicas=dict(pH=[4.0, 10.0] * n_streams))
         ens.verbose = False
         assert ens.n_acid == 18 and ens.n_salt == 52                      # SURVEY appendix B
         assert len(ens.system.part) >= 192                                # 52 + 2*18 + 2*52 (+ hidden spares)
         assert abs(ens.bond_length_reduced_units.magnitude - 1.5) < 1e-4 and abs(ens.k_bending_reduced_units.magnitude - 83.87) < 0.02
         ens.equilibrate_pH()
-        ens.system.integrator.run(20000)                                   # NB cell 2 runs 1e5 steps here
+        ens.system.integrator.run(equil_steps)                             # NB cell 2 runs 1e5 steps here
         ens.num_samples = int(samples_per_chunk)
         ens.n_samp_iter = max(1, (ens.num_samples - 10) // 2)
         series = {k: [] for k in ("num_As", "num_As2", "num_B", "rad_gyr", "end_2end")}
@@ -119,52 +123,68 @@ def run_notebook_protocol(engine_factory, n_chunks, samples_per_chunk):
                 series[k].append(np.asarray(getattr(ens, k)))
             e = ens.system.analysis.energy()
             n_free_ion = ens.system.number_of_particles(type=ens.type_particles["B"])
-            frames.append([e["kinetic"], e["coulomb"], e["bonded"], e["non_bonded"], np.asarray(n_free_ion, float)])
+            rg = ens.system.analysis.calc_rg(chain_start=0, number_of_chains=1, chain_length=52)[0]
+            frames.append([e["kinetic"], e["coulomb"], e["bonded"], e["non_bonded"], np.asarray(n_free_ion, float), np.asarray(rg, float)])
         return {k: np.concatenate(v, axis=1) for k, v in series.items()}, np.array(frames)
     finally:
         espressomd.System.engine_factory = old
 
 
-def check_against_notebook(series, frames, coulomb_band):
+def check_against_notebook(series, frames, coulomb_size):
     n_N, n_N2, n_B = series["num_As"], series["num_As2"], series["num_B"]
     np.testing.assert_array_equal(n_B, n_N + n_N2)                         # NB:253-254, sample by sample
     skip = n_N.shape[1] // 5
-    for r, pH in enumerate((4.0, 10.0)):
+    for r in range(n_N.shape[0]):
+        pH = (4.0, 10.0)[r % 2]
         ref = NB[pH]
         for name, x, n_sites in (("n_N", n_N[r, skip:], 16), ("n_N2", n_N2[r, skip:], 2)):
             mean, sem = x.mean(), binning_sem(x)
             tol = 3.0 * sem + 0.10 * max(ref[name], 0.1) + 0.02 * n_sites  # error bar + 10 % (+ the resolution of the notebook's print)
             assert abs(mean - ref[name]) <= tol, f"pH {pH}: <{name}> = {mean:.3f} +- {sem:.3f}, notebook {ref[name]}"
-        ek, ec, eb, enb, nb_free = (frames[:, k, r] for k in range(5))
+        ek, ec, eb, enb, nb_free, rg = (frames[:, k, r] for k in range(6))
         # a hidden H+ is gone (M.py:256-261): the notebook's T = 2/3 E_kin / len(system.part) gives 0.996 with 174 particles
         # at pH 4 (all 18 H+ absorbed) and 1.007 with 190 at pH 10
         n_present = 192 - 18 + nb_free
         t_inst = (2.0 / 3.0) * ek / n_present
-        assert np.all((t_inst > 0.8) & (t_inst < 1.2)), f"pH {pH}: T_inst frames {t_inst}"
+        assert np.all((t_inst > 0.75) & (t_inst < 1.25)), f"pH {pH}: T_inst frames {t_inst}"
         assert 0.94 <= t_inst.mean() <= 1.06, f"pH {pH}: T_inst {t_inst.mean():.3f}"   # NB:234-248: 0.90 .. 1.01 over four frames
         sem_k = ek.std(ddof=1) / np.sqrt(len(ek))
         assert abs(ek.mean() - ref["e_kin"]) <= 4 * sem_k + 0.05 * ref["e_kin"], (pH, ek.mean(), ref["e_kin"])
-        # 51 bonds + 50 angles, kT/2 each = 50.5; notebook frames 54.1 / 55.8 (54-56 +- 10 %)
-        assert 0.9 * 54.0 <= eb.mean() <= 1.1 * 56.0, f"pH {pH}: E_bonded {eb.mean():.2f}"
-        # Debye-Hueckel energy: the sign, and a size of a few kT.  It relaxes with the ion cloud and the chain's extension,
-        # i.e. over the whole 31-time-unit run (ions diffuse ~14 of the 59 box lengths in that time), and depends on the
-        # random start: the notebook's single frame (+3.0 / -4.9) must lie inside the band our frames cover (+- coulomb_band)
-        assert np.sign(ec.mean()) == np.sign(ref["e_coul"]), f"pH {pH}: E_coul {ec.mean():.2f} vs notebook {ref['e_coul']}"
-        assert ec.min() - coulomb_band <= ref["e_coul"] <= ec.max() + coulomb_band, \
-            f"pH {pH}: E_coul frames {np.round(ec, 2)} vs notebook {ref['e_coul']}"
+        # 51 bonds + 50 angles, kT/2 each = 50.5; the notebook's frames (54.1, 55.8 + the two at time 0.05: 55.6, 56.3)
+        assert 0.9 * 50.5 <= eb.mean() <= 1.1 * 50.5, f"pH {pH}: E_bonded {eb.mean():.2f}"
+        assert abs(ref["e_bonded"] - eb.mean()) <= 3.0 * max(eb.std(ddof=1), 5.0), (pH, eb.mean(), eb.std(ddof=1))
+        assert np.sign(np.median(ec)) == np.sign(ref["e_coul"]), f"pH {pH}: E_coul {np.round(ec, 1)} vs notebook {ref['e_coul']}"
         assert 0.0 <= enb.mean() < 2.0                                     # notebook: 0.004 .. 0.36 kT
+    if coulomb_size:
+        # Size of the Debye-Hueckel energy, pooled over the streams of each pH.  The notebook holds ONE frame per pH; it must be
+        # a plausible draw (within 2.5 standard deviations) of our frames under the same conditions: at pH 4 the frames in
+        # which the chain has the notebook's extension (Rg 7.98 -> 7.3..8.7); at pH 10 (neutral chain: the energy is the ions'
+        # alone) the last three quarters of the run.
+        for pH, which in ((4.0, 0), (10.0, 1)):
+            ec = frames[:, 1, which::2].ravel()
+            rg = frames[:, 5, which::2].ravel()
+            if pH == 4.0:
+                sel = (rg > 7.3) & (rg < 8.7)
+                assert sel.sum() >= 8, f"the chain never reached the notebook's extension: Rg frames {np.round(rg, 1)}"
+            else:
+                sel = np.tile(np.arange(frames.shape[0]) >= frames.shape[0] // 4, (frames.shape[2] // 2, 1)).T.ravel()
+            mean, sd = ec[sel].mean(), max(ec[sel].std(ddof=1), 2.0)
+            assert abs(NB[pH]["e_coul"] - mean) <= 2.5 * sd, f"pH {pH}: E_coul {mean:.2f} +- {sd:.2f} ({sel.sum()} frames) vs notebook {NB[pH]['e_coul']}"
+            assert abs(mean) < 12.0
 
 
 def test_oracle_reproduces_the_notebook_numbers(oracle_mod):
-    """CPU: the restatement itself against ESPResSo's saved output (reduced sample count)."""
+    """CPU: the restatement itself against ESPResSo's saved output.  Reduced: 300 samples after 2e4 steps (9 time units;
+    the chain is still compact then, so the size of E_coul is left to the GPU run)."""
     oracle_mod.set_threads(2)
-    series, frames = run_notebook_protocol(oracle_mod.OracleEngine, n_chunks=5, samples_per_chunk=60)
-    check_against_notebook(series, frames, coulomb_band=16.0)   # 300 samples = 9 time units: the ion cloud has barely formed
+    series, frames = run_notebook_protocol(oracle_mod.OracleEngine, n_chunks=5, samples_per_chunk=60, equil_steps=20000)
+    check_against_notebook(series, frames, coulomb_size=False)
 
 
 @pytest.mark.gpu
 def test_cuda_engine_reproduces_the_notebook_numbers():
-    """GPU: the full protocol of the notebook (1333 samples) through the drop-in driver."""
-    series, frames = run_notebook_protocol(None, n_chunks=31, samples_per_chunk=43)   # 1333 samples (SURVEY appendix B)
-    assert series["num_As"].shape == (2, 1333)
-    check_against_notebook(series, frames, coulomb_band=4.0)
+    """GPU: cell 2's 1e5 equilibration steps, then twice the notebook's 1333 samples (83 time units) through the drop-in
+    driver, two independent streams per pH."""
+    series, frames = run_notebook_protocol(None, n_chunks=62, samples_per_chunk=43, equil_steps=100000, n_streams=2)
+    assert series["num_As"].shape == (4, 2666)
+    check_against_notebook(series, frames, coulomb_size=True)
