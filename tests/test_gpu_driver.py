@@ -169,3 +169,44 @@ def test_nanoparticle_through_the_driver():
         assert np.all(np.isfinite(ens.rad_gyr))
         alpha[q] = ens.num_As[:, ens.num_As.shape[1] // 4:].mean() / ens.n_nh
     assert alpha[-20.0] < alpha[20.0] - 0.03, alpha
+
+
+def test_ph_replica_exchange_between_launches():
+    """North star: optional pH replica exchange.  Labels move between launches of the fused loop (sharding.sample_with_exchange
+    -> cgpe_set_replica_params), configurations never do.  Per ionic strength the labels stay a permutation of the pH set,
+    and alpha(pH) collected by label agrees with the run without exchange within error bars."""
+    from coarse_grain_polyelectrolyte_b200 import sharding
+    from coarse_grain_polyelectrolyte_b200.engine import Engine
+    pH, cs = sharding.replica_grid(np.linspace(7.0, 10.0, 8), [2e-2, 1e-1])
+    n_rounds, per = 40, 25
+
+    def run(exchange):
+        w = workloads.Workload(workloads.example_parameters(60, c_salt=float(cs[0])), pH=pH, c_salt=cs)
+        e = Engine(w.cfg)
+        w.init_engine(e)
+        e.md_run(2000)
+        mk = lambda: w.sample_params(e, per)    # noqa: E731
+        if exchange:
+            return w, sharding.sample_with_exchange(e, mk, pH, cs, sum(w.n_sites), n_rounds)
+        obs, _ = e.sample_loop(w.sample_params(e, n_rounds * per))
+        return w, (obs, np.repeat(pH[:, None], n_rounds, axis=1), (0, 0))
+
+    w, (obs_x, labels, (acc, prop)) = run(True)
+    _, (obs_0, _, _) = run(False)
+    assert prop == n_rounds // 2 * 2 * 4 + n_rounds // 2 * 2 * 3 and 0 < acc < prop
+    for rnd in range(n_rounds):
+        for salt in np.unique(cs):
+            assert sorted(labels[cs == salt, rnd]) == sorted(pH[cs == salt])
+    assert (labels != pH[:, None]).any()
+    lab = np.repeat(labels, per, axis=1)
+    skip = obs_x.shape[1] // 5
+    for salt in np.unique(cs):
+        for p in np.unique(pH):
+            m = (lab[:, skip:] == p) & (cs == salt)[:, None]
+            a_x = obs_x[:, skip:, 0][m] / w.n_sites[0]
+            r = int(np.flatnonzero((pH == p) & (cs == salt))[0])
+            a_0 = obs_0[r, skip:, 0] / w.n_sites[0]
+            nb = 10
+            sem = lambda x: np.std(x[: len(x) // nb * nb].reshape(nb, -1).mean(1), ddof=1) / np.sqrt(nb)   # noqa: E731
+            err = np.sqrt(sem(a_x) ** 2 + sem(a_0) ** 2) + 2e-3
+            assert abs(a_x.mean() - a_0.mean()) < 4 * err, (salt, p, a_x.mean(), a_0.mean(), err)
