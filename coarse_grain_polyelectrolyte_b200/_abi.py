@@ -15,6 +15,8 @@ MAX_REACTIONS = 4
 MAX_MC_BLOCKS = 4
 N_OBS = 6
 N_ENERGY = 5
+FRAME_COLS = 8
+FRAME_BONDS, FRAME_DIHEDRALS = 1, 2
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STATE, ERR_NUMERIC = 0, -1, -2, -3, -4, -5, -6
 BOND_NONE, BOND_HARMONIC, BOND_FENE = 0, 1, 2
@@ -114,6 +116,9 @@ SIGNATURES = {
     "list_stats": (C.c_int, [_p, _p]),
     "set_engine": (C.c_int, [_p, C.c_int32]),
     "engine_info": (C.c_int, [_p, _i32p, _p, _p]),
+    "frames_begin": (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32]),
+    "frames_fetch": (C.c_int, [_p, _p, _p, _p, _p]),
+    "frames_end": (C.c_int, [_p]),
     "last_call_ms": (C.c_int, [_p, _fp, _i32p]),
 }
 
@@ -362,6 +367,26 @@ class EngineBase:
         self._check(self._b.engine_info(self._h, C.byref(eng), _ptr(cb), _ptr(ns)), "engine_info")
         return {"engine": ("solo", "duo", "wide")[eng.value] if 0 <= eng.value <= 2 else "oracle", "compact_builds": cb,
                 "cta_ns": ns}
+
+    # -- on-device accumulation (Observables.py:54-76) ---------------------------------------------
+    def frames_begin(self, every, flags=0, capacity=1024):
+        self._check(self._b.frames_begin(self._h, int(every), int(flags), int(capacity)), "frames_begin")
+        self._frames = (int(flags), int(capacity))
+
+    def frames_fetch(self):
+        """(frames [R][n][8], bonds [R][n][N-1] or None, dihedrals [R][n][N-3] or None) per replica as lists of arrays:
+        the frames recorded since the last fetch (COM x,y,z, COM velocity x,y,z, Rg, Ree)."""
+        flags, cap = self._frames
+        fr = np.empty((self.R, cap, FRAME_COLS), np.float64)
+        bo = np.empty((self.R, cap, self.n_beads - 1), np.float32) if flags & FRAME_BONDS and self.n_beads > 1 else None
+        di = np.empty((self.R, cap, self.n_beads - 3), np.float32) if flags & FRAME_DIHEDRALS and self.n_beads > 3 else None
+        n = np.zeros(self.R, np.int32)
+        self._check(self._b.frames_fetch(self._h, _ptr(fr), _ptr(bo), _ptr(di), _ptr(n)), "frames_fetch")
+        cut = lambda a: None if a is None else [a[r, :n[r]] for r in range(self.R)]   # noqa: E731
+        return cut(fr), cut(bo), cut(di)
+
+    def frames_end(self):
+        self._check(self._b.frames_end(self._h), "frames_end")
 
     def last_call_ms(self):
         ms, n = C.c_float(), C.c_int32()

@@ -33,6 +33,7 @@ struct cgpe_handle {
   int engine_pref = -1;        // cgpe_set_engine: -1 = choose, 0 = one CTA per replica, 1 = cluster engine
   int n_sm = 0;
   size_t dhc_need_solo = 0;
+  void *frame_alloc[3] = {nullptr, nullptr, nullptr};   // DevState::frames, frame_bonds, frame_dih
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
   int device;
@@ -177,6 +178,15 @@ int choose_capacities(cgpe_handle *h) {
 }
 
 int check_device_errors(cgpe_handle *h) {
+  if (h->p.frame_every > 0) {
+    std::vector<int> nf(h->p.R);
+    CU(cudaMemcpyAsync(nf.data(), h->g.n_frames, sizeof(int) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < h->p.R; ++r)
+      if (nf[r] > h->p.frame_cap)
+        return fail(h, CGPE_ERR_CAPACITY, "frame recorder overflow: replica %d recorded %d frames, capacity %d (cgpe_frames_begin); fetch more often",
+                    r, nf[r], h->p.frame_cap);
+  }
   std::vector<int> err(h->p.R);
   CU(cudaMemcpyAsync(err.data(), h->g.err, sizeof(int) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -212,6 +222,7 @@ int require_engine(cgpe_handle *h) {
 // CGPE_ENGINE=solo|duo overrides.
 bool use_duo(const cgpe_handle *h) {
   if (h->wide || !h->duo.ok || h->launch.items == 0) return false;
+  if (h->p.frame_every > 0) return false;   // the frame recorder lives in the one-CTA engine
   if (h->engine_pref >= 0) return h->engine_pref == 1;
   const DevParams &p = h->p;
   const double b = h->cfg.bond_r0 > 0.0 ? h->cfg.bond_r0 : 1.0;
@@ -484,7 +495,8 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   ALLOC(g.ion_cnt, (size_t)p.R * 2);
   ALLOC(g.kappa, p.R); ALLOC(g.rcut, p.R); ALLOC(g.kT, p.R); ALLOC(g.gamma, p.R); ALLOC(g.pH, p.R);
   ALLOC(g.time, p.R); ALLOC(g.md_counter, p.R); ALLOC(g.md_steps, p.R); ALLOC(g.samples_done, p.R);
-  ALLOC(g.rebuilds, p.R); ALLOC(g.compact_builds, p.R); ALLOC(g.cta_ns, (size_t)p.R * 4); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
+  ALLOC(g.rebuilds, p.R); ALLOC(g.compact_builds, p.R); ALLOC(g.cta_ns, (size_t)p.R * 4);
+  ALLOC(g.n_frames, p.R); ALLOC(g.frame_phase, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
   ALLOC(g.f_valid, p.R); ALLOC(g.err, p.R);
   ALLOC(h->d_tmp_d, (size_t)p.R * 8); ALLOC(h->d_tmp_i, (size_t)p.R * 3); ALLOC(h->d_tmp_f4, RP);
 #undef ALLOC
@@ -510,6 +522,7 @@ void cgpe_destroy(cgpe_handle *h) {
   for (void *ptr : h->allocs) cudaFree(ptr);
   for (void *ptr : h->wide_allocs) cudaFree(ptr);
   if (h->dhc_alloc) cudaFree(h->dhc_alloc);
+  for (void *ptr : h->frame_alloc) if (ptr) cudaFree(ptr);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_qdist) cudaFree(h->d_qdist);
   if (h->d_trace) cudaFree(h->d_trace);
@@ -596,6 +609,7 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
   h->g.dhc = nullptr; p.dhc_cap = 0; p.dhc_stride = 0;
   h->duo.ok = 0;
   if (h->launch.items == 0) {
+    if (p.frame_every > 0) return fail(h, CGPE_ERR_UNSUPPORTED, "the frame recorder is served by the shared-memory engine (<= 2048 particles per replica)");
     if (p.P > p.NC && p.n_ions == 0)
       return fail(h, CGPE_ERR_UNSUPPORTED, "spectator particles (slots without an ion reaction) are served by the shared-memory engine only (<= 2048 particles per replica)");
     int rc_w = ensure_wide(h, chg_packed);
@@ -1035,6 +1049,63 @@ int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds, i
   if (compact_builds) CU(cudaMemcpyAsync(compact_builds, h->g.compact_builds, sizeof(int64_t) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
   if (cta_ns) CU(cudaMemcpyAsync(cta_ns, h->g.cta_ns, sizeof(int64_t) * h->p.R * 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return CGPE_OK;
+}
+
+int cgpe_frames_end(cgpe_handle *h) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  DeviceGuard guard(h->device);
+  CU(cudaStreamSynchronize(h->stream));
+  h->p.frame_every = 0; h->p.frame_flags = 0; h->p.frame_cap = 0;
+  for (void *&ptr : h->frame_alloc) { if (ptr) cudaFree(ptr); ptr = nullptr; }
+  h->g.frames = nullptr; h->g.frame_bonds = nullptr; h->g.frame_dih = nullptr;
+  return CGPE_OK;
+}
+
+int cgpe_frames_begin(cgpe_handle *h, int32_t every, int32_t flags, int32_t capacity) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (every < 1 || capacity < 1 || (flags & ~(CGPE_FRAME_BONDS | CGPE_FRAME_DIHEDRALS)))
+    return fail(h, CGPE_ERR_INVALID, "frames: every and capacity must be positive, flags a combination of CGPE_FRAME_BONDS, CGPE_FRAME_DIHEDRALS");
+  if (h->have_state && (h->wide || h->launch.items == 0))
+    return fail(h, CGPE_ERR_UNSUPPORTED, "the frame recorder is served by the shared-memory engine (<= 2048 particles per replica)");
+  const bool keep_phase = h->p.frame_every == every;   // re-arming with the same interval (a larger capacity): the step phase carries over
+  int rc = cgpe_frames_end(h);
+  if (rc) return rc;
+  DeviceGuard guard(h->device);
+  const DevParams &p = h->p;
+  const size_t n = (size_t)p.R * capacity;
+  CU(cudaMalloc(&h->frame_alloc[0], sizeof(double) * n * CGPE_FRAME_COLS));
+  h->g.frames = static_cast<double *>(h->frame_alloc[0]);
+  if ((flags & CGPE_FRAME_BONDS) && p.N > 1) {
+    CU(cudaMalloc(&h->frame_alloc[1], sizeof(float) * n * (p.N - 1)));
+    h->g.frame_bonds = static_cast<float *>(h->frame_alloc[1]);
+  }
+  if ((flags & CGPE_FRAME_DIHEDRALS) && p.N > 3) {
+    CU(cudaMalloc(&h->frame_alloc[2], sizeof(float) * n * (p.N - 3)));
+    h->g.frame_dih = static_cast<float *>(h->frame_alloc[2]);
+  }
+  CU(cudaMemsetAsync(h->g.n_frames, 0, sizeof(int) * p.R, h->stream));
+  if (!keep_phase) CU(cudaMemsetAsync(h->g.frame_phase, 0, sizeof(int) * p.R, h->stream));
+  h->p.frame_every = every; h->p.frame_flags = flags; h->p.frame_cap = capacity;
+  return CGPE_OK;
+}
+
+int cgpe_frames_fetch(cgpe_handle *h, double *frames, float *bonds, float *dihedrals, int32_t *n_frames) {
+  if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
+  if (h->p.frame_every <= 0) return fail(h, CGPE_ERR_STATE, "cgpe_frames_begin has not been called");
+  DeviceGuard guard(h->device);
+  const DevParams &p = h->p;
+  const size_t n = (size_t)p.R * p.frame_cap;
+  if (frames) CU(cudaMemcpyAsync(frames, h->g.frames, sizeof(double) * n * CGPE_FRAME_COLS, cudaMemcpyDeviceToHost, h->stream));
+  if (bonds && h->g.frame_bonds) CU(cudaMemcpyAsync(bonds, h->g.frame_bonds, sizeof(float) * n * (p.N - 1), cudaMemcpyDeviceToHost, h->stream));
+  if (dihedrals && h->g.frame_dih) CU(cudaMemcpyAsync(dihedrals, h->g.frame_dih, sizeof(float) * n * (p.N - 3), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<int> nf(p.R);
+  CU(cudaMemcpyAsync(nf.data(), h->g.n_frames, sizeof(int) * p.R, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  int rc = check_device_errors(h);
+  if (rc) return rc;
+  if (n_frames) for (int r = 0; r < p.R; ++r) n_frames[r] = nf[r];
+  CU(cudaMemsetAsync(h->g.n_frames, 0, sizeof(int) * p.R, h->stream));
   return CGPE_OK;
 }
 

@@ -62,6 +62,9 @@ struct DevParams {
   float grid_w_min;             // smallest cell edge of the all-particle grid (explicit ions: the largest exclusion range)
   float force_cap;              // 0 = off
   uint32_t fixed_mask;          // bit t: particles of type t never move (cgpe_config::fixed_type_mask)
+  int frame_every;              // > 0: every frame_every MD steps a frame of chain-0 observables is recorded (cgpe_frames_begin)
+  int frame_flags;              // CGPE_FRAME_BONDS | CGPE_FRAME_DIHEDRALS
+  int frame_cap;                // frames per replica the buffers hold
   SmemOff off;
   DevReaction rx[kMaxRx];
 };
@@ -85,6 +88,11 @@ struct DevState {
   double *pH;         // [R]
   double *time;       // [R]
   long long *md_counter, *md_steps, *samples_done, *rebuilds;   // [R]
+  double *frames;              // [R][frame_cap][CGPE_FRAME_COLS] COM position, COM velocity, Rg, Ree of chain 0
+  float *frame_bonds;          // [R][frame_cap][N-1] bond lengths (CGPE_FRAME_BONDS)
+  float *frame_dih;            // [R][frame_cap][N-3] torsion angles in (-pi, pi] (CGPE_FRAME_DIHEDRALS)
+  int *n_frames;               // [R] frames recorded since the last fetch (may exceed frame_cap: the excess was dropped)
+  int *frame_phase;            // [R] MD steps since the last frame
   long long *cta_ns;           // [R][2][2] start / end (GPU global timer, ns) of the CTA(s) of each replica in the last fused sampling launch
   long long *compact_builds;   // [R] times the compact Debye-Hueckel partner lists were written (cgpe_engine_info)
   long long *trials, *accepted;                                  // [R][n_rx]

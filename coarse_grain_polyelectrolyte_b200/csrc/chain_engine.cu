@@ -93,6 +93,7 @@ struct Ctx {
   int dh_g0, dh_ci0;  // this thread's first (sub-thread, row) work item of the Debye-Hueckel phase
   int err;            // thread-local error bits, merged at exit
   long long rebuilds; // uniform
+  int frame_since, frame_n;   // frame recorder: MD steps since the last frame, frames recorded so far (uniform)
 };
 
 template <bool WRAP>
@@ -233,6 +234,7 @@ __device__ void store_state(Ctx &c, Thr<ITEMS> &t, bool store_forces) {
   }
   if (c.err) atomicOr(&c.g.err[c.r], c.err);
   if (c.tid == 0 && c.rebuilds) c.g.rebuilds[c.r] += c.rebuilds;
+  if (c.tid == 0 && p.frame_every > 0) { c.g.frame_phase[c.r] = c.frame_since; c.g.n_frames[c.r] = c.frame_n; }
 }
 
 // ---- Verlet lists ------------------------------------------------------------------------------
@@ -672,6 +674,11 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
     for (int k = 0; k < ITEMS; ++k)
 #pragma unroll
       for (int a = 0; a < 3; ++a) t.v[k][a] = fmaf(p.half_dt, t.f[k][a], t.v[k][a]);
+    if (p.frame_every > 0 && ++c.frame_since >= p.frame_every) {   // uniform: every thread counts the same steps
+      c.frame_since = 0;
+      record_frame(c, t, c.frame_n);
+      c.frame_n += 1;
+    }
   }
   c.compact = false;   // trial moves change the charges
 }
@@ -1073,6 +1080,71 @@ __device__ void chain_observables(Ctx &c, Thr<ITEMS> &t, double *rg, double *ree
   *ree = sqrt(ex * ex + ey * ey + ez * ez);
 }
 
+// ---- frame recorder (cgpe_frames_begin): the observables of Observables.py:54-76 without leaving the launch ----
+// COM position / velocity, Rg, Ree of chain 0 [+ bond lengths, torsion angles] appended to the replica's frame buffers.
+// All threads; positions in shared memory current; contains block barriers.
+template <int ITEMS>
+__device__ void record_frame(Ctx &c, Thr<ITEMS> &t, int k) {
+  const DevParams &p = c.p;
+  const float4 p0 = c.s.pos[0];
+  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < ITEMS; ++q) {
+    const int i = c.tid + q * c.nt;
+    if (i < p.N) {
+      const double dx = (double)t.x[q][0] - p0.x, dy = (double)t.x[q][1] - p0.y, dz = (double)t.x[q][2] - p0.z;
+      a[0] += dx; a[1] += dy; a[2] += dz; a[3] += dx * dx + dy * dy + dz * dz;
+      b[0] += t.v[q][0]; b[1] += t.v[q][1]; b[2] += t.v[q][2];
+    }
+  }
+  double out[8];
+  for (int pass = 0; pass < 2; ++pass) {
+    double *v = pass == 0 ? a : b;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = warp_sum(v[q]);
+    __syncthreads();
+    if (c.lane == 0)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c.s.red[c.warp * 4 + q] = v[q];
+    __syncthreads();
+    double s[4] = {0, 0, 0, 0};
+    for (int w = 0; w < (c.nt + 31) / 32; ++w)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += c.s.red[w * 4 + q];
+    const double inv = 1.0 / p.N;
+    if (pass == 0) {
+      out[0] = p0.x + s[0] * inv; out[1] = p0.y + s[1] * inv; out[2] = p0.z + s[2] * inv;
+      const double var = s[3] * inv - (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) * inv * inv;
+      out[6] = sqrt(var > 0.0 ? var : 0.0);
+    } else {
+      out[3] = s[0] * inv; out[4] = s[1] * inv; out[5] = s[2] * inv;
+    }
+  }
+  if (k >= p.frame_cap) return;   // dropped; n_frames keeps counting and the host reports it
+  const size_t slot = (size_t)c.r * p.frame_cap + k;
+  if (c.tid == 0) {
+    const float4 pe = c.s.pos[p.N - 1];
+    const double ex = (double)pe.x - p0.x, ey = (double)pe.y - p0.y, ez = (double)pe.z - p0.z;
+    out[7] = sqrt(ex * ex + ey * ey + ez * ez);
+    double *f = c.g.frames + slot * CGPE_FRAME_COLS;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = out[q];
+  }
+  if ((p.frame_flags & CGPE_FRAME_BONDS) && c.g.frame_bonds)
+    for (int i = c.tid + 1; i < p.N; i += c.nt) {
+      const V3 d = xyz(c.s.pos[i]) - xyz(c.s.pos[i - 1]);
+      c.g.frame_bonds[slot * (p.N - 1) + i - 1] = sqrtf(dot(d, d));
+    }
+  if ((p.frame_flags & CGPE_FRAME_DIHEDRALS) && c.g.frame_dih && p.N >= 4)
+    for (int i = c.tid; i < p.N - 3; i += c.nt) {   // torsion of (i, i+1, i+2, i+3), the convention of observables.BondDihedrals
+      const V3 b1 = xyz(c.s.pos[i + 1]) - xyz(c.s.pos[i]), b2 = xyz(c.s.pos[i + 2]) - xyz(c.s.pos[i + 1]),
+               b3 = xyz(c.s.pos[i + 3]) - xyz(c.s.pos[i + 2]);
+      const V3 n1 = cross(b1, b2), n2 = cross(b2, b3);
+      const V3 m = cross(n1, rsqrtf(dot(b2, b2)) * b2);
+      c.g.frame_dih[slot * (p.N - 3) + i] = atan2f(dot(m, n2), dot(n1, n2));
+    }
+}
+
 __device__ void init_ctx(Ctx &c) {
   const DevParams &p = c.p;
   c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
@@ -1091,6 +1163,8 @@ __device__ void init_ctx(Ctx &c) {
   c.noise_pref = sqrtf(24.0f * c.gamma * c.g.kT[c.r] / p.dt);
   c.err = 0;
   c.rebuilds = 0;
+  c.frame_since = p.frame_every > 0 ? c.g.frame_phase[c.r] : 0;
+  c.frame_n = p.frame_every > 0 ? c.g.n_frames[c.r] : 0;
 }
 
 extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -289,6 +289,16 @@ class _Integrator:
             return
         self._system.thermostat._require()
         acc = self._system.auto_update_accumulators
+        if len(acc) > 0 and self._system._frames_ready(eng, lambda every: steps // every + 2):
+            # every registered accumulator can be fed from the engine's frame recorder: ONE launch for all the steps
+            eng.md_run(steps)
+            self._system._state_cache = None
+            self._system._frames_replay(eng)
+            for a in acc:                                # keep the host-side phase in step (a later call may fall back)
+                a._since_update = (a._since_update + steps) % a.delta_N
+            return
+        if len(acc) == 0 and self._system._frames_state is not None:
+            self._system._frames_off(eng)
         while steps > 0:   # stop at every step count at which a registered accumulator is due (O.py:13-15)
             n = steps if len(acc) == 0 else min(steps, acc.steps_until_next())
             eng.md_run(n)
@@ -419,6 +429,7 @@ class System:
         self._fixed = np.zeros(0, dtype=bool)   # per particle: fix=[True]*3
         self._hidden_type = None               # type index of hidden (non-interacting) ion slots once they exist
         self._state_cache = None
+        self._frames_state = None              # on-device frame recorder armed for the registered accumulators
         _current_system = self
 
     # -- ESPResSo attributes ---------------------------------------------------------------------
@@ -633,6 +644,103 @@ class System:
             self._state_cache = None
         return self._engine
 
+    # -- accumulators fed from the engine's on-device frame recorder (cgpe_frames_*) ---------------------
+    def _frames_plan(self):
+        """None, or how the registered accumulators map onto recorded frames: (every, flags, [(accumulator, source, stride)]).
+        Served: TimeSeries / MeanVarianceCalculator / Correlator of ComPosition, ComVelocity, ParticleDistances, BondDihedrals
+        over the beads of chain 0 in order (what Observables.py:54-76 registers), all in phase."""
+        import math
+        from . import observables as obs_mod
+        accs = list(self.auto_update_accumulators)
+        if not accs or self._n_part == 0:
+            return None
+        try:
+            _, n_beads, *_ = self._topology()
+        except Exception:      # noqa: BLE001  (not a chain system)
+            return None
+        chain = np.arange(n_beads)
+        every = 0
+        for a in accs:
+            every = math.gcd(every, a.delta_N)
+        flags, items = 0, []
+        for a in accs:
+            o = getattr(a, "obs", None) or getattr(a, "obs1", None)
+            if o is None or getattr(a, "obs2", None) is not None:
+                return None
+            if o.ids is None or not np.array_equal(o.ids, chain) or (o._bound is not None and o._bound is not self):
+                return None
+            src = {obs_mod.ComPosition: "com", obs_mod.ComVelocity: "vcom", obs_mod.ParticleDistances: "bonds",
+                   obs_mod.BondDihedrals: "dih"}.get(type(o))
+            if src is None:
+                return None
+            flags |= _abi.FRAME_BONDS if src == "bonds" else _abi.FRAME_DIHEDRALS if src == "dih" else 0
+            items.append((a, src, a.delta_N // every))
+        return every, flags, items
+
+    def _frames_ready(self, eng, capacity_of):
+        """Arm the frame recorder for the registered accumulators (capacity_of(every) frames per replica); False if they need
+        the step-by-step host path."""
+        plan = self._frames_plan()
+        if plan is None or not hasattr(eng, "frames_begin"):
+            self._frames_off(eng)
+            return False
+        every, flags, items = plan
+        capacity = int(capacity_of(every))
+        key = (every, flags, tuple(id(a) for a, _, _ in items))
+        st = self._frames_state
+        if st is None or st["key"] != key or st["engine"] is not eng or st["capacity"] < capacity:
+            grow = st is not None and st["engine"] is eng and st["key"] == key
+            if grow:
+                self._frames_replay(eng)                 # nothing recorded so far may be lost; phase and counters carry over
+            else:
+                self._frames_off(eng)
+                if any(a._since_update != 0 for a, _, _ in items):
+                    return False                         # accumulators in mid-interval: the recorder starts at phase 0
+            try:
+                eng.frames_begin(every, flags, int(capacity))
+            except _abi.CgpeError:
+                self._frames_state = None
+                return False
+            keep = self._frames_state if grow else dict(backlog=None, count=0)
+            self._frames_state = dict(key=key, engine=eng, capacity=int(capacity), backlog=keep["backlog"], count=keep["count"])
+        return True
+
+    def _frames_off(self, eng):
+        if self._frames_state is not None:
+            try:
+                self._frames_state["engine"].frames_end()
+            except Exception:      # noqa: BLE001
+                pass
+            self._frames_state = None
+
+    def _frames_replay(self, eng):
+        """Fetch what the recorder holds and feed it to the accumulators in order.  Replicas of a fused sampling loop record
+        different numbers of frames (each has its own burst schedule); the replica-batched accumulators take the frames all
+        replicas have, the surplus waits for the next call."""
+        st = self._frames_state
+        if st is None:
+            return
+        plan = self._frames_plan()
+        if plan is None or (plan[0], plan[1], tuple(id(a) for a, _, _ in plan[2])) != st["key"]:
+            self._frames_off(eng)                        # the accumulators were cleared or replaced: nothing to feed
+            return
+        _, _, items = plan
+        fr, bo, di = eng.frames_fetch()
+        R = self.n_replicas
+        new = [dict(com=fr[r][:, 0:3], vcom=fr[r][:, 3:6], bonds=None if bo is None else bo[r], dih=None if di is None else di[r])
+               for r in range(R)]
+        if st["backlog"] is not None:
+            new = [{k: (v if st["backlog"][r][k] is None else np.concatenate([st["backlog"][r][k], v]))
+                    for k, v in new[r].items()} for r in range(R)]
+        n = min(len(d["com"]) for d in new)
+        for k in range(n):
+            st["count"] += 1
+            for acc, src, stride in items:
+                if st["count"] % stride == 0:
+                    val = np.stack([new[r][src][k] for r in range(R)])
+                    acc.update_with(val[0] if R == 1 else val)
+        st["backlog"] = [{k: (None if v is None else v[n:]) for k, v in d.items()} for d in new]
+
     def _state(self):
         """(xyzq [R][P][4], vel [R][P][4], type [R][P]) of the current configuration."""
         if self._engine is None:
@@ -666,8 +774,21 @@ class System:
         sp = eng.sample_params(n_samples, md_steps_per_burst=md_steps_per_burst, use_md=use_md, mc_blocks=blocks,
                                q_snapshot_every=q_snapshot_every, q_snapshot_rows=rows,
                                schedule_seed=schedule_seed, p_burst1=p_burst1, p_burst2=p_burst2)
+        if len(self.auto_update_accumulators) > 0:
+            # registered accumulators (Observables.py) are fed from frames the kernel records every delta_N steps: the loop
+            # stays ONE launch.  Capacity: expected frames of the schedule + 40 %, but never more than every burst taken.
+            def cap(every):
+                per_burst = md_steps_per_burst // every + 1
+                return int(min(2 * n_samples * per_burst, 1.4 * n_samples * (p_burst1 + p_burst2) * per_burst + 64)) + 2
+            if not (use_md and self._frames_ready(eng, cap)):
+                raise RuntimeError("the registered accumulators cannot be fed by the engine's frame recorder; use the step-by-step "
+                                   "loop (EnsembleDynamics._perform_sampling_stepwise)")
+        elif self._frames_state is not None:
+            self._frames_off(eng)
         out = eng.sample_loop(sp)
         self._state_cache = None
+        if self._frames_state is not None:
+            self._frames_replay(eng)
         return out
 
 

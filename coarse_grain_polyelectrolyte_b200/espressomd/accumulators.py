@@ -28,6 +28,10 @@ class TimeSeries(_Accumulator):
     def update(self):
         self._data.append(np.array(self.obs.calculate(), dtype=np.float64))
 
+    def update_with(self, value, _second=None):
+        """Feed one sample that was evaluated elsewhere (the engine's on-device frame recorder)."""
+        self._data.append(np.array(value, dtype=np.float64))
+
     def time_series(self):
         return np.array(self._data)
 
@@ -42,7 +46,10 @@ class MeanVarianceCalculator(_Accumulator):
         self._n, self._mean, self._m2 = 0, None, None
 
     def update(self):
-        x = np.array(self.obs.calculate(), dtype=np.float64)
+        self.update_with(self.obs.calculate())
+
+    def update_with(self, value, _second=None):
+        x = np.array(value, dtype=np.float64)
         if self._mean is None:
             self._mean, self._m2 = np.zeros_like(x), np.zeros_like(x)
         self._n += 1
@@ -134,6 +141,15 @@ class Correlator(_Accumulator):
         a = np.array(self.obs1.calculate(), dtype=np.float64)
         b = a if self.obs2 is None else np.array(self.obs2.calculate(), dtype=np.float64)
         self._push(0, a, b)
+
+    def update_with(self, value, second=None):
+        """Feed one sample that was evaluated elsewhere (the engine's on-device frame recorder)."""
+        if self._finalized:
+            raise RuntimeError("the correlator has been finalized")
+        if self._levels is None:
+            self._setup()
+        a = np.array(value, dtype=np.float64)
+        self._push(0, a, a if second is None else np.array(second, dtype=np.float64))
 
     def finalize(self):
         self._finalized = True

@@ -43,6 +43,9 @@ extern "C" {
 #define CGPE_MAX_MC_BLOCKS 4  /* MC blocks per sample (the reference uses 2, E.py:94-95)       */
 #define CGPE_N_OBS 6          /* observable columns written per sample                         */
 #define CGPE_N_ENERGY 5       /* total, kinetic, coulomb, bonded, non_bonded                   */
+#define CGPE_FRAME_COLS 8     /* columns of a recorded frame: COM x,y,z, COM velocity x,y,z, Rg, Ree */
+#define CGPE_FRAME_BONDS 1    /* cgpe_frames_begin flags: also record the N-1 bond lengths ...   */
+#define CGPE_FRAME_DIHEDRALS 2 /* ... and the N-3 torsion angles of chain 0                      */
 
 typedef enum cgpe_status {
   CGPE_OK = 0,
@@ -241,6 +244,19 @@ CGPE_API int cgpe_set_engine(cgpe_handle *h, int32_t engine);
  * in ns of the GPU's global timer, of the CTA(s) that ran each replica in the last fused sampling launch
  * (second CTA zero for the one-CTA engines): the load-balance picture of a launch. */
 CGPE_API int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds, int64_t *cta_ns);
+/* On-device accumulation for the observables the reference registers with system.auto_update_accumulators
+ * (Observables.py:54-76: ParticleDistances / BondDihedrals TimeSeries, ComPosition / ComVelocity correlators, delta_N = 100):
+ * after cgpe_frames_begin every `every`-th MD step of a replica -- inside cgpe_md_run and inside the fused cgpe_sample_loop,
+ * without leaving the launch -- appends one frame of chain 0 to device buffers: COM position, COM velocity, Rg, Ree
+ * (CGPE_FRAME_COLS doubles) and, on request (flags), the N-1 bond lengths and the N-3 torsion angles (float).  `capacity` =
+ * frames per replica the buffers hold; frames beyond it are dropped and reported by the next synchronising call
+ * (CGPE_ERR_CAPACITY).  cgpe_frames_fetch copies out what was recorded since the last fetch -- frames [R][capacity][8],
+ * bonds [R][capacity][N-1], dihedrals [R][capacity][N-3], n_frames [R]; any pointer may be NULL -- and empties the buffers;
+ * the step phase of the recorder carries over, also across a cgpe_frames_begin with the same `every` (a larger capacity).
+ * Shared-memory engine (<= 2048 particles per replica). */
+CGPE_API int cgpe_frames_begin(cgpe_handle *h, int32_t every, int32_t flags, int32_t capacity);
+CGPE_API int cgpe_frames_fetch(cgpe_handle *h, double *frames, float *bonds, float *dihedrals, int32_t *n_frames);
+CGPE_API int cgpe_frames_end(cgpe_handle *h);
 /* device time of the last hot-path call in milliseconds (CUDA events on the handle's stream) and
  * the number of kernels it launched */
 CGPE_API int cgpe_last_call_ms(cgpe_handle *h, float *ms, int32_t *n_launches);

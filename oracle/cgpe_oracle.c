@@ -1092,6 +1092,10 @@ int orc_engine_info(orc_handle *h, int32_t *engine, int64_t *compact_builds, int
   if (compact_builds) for (int r = 0; r < h->cfg.n_replicas; ++r) compact_builds[r] = 0;
   return CGPE_OK;
 }
+/* the frame recorder belongs to the CUDA engines; the oracle's role is taken by the host-side accumulators of the facade */
+int orc_frames_begin(orc_handle *h, int32_t every, int32_t flags, int32_t capacity) { (void)every; (void)flags; (void)capacity; snprintf(h->err, 512, "the oracle records no frames"); return CGPE_ERR_UNSUPPORTED; }
+int orc_frames_fetch(orc_handle *h, double *frames, float *bonds, float *dihedrals, int32_t *n_frames) { (void)frames; (void)bonds; (void)dihedrals; (void)n_frames; snprintf(h->err, 512, "the oracle records no frames"); return CGPE_ERR_UNSUPPORTED; }
+int orc_frames_end(orc_handle *h) { (void)h; return CGPE_OK; }
 int orc_last_call_ms(orc_handle *h, float *ms, int32_t *n) { (void)h; if (ms) *ms = 0.f; if (n) *n = 0; return CGPE_OK; }
 
 /* ------------------------------------------------------------------------------------------- */

@@ -96,8 +96,10 @@ class EnsembleDynamics(Model):
     # -- E.py:75-119 ---------------------------------------------------------------------------------
     def perform_sampling(self, npH=None):
         system = self.system
-        if len(system.auto_update_accumulators) > 0:
-            # registered accumulators are fed by integrator.run: take the reference's loop call by call
+        if len(system.auto_update_accumulators) > 0 and (not self.USE_WCA or system._frames_plan() is None):
+            # accumulators the engine's frame recorder cannot feed (RDF, particle positions, ...) are updated by integrator.run:
+            # take the reference's loop call by call.  The ones Observables.py registers for the chain (bond lengths, torsions,
+            # COM position / velocity correlators) are recorded on the device and the loop below stays one launch.
             return self._perform_sampling_stepwise()
         system.time = 0.0
         start = time.time()

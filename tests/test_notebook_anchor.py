@@ -188,3 +188,33 @@ def test_cuda_engine_reproduces_the_notebook_numbers():
     series, frames = run_notebook_protocol(None, n_chunks=62, samples_per_chunk=43, equil_steps=100000, n_streams=2)
     assert series["num_As"].shape == (4, 2666)
     check_against_notebook(series, frames, coulomb_size=True)
+
+
+@pytest.mark.gpu
+def test_com_velocity_autocorrelation_matches_the_notebook_fit():
+    """NB cell 28 (raw JSON ~ line 918 ff.): ESPResSo's COM velocity autocorrelation of this N = 52 chain, fitted with
+    a exp(-b tau), gave a = 0.0608, b = 0.980.  The COM of a Langevin chain with one friction constant is an Ornstein-Uhlenbeck
+    particle whatever the interactions: a = 3 kT / N = 0.0577, b = gamma = 1.  The correlator of Observables.com_vel_cor (fed by
+    the on-device frame recorder inside the fused sampling loop) must give both within 6 %, and the notebook's fit within 10 %."""
+    from modules.EnsembleDynamics import EnsembleDynamics
+    from modules.Observables import Observables
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from run_diffusion import fit_vacf, green_kubo
+    ens = EnsembleDynamics(copy.deepcopy(NOTEBOOK_PARAMETERS), replicas=dict(pH=[4.0, 10.0, 4.0, 10.0]))
+    reg = Observables()
+    ids = list(range(52))
+    reg.add_observable("com_vel_cor", reg.com_vel_cor, ids, 1000)          # NB cell 7
+    reg.update_accumulators(ens.system)
+    ens.equilibrate_pH()
+    ens.num_samples = 2666
+    ens.n_samp_iter = 1328
+    ens.perform_sampling()
+    assert ens.system._engine.last_call_ms()[1] == 1                         # the accumulators did not break the fused launch
+    c = reg.observables["com_vel_cor"]
+    tau, acf = c.lag_times(), c.result()[..., 0].mean(axis=1)               # mean over the four replicas
+    assert c.sample_sizes()[0] > 7000
+    a, b = fit_vacf(tau, acf, n=85)
+    assert abs(a - 3.0 / 52) < 0.06 * 3.0 / 52 and abs(b - 1.0) < 0.06, (a, b)
+    assert abs(a - 0.0608) < 0.10 * 0.0608 and abs(b - 0.980) < 0.10 * 0.980, (a, b)
+    d_gk, _ = green_kubo(tau, acf)                                           # NB cell 29; Rouse: D = kT / (N gamma) = 0.0192
+    assert abs(d_gk - 1.0 / 52) < 0.2 / 52, d_gk

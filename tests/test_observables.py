@@ -178,8 +178,8 @@ def test_accumulators_follow_integrator_run():
     msd = reg.observables["msd"]
     assert msd.result().shape[1:] == (2, 3) and msd.sample_sizes()[0] == 4 and msd.lag_times()[1] == pytest.approx(100 * s.time_step)
     assert np.all(msd.result()[0] == 0.0) and np.all(msd.result()[1] > 0.0)
-    # the fused sampling loop bypasses integrator.run: with accumulators registered perform_sampling takes
-    # the reference's loop call by call, and the accumulators keep filling
+    # with these accumulators registered perform_sampling stays on the fused loop (the engine records their frames on the
+    # device every gcd(100, 30) = 10 steps), and the accumulators keep filling
     n_before = len(reg.observables["fast"].time_series())
     ens.equilibrate_pH()
     ens.perform_sampling()
@@ -191,3 +191,91 @@ def test_accumulators_follow_integrator_run():
     assert len(s.auto_update_accumulators) == 0
     ens.perform_sampling()         # back on the fused loop
     assert ens.num_As.shape == (2, ens.num_samples)
+
+
+@pytest.mark.gpu
+def test_device_frame_recorder_feeds_the_accumulators_like_the_host_path():
+    """The accumulators of Observables.py:54-76 (bond lengths, torsions, COM position / velocity correlators) registered on
+    two identical systems: one is updated the reference's way -- integrator.run stops every delta_N steps and the observables
+    are evaluated on a state read-back -- the other by the frames the MD kernel records on the device inside ONE launch
+    (cgpe_frames_*).  Same seeds, and a horizon short enough (60 steps) for the two FP32 trajectories to stay together
+    (they part like any two roundings of a chaotic system: 150 ulp after 40 steps, test_md_steps_match_oracle), so the
+    accumulated data agree to round-off.  delta_N = 10 and 5 instead of the registry's 100 for that reason."""
+    from coarse_grain_polyelectrolyte_b200 import workloads
+    from coarse_grain_polyelectrolyte_b200.espressomd import accumulators as A, observables as O
+    from modules.EnsembleDynamics import EnsembleDynamics
+
+    def build(device_path):
+        params = workloads.example_parameters(40, **{"Montecarlo properties": {"N_BLOCKS": 1, "DESIRED_BLOCK_SIZE": 14},
+                                                     "Simulation configuration": {"ION_MODEL": "implicit"}})
+        ens = EnsembleDynamics(params, replicas=dict(pH=[7.0, 9.0], c_salt=[2e-2, 2e-2]))
+        ids = list(range(ens.n_mon))
+        sy = ens.system       # bound explicitly: an unbound observable reads the most recently created System
+        accs = {
+            "bonds": A.TimeSeries(obs=O.ParticleDistances(ids=ids, system=sy), delta_N=10),
+            "dih": A.TimeSeries(obs=O.BondDihedrals(ids=ids, system=sy), delta_N=10),
+            "msd": A.Correlator(obs1=O.ComPosition(ids=ids, system=sy), tau_lin=4, tau_max=0.05, delta_N=10,
+                                corr_operation="square_distance_componentwise", compress1="discard1"),
+            "vacf": A.Correlator(obs1=O.ComVelocity(ids=ids, system=sy), tau_lin=4, tau_max=0.05, delta_N=10,
+                                 corr_operation="scalar_product", compress1="discard1"),
+            "fast": A.TimeSeries(obs=O.ComVelocity(ids=ids, system=sy), delta_N=5),
+        }
+        for a in accs.values():
+            ens.system.auto_update_accumulators.add(a)
+        if not device_path:
+            ens.system._frames_plan = lambda: None          # force the step-by-step host path
+        return ens, accs
+
+    host, dev = build(False), build(True)
+    for ens, _ in (host, dev):
+        ens.system.integrator.run(25)
+        ens.system.integrator.run(35)
+    assert dev[0].system._frames_state is not None and host[0].system._frames_state is None
+    assert dev[0].system._engine.last_call_ms()[1] == 1          # the 35 steps were one launch
+    for name in ("bonds", "dih", "fast"):
+        a, b = host[1][name].time_series(), dev[1][name].time_series()
+        assert a.shape == b.shape and a.shape[0] == (12 if name == "fast" else 6), (name, a.shape, b.shape)
+        if name == "dih":
+            assert np.abs(np.angle(np.exp(1j * (a - b)))).max() < 2e-3
+        else:
+            np.testing.assert_allclose(b, a, rtol=5e-4, atol=5e-4)
+    for name in ("msd", "vacf"):
+        ch, cd = host[1][name], dev[1][name]
+        np.testing.assert_array_equal(ch.lag_times(), cd.lag_times())
+        np.testing.assert_array_equal(ch.sample_sizes(), cd.sample_sizes())
+        np.testing.assert_allclose(cd.result(), ch.result(), rtol=5e-3, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_registered_observables_keep_the_fused_sampling_loop():
+    """perform_sampling with the chain observables of Observables.py registered stays ONE launch; the accumulators receive the
+    frames recorded every delta_N steps of every replica's own bursts.  COM diffusion: MSD(tau) of the recorded COM positions
+    grows linearly, 6 D tau with D = kT / (N gamma) (Rouse: all beads carry the same friction)."""
+    from coarse_grain_polyelectrolyte_b200 import workloads
+    from modules.EnsembleDynamics import EnsembleDynamics
+    params = workloads.example_parameters(40, **{"Montecarlo properties": {"N_BLOCKS": 8, "DESIRED_BLOCK_SIZE": 35},
+                                                 "Simulation configuration": {"ION_MODEL": "implicit"}})
+    ens = EnsembleDynamics(params, replicas=dict(pH=[7.0, 8.0, 9.0, 10.0], c_salt=[2e-2] * 4))
+    ids = list(range(ens.n_mon))
+    reg = Observables()
+    reg.add_observable("msd", reg.com_pos_cor, ids, 8.0)
+    reg.add_observable("bonds", reg.particle_distance_observable, ids)
+    reg.update_accumulators(ens.system)
+    ens.equilibrate_pH()
+    ens.perform_sampling()
+    eng = ens.system._engine
+    assert eng.last_call_ms()[1] == 1 and eng.engine_info()["engine"] == "solo"
+    assert ens.num_As.shape == (4, ens.num_samples)
+    msd = reg.observables["msd"]
+    n_frames = msd.sample_sizes()[0]
+    md_steps = np.rint(ens.times[:, -1] / ens.system.time_step)               # MD steps of the sampling loop, per replica
+    assert abs(n_frames - (int(md_steps.min() // 100) + 10)) <= 1             # + the 1000 steps of equilibrate_pH
+    assert n_frames > 0.5 * ens.num_samples * 5 * 0.7
+    bonds = reg.observables["bonds"].time_series()
+    assert bonds.shape == (n_frames, 4, ens.n_mon - 1)
+    assert abs(bonds.mean() - ens.bond_length_reduced_units.magnitude) < 0.1
+    tau, res = msd.lag_times(), msd.result().sum(axis=-1).mean(axis=1)       # sum over x, y, z; mean over replicas
+    sel = (tau > 0.5) & (tau < 4.0)
+    slope = np.polyfit(tau[sel], res[sel], 1)[0]
+    d_rouse = 1.0 / ens.n_mon
+    assert 0.5 * 6 * d_rouse < slope < 2.0 * 6 * d_rouse, (slope, 6 * d_rouse)
