@@ -109,22 +109,30 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/ncu_traffic.json; the capture command is recorded there).  None if absent."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+def _ncu_summary(engine):
+    name = {"duo": "r2_sample_loop_duo_ncu_summary.json", "solo": "r2_sample_loop_solo_ncu_summary.json"}.get(engine)
+    return os.path.join(ROOT, "profiles", name) if name else None
+
+
+def ncu_traffic(engine="solo"):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of the engine in force
+    (profiles/r2_sample_loop_{solo,duo}_ncu_summary.json; the capture command is recorded there; a 10-sample launch of the
+    same 128 x N=1000 shard: the traffic is the state in and out, it does not grow with the samples).  None if absent."""
+    path = _ncu_summary(engine)
     try:
         with open(path) as f:
-            return json.load(f)
-    except (OSError, ValueError):
+            d = json.load(f)
+        return {"dram_bytes_per_launch": d["derived"]["dram_bytes_per_launch"],
+                "source": f"ncu --set full capture profiles/{os.path.basename(path)} (10-sample launch of the same shard)"}
+    except (OSError, ValueError, KeyError, TypeError):
         return None
 
 
-def ncu_issue():
-    """Instruction-issue figures of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_sample_loop_ncu_summary.json): the roof that actually binds this kernel.  Measured under the
-    profiler on the same command, reported beside the live flop count, never instead of it."""
-    path = os.path.join(ROOT, "profiles", "r1_sample_loop_ncu_summary.json")
+def ncu_issue(engine="solo"):
+    """Instruction-issue figures of the dominant kernel from the committed ncu --set full capture of the engine in force:
+    the roof that actually binds this kernel.  Measured under the profiler on the same workload, reported beside the live
+    flop count, never instead of it."""
+    path = _ncu_summary(engine)
     try:
         with open(path) as f:
             m = json.load(f)["metrics"]
@@ -132,7 +140,8 @@ def ncu_issue():
         return {"warp_inst_per_cycle_per_sm": ipc, "peak": 4.0, "frac": ipc / 4.0,
                 "issue_slots_busy_of_active_cycles": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]) / 100.0,
                 "sm_active_of_elapsed_cycles": float(m["sm__cycles_active.avg"][0]) / float(m["sm__cycles_elapsed.avg"][0]),
-                "source": "ncu --set full capture profiles/r1_sample_loop_ncu_summary.json (40-step launch, under the profiler)"}
+                "lanes_per_warp_instruction": float(m["smsp__thread_inst_executed_per_inst_executed.ratio"][0]),
+                "source": f"ncu --set full capture profiles/{os.path.basename(path)} (10-sample launch, under the profiler)"}
     except (OSError, ValueError, KeyError):
         return None
 
@@ -497,9 +506,9 @@ def main():
                          "note": "busy time of every CTA of the timed launch (GPU global timer) against launch x SMs; two CTAs share an SM in the cluster engine"},
         "roofline": {
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-            "traffic": None if wide else (ncu_traffic() or {}).get("dram_bytes_per_launch"),
+            "traffic": None if wide else (ncu_traffic(engine_info["engine"]) or {}).get("dram_bytes_per_launch"),
             "traffic_source": "no ncu --set full capture of the global-memory engine's kernels committed" if wide
-                              else (ncu_traffic() or {}).get("source", "no ncu capture committed"), "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_kind} clock; no FP32 entry in MEASURED_PEAKS.json)",
+                              else (ncu_traffic(engine_info["engine"]) or {}).get("source", "no ncu capture committed"), "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz ({peak_kind} clock; no FP32 entry in MEASURED_PEAKS.json)",
             "kernel": "wk_forces + wk_dh_rows (per MD step) / wk_mc_block (trials)" if wide else ("k_duo_sample_loop" if engine_info["engine"] == "duo" else "k_sample_loop"),
             "algorithmic_flop_per_md_step": per_step, "unique_listed_pairs": [float(s) / 2 for s in stats],
             "note": ("Verlet-list algorithm: work counted on the pairs the lists hold (SURVEY 8d formula) over the whole step "
@@ -510,7 +519,7 @@ def main():
                      "the packed FFMA2 form takes two issue slots, tools/ubench_issue.cu) and by the launch lasting as long as "
                      "its slowest replica, not by a pipe"),
             "allpairs_equivalent_tflops": allpairs_equiv,
-            "instruction_issue": None if wide else ncu_issue(),
+            "instruction_issue": None if wide else ncu_issue(engine_info["engine"]),
         },
         "roofline_mc": {
             "bound": "mufu", "unit": "partner-terms/s x 2 MUFU", "peak": mufu_peak,
