@@ -34,6 +34,8 @@ struct cgpe_handle {
   int n_sm = 0;
   size_t dhc_need_solo = 0;
   void *frame_alloc[3] = {nullptr, nullptr, nullptr};   // DevState::frames, frame_bonds, frame_dih
+  void *mc_e_alloc = nullptr;  // DevState::mc_e
+  size_t mc_e_bytes = 0;
   cudaStream_t own_stream, stream;
   cudaEvent_t ev0, ev1;
   int device;
@@ -523,6 +525,7 @@ void cgpe_destroy(cgpe_handle *h) {
   for (void *ptr : h->wide_allocs) cudaFree(ptr);
   if (h->dhc_alloc) cudaFree(h->dhc_alloc);
   for (void *ptr : h->frame_alloc) if (ptr) cudaFree(ptr);
+  if (h->mc_e_alloc) cudaFree(h->mc_e_alloc);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_qdist) cudaFree(h->d_qdist);
   if (h->d_trace) cudaFree(h->d_trace);
@@ -635,6 +638,22 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     } else {
       int rc_duo = plan_duo(h);
       if (rc_duo) return rc_duo;
+    }
+  }
+  // pair-kernel matrix of the trial moves (chain_engine.cu mc_prepare / mc_block): implicit-ion replicas of the shared-memory
+  // engines, as long as it stays a small part of HBM
+  h->g.mc_e = nullptr; h->g.mc_e_stride = 0;
+  if (h->launch.items != 0 && p.n_ions == 0 && p.use_dh && p.n_rx > 0 && n_chg > 0 && !std::getenv("CGPE_NO_MC_MATRIX")) {
+    const int stride = (n_chg + 127) / 128 * 128;
+    const size_t need = sizeof(float) * (size_t)p.R * n_chg * stride;
+    if (need <= ((size_t)8 << 30)) {
+      if (need > h->mc_e_bytes) {
+        if (h->mc_e_alloc) { cudaFree(h->mc_e_alloc); h->mc_e_alloc = nullptr; h->mc_e_bytes = 0; }
+        CU(cudaMalloc(&h->mc_e_alloc, need));
+        h->mc_e_bytes = need;
+      }
+      h->g.mc_e = static_cast<float *>(h->mc_e_alloc);
+      h->g.mc_e_stride = stride;
     }
   }
   {   // list radii: see upload_wca

@@ -80,6 +80,9 @@ struct DevState {
   int *lst_prot;      // [R][n_rx][P] bookkeeping lists (particle ids), swap-remove order
   int *lst_deprot;    // [R][n_rx][P]
   int *cnt;           // [R][n_rx][2] n_prot, n_deprot
+  float *mc_e;        // [R][n_chg][mc_e_stride] exp(-kappa r)/r of every listed pair inside r_cut, 0 elsewhere: written by mc_prepare for
+                      // the reaction blocks of a sample (positions rest meanwhile), read row-wise by an accepted flip.  NULL: not in use
+  int mc_e_stride;    // row stride in floats (multiple of 128)
   uint16_t *dhc;      // [R][dhc_cap / 8][dhc_stride][8] listed AND charged partners of every (site, sub-thread), shared-memory engine
   int *ion_active;    // [R][n_ions] particle ids of the free H+ (type_ion), swap-remove order
   int *ion_free;      // [R][n_ions] hidden slots, used as a stack

@@ -55,7 +55,7 @@ size_t chain_smem_bytes(DevParams &p) {
   f.ld = take(sizeof(uint16_t) * n_rx * n_chg, 2);
   f.wn = take((size_t)p.P, 1);
   f.type = take((size_t)p.P, 1);
-  f.phi = take(sizeof(float) * n_chg, 4);
+  f.phi = take(sizeof(float) * ((n_chg + 127) / 128 * 128), 16);   // padded to the row stride of DevState::mc_e (float4 updates)
   f.wc = take(sizeof(float) * n_chg, 4);
   f.rxof = take(n_chg, 1);
   f.cpos = take(sizeof(float4) * (n_chg + 1), 16);   // +1: far-away, uncharged dummy that pads the compact partner lists
@@ -636,8 +636,77 @@ __device__ __forceinline__ void compute_forces(Ctx &c, Thr<ITEMS> &t, bool therm
   else compute_forces_impl<ITEMS, false>(c, t, thermostat, counter);
 }
 
-// ---- velocity Verlet + Langevin (R2) ------------------------------------------------------------
+// ---- frame recorder (cgpe_frames_begin): the observables of Observables.py:54-76 without leaving the launch ----
+// COM position / velocity, Rg, Ree of chain 0 [+ bond lengths, torsion angles] appended to the replica's frame buffers.
+// All threads; positions in shared memory current; contains block barriers.  Not inlined, and handed plain values instead of
+// the kernel's context: it runs once in a hundred steps and must not cost the step loop registers.
 template <int ITEMS>
+struct FrameArgs { float x[ITEMS][3], v[ITEMS][3]; };
+
+template <int ITEMS>
+__device__ __noinline__ void record_frame(const DevParams &p, const DevState &g, const float4 *pos, double *red, int r, int k,
+                                          FrameArgs<ITEMS> t) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const float4 p0 = pos[0];
+  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < ITEMS; ++q) {
+    const int i = tid + q * nt;
+    if (i < p.N) {
+      const double dx = (double)t.x[q][0] - p0.x, dy = (double)t.x[q][1] - p0.y, dz = (double)t.x[q][2] - p0.z;
+      a[0] += dx; a[1] += dy; a[2] += dz; a[3] += dx * dx + dy * dy + dz * dz;
+      b[0] += t.v[q][0]; b[1] += t.v[q][1]; b[2] += t.v[q][2];
+    }
+  }
+  double out[8];
+  for (int pass = 0; pass < 2; ++pass) {
+    double *v = pass == 0 ? a : b;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = warp_sum(v[q]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red[warp * 4 + q] = v[q];
+    __syncthreads();
+    double s[4] = {0, 0, 0, 0};
+    for (int w = 0; w < (nt + 31) / 32; ++w)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += red[w * 4 + q];
+    const double inv = 1.0 / p.N;
+    if (pass == 0) {
+      out[0] = p0.x + s[0] * inv; out[1] = p0.y + s[1] * inv; out[2] = p0.z + s[2] * inv;
+      const double var = s[3] * inv - (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) * inv * inv;
+      out[6] = sqrt(var > 0.0 ? var : 0.0);
+    } else {
+      out[3] = s[0] * inv; out[4] = s[1] * inv; out[5] = s[2] * inv;
+    }
+  }
+  if (k >= p.frame_cap) return;   // dropped; n_frames keeps counting and the host reports it
+  const size_t slot = (size_t)r * p.frame_cap + k;
+  if (tid == 0) {
+    const float4 pe = pos[p.N - 1];
+    const double ex = (double)pe.x - p0.x, ey = (double)pe.y - p0.y, ez = (double)pe.z - p0.z;
+    out[7] = sqrt(ex * ex + ey * ey + ez * ez);
+    double *f = g.frames + slot * CGPE_FRAME_COLS;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = out[q];
+  }
+  if ((p.frame_flags & CGPE_FRAME_BONDS) && g.frame_bonds)
+    for (int i = tid + 1; i < p.N; i += nt) {
+      const V3 d = xyz(pos[i]) - xyz(pos[i - 1]);
+      g.frame_bonds[slot * (p.N - 1) + i - 1] = sqrtf(dot(d, d));
+    }
+  if ((p.frame_flags & CGPE_FRAME_DIHEDRALS) && g.frame_dih && p.N >= 4)
+    for (int i = tid; i < p.N - 3; i += nt) {   // torsion of (i, i+1, i+2, i+3), the convention of observables.BondDihedrals
+      const V3 b1 = xyz(pos[i + 1]) - xyz(pos[i]), b2 = xyz(pos[i + 2]) - xyz(pos[i + 1]), b3 = xyz(pos[i + 3]) - xyz(pos[i + 2]);
+      const V3 n1 = cross(b1, b2), n2 = cross(b2, b3);
+      const V3 m = cross(n1, rsqrtf(dot(b2, b2)) * b2);
+      g.frame_dih[slot * (p.N - 3) + i] = atan2f(dot(m, n2), dot(n1, n2));
+    }
+}
+
+// ---- velocity Verlet + Langevin (R2) ------------------------------------------------------------
+template <int ITEMS, bool FRAMES>
 __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long &counter, bool &f_valid,
                          bool &lists_valid) {
   const DevParams &p = c.p;
@@ -674,9 +743,14 @@ __device__ void md_steps(Ctx &c, Thr<ITEMS> &t, int n_steps, unsigned long long 
     for (int k = 0; k < ITEMS; ++k)
 #pragma unroll
       for (int a = 0; a < 3; ++a) t.v[k][a] = fmaf(p.half_dt, t.f[k][a], t.v[k][a]);
-    if (p.frame_every > 0 && ++c.frame_since >= p.frame_every) {   // uniform: every thread counts the same steps
+    if (FRAMES && ++c.frame_since >= p.frame_every) {   // uniform: every thread counts the same steps (compiled in only when armed)
       c.frame_since = 0;
-      record_frame(c, t, c.frame_n);
+      FrameArgs<ITEMS> fa;
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { fa.x[k][a] = t.x[k][a]; fa.v[k][a] = t.v[k][a]; }
+      record_frame<ITEMS>(p, c.g, c.s.pos, c.s.red, c.r, c.frame_n, fa);
       c.frame_n += 1;
     }
   }
@@ -767,6 +841,28 @@ __device__ void mc_prepare(Ctx &c) {
     for (int n = c.tid; n <= n_sites; n += c.nt)
       c.s.ratio[(size_t)m * (p.n_chg + 1) + n] = (float)n / (float)(n_sites - n + 1);
   }
+  if (p.use_dh && c.g.mc_e) {
+    // Positions rest during the reaction blocks of this sample: the pair kernel e(r_ij) = exp(-kappa r)/r of every listed pair
+    // inside r_cut is evaluated ONCE here, by all threads, into an L2-resident matrix; an accepted flip then updates the cached
+    // potentials of its partners with one row read (mc_block) instead of a distance + rsqrt + ex2 chain per partner behind two
+    // block-wide barriers.  Same arithmetic as mc_phi_word, so the Markov chain is unchanged bit for bit.
+    const int stride = c.g.mc_e_stride;
+    float *e0 = c.g.mc_e + (size_t)c.r * p.n_chg * stride;
+    for (int idx = c.tid; idx < p.n_chg * stride; idx += c.nt) {
+      const int ci = idx / stride, ck = idx - ci * stride;
+      float e = 0.f;
+      if (ck < p.n_chg && ((c.s.dbits[(size_t)ci * p.dw + (ck >> 5)] >> (ck & 31)) & 1u)) {
+        V3 d;
+        const float4 pi4 = c.s.cpos[ci], pk4 = c.s.cpos[ck];
+        const float r2 = c.wrap ? dist2<true>(c, pi4, pk4, &d) : dist2<false>(c, pi4, pk4, &d);
+        if (r2 < c.rc2) {
+          float fr;
+          e = dh_energy_unit(r2, c.kappa, c.neg_kappa_log2e, &fr);
+        }
+      }
+      __stcg(e0 + idx, e);
+    }
+  }
   __syncthreads();
   for (int ci = c.tid; ci < p.n_chg; ci += c.nt) {
     float ph = 0.f;
@@ -816,7 +912,8 @@ template <bool IONS>
 __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_ctr, long long &accepted,
                          cgpe_trial_record *trace) {
   const DevParams &p = c.p;
-  const bool helpers = p.use_dh && c.nt > 32;   // same for every thread
+  const bool use_matrix = !IONS && p.use_dh && c.g.mc_e != nullptr;   // implicit ions: partner updates from the pair-kernel matrix
+  const bool helpers = p.use_dh && c.nt > 32 && !use_matrix;   // same for every thread
   float *ord = reinterpret_cast<float *>(c.s.red);   // {x, y, z, -, dq, ci, op}: the reduction scratch is idle here
   if (c.warp != 0 && n_trials > 0 && helpers) {
     const int nw = (p.n_chg + 31) >> 5, n_help = (c.nt >> 5) - 1;
@@ -940,7 +1037,26 @@ __device__ void mc_block(Ctx &c, int m, int n_trials, unsigned long long &trial_
           }
           if (fwd) { n_p -= 1; n_d += 1; } else { n_d -= 1; n_p += 1; }
           acc += 1;
-          if (p.use_dh && dq != 0.f) {
+          if (use_matrix && dq != 0.f) {
+            // phi of every partner changes by dq e(r): one coalesced read of the flipped site's matrix row (four partners per
+            // lane and load, all loads of a round in flight together), zeros for partners that are not listed or out of range
+            const int stride = c.g.mc_e_stride;
+            const float4 *erow = reinterpret_cast<const float4 *>(c.g.mc_e + ((size_t)c.r * p.n_chg + ci) * stride);
+            float4 *phi4 = reinterpret_cast<float4 *>(c.s.phi);
+            for (int g0 = 0; g0 * 128 < p.n_chg; g0 += 4) {
+              float4 e[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                e[g] = (g0 + g) * 128 < p.n_chg ? __ldcg(erow + (g0 + g) * 32 + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if ((g0 + g) * 128 < p.n_chg) {
+                  float4 ph = phi4[(g0 + g) * 32 + c.lane];
+                  ph.x = fmaf(dq, e[g].x, ph.x); ph.y = fmaf(dq, e[g].y, ph.y); ph.z = fmaf(dq, e[g].z, ph.z); ph.w = fmaf(dq, e[g].w, ph.w);
+                  phi4[(g0 + g) * 32 + c.lane] = ph;
+                }
+            }
+          } else if (p.use_dh && dq != 0.f) {
             // phi of every listed partner inside r_cut changes by dq e(r): lane b handles bit b of
             // each non-empty word (the helpers one word each, see above)
             // (a row of one or two words -- high salt -- costs this warp less than two barriers of 32 warps;
@@ -1080,71 +1196,6 @@ __device__ void chain_observables(Ctx &c, Thr<ITEMS> &t, double *rg, double *ree
   *ree = sqrt(ex * ex + ey * ey + ez * ez);
 }
 
-// ---- frame recorder (cgpe_frames_begin): the observables of Observables.py:54-76 without leaving the launch ----
-// COM position / velocity, Rg, Ree of chain 0 [+ bond lengths, torsion angles] appended to the replica's frame buffers.
-// All threads; positions in shared memory current; contains block barriers.
-template <int ITEMS>
-__device__ void record_frame(Ctx &c, Thr<ITEMS> &t, int k) {
-  const DevParams &p = c.p;
-  const float4 p0 = c.s.pos[0];
-  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int q = 0; q < ITEMS; ++q) {
-    const int i = c.tid + q * c.nt;
-    if (i < p.N) {
-      const double dx = (double)t.x[q][0] - p0.x, dy = (double)t.x[q][1] - p0.y, dz = (double)t.x[q][2] - p0.z;
-      a[0] += dx; a[1] += dy; a[2] += dz; a[3] += dx * dx + dy * dy + dz * dz;
-      b[0] += t.v[q][0]; b[1] += t.v[q][1]; b[2] += t.v[q][2];
-    }
-  }
-  double out[8];
-  for (int pass = 0; pass < 2; ++pass) {
-    double *v = pass == 0 ? a : b;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = warp_sum(v[q]);
-    __syncthreads();
-    if (c.lane == 0)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) c.s.red[c.warp * 4 + q] = v[q];
-    __syncthreads();
-    double s[4] = {0, 0, 0, 0};
-    for (int w = 0; w < (c.nt + 31) / 32; ++w)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) s[q] += c.s.red[w * 4 + q];
-    const double inv = 1.0 / p.N;
-    if (pass == 0) {
-      out[0] = p0.x + s[0] * inv; out[1] = p0.y + s[1] * inv; out[2] = p0.z + s[2] * inv;
-      const double var = s[3] * inv - (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) * inv * inv;
-      out[6] = sqrt(var > 0.0 ? var : 0.0);
-    } else {
-      out[3] = s[0] * inv; out[4] = s[1] * inv; out[5] = s[2] * inv;
-    }
-  }
-  if (k >= p.frame_cap) return;   // dropped; n_frames keeps counting and the host reports it
-  const size_t slot = (size_t)c.r * p.frame_cap + k;
-  if (c.tid == 0) {
-    const float4 pe = c.s.pos[p.N - 1];
-    const double ex = (double)pe.x - p0.x, ey = (double)pe.y - p0.y, ez = (double)pe.z - p0.z;
-    out[7] = sqrt(ex * ex + ey * ey + ez * ez);
-    double *f = c.g.frames + slot * CGPE_FRAME_COLS;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) f[q] = out[q];
-  }
-  if ((p.frame_flags & CGPE_FRAME_BONDS) && c.g.frame_bonds)
-    for (int i = c.tid + 1; i < p.N; i += c.nt) {
-      const V3 d = xyz(c.s.pos[i]) - xyz(c.s.pos[i - 1]);
-      c.g.frame_bonds[slot * (p.N - 1) + i - 1] = sqrtf(dot(d, d));
-    }
-  if ((p.frame_flags & CGPE_FRAME_DIHEDRALS) && c.g.frame_dih && p.N >= 4)
-    for (int i = c.tid; i < p.N - 3; i += c.nt) {   // torsion of (i, i+1, i+2, i+3), the convention of observables.BondDihedrals
-      const V3 b1 = xyz(c.s.pos[i + 1]) - xyz(c.s.pos[i]), b2 = xyz(c.s.pos[i + 2]) - xyz(c.s.pos[i + 1]),
-               b3 = xyz(c.s.pos[i + 3]) - xyz(c.s.pos[i + 2]);
-      const V3 n1 = cross(b1, b2), n2 = cross(b2, b3);
-      const V3 m = cross(n1, rsqrtf(dot(b2, b2)) * b2);
-      c.g.frame_dih[slot * (p.N - 3) + i] = atan2f(dot(m, n2), dot(n1, n2));
-    }
-}
-
 __device__ void init_ctx(Ctx &c) {
   const DevParams &p = c.p;
   c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
@@ -1202,7 +1253,7 @@ __device__ __forceinline__ void bind_smem(const DevParams &p, ChainSmem *s) {
 }
 
 // ---- kernels -----------------------------------------------------------------------------------
-template <int ITEMS>
+template <int ITEMS, bool FRAMES>
 __global__ void __launch_bounds__(1024, 1)
 k_md_run(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, int n_steps) {
   Ctx c{p, g};
@@ -1213,7 +1264,7 @@ k_md_run(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
   bool f_valid = g.f_valid[c.r] != 0, lists_valid = false;
   unsigned long long counter = (unsigned long long)g.md_counter[c.r];
   load_state(c, t, f_valid);
-  md_steps(c, t, n_steps, counter, f_valid, lists_valid);
+  md_steps<ITEMS, FRAMES>(c, t, n_steps, counter, f_valid, lists_valid);
   store_state(c, t, true);
   if (c.tid == 0) {
     g.md_counter[c.r] = (long long)counter;
@@ -1376,7 +1427,7 @@ k_list_stats(const __grid_constant__ DevParams p, const __grid_constant__ DevSta
 }
 
 // The sampling loop of perform_sampling (E.py:88-106), one launch for all samples.
-template <int ITEMS, bool IONS, int MAXT>
+template <int ITEMS, bool IONS, int MAXT, bool FRAMES>
 __global__ void __launch_bounds__(MAXT, 1)
 k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevState g,
               const __grid_constant__ cgpe_sample_params sp, uint32_t thr1, uint32_t thr2, double *obs,
@@ -1410,7 +1461,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
                     ((o.y >> 8) < thr2 ? sp.md_steps_per_burst : 0);    // E.py:91-92
       if (n > 0) {
         if (!lists_valid) { build_lists(c, t); lists_valid = true; }
-        md_steps(c, t, n, counter, f_valid, lists_valid);
+        md_steps<ITEMS, FRAMES>(c, t, n, counter, f_valid, lists_valid);
         steps += n;
         __syncthreads();  // list rows and positions visible to the MC warp
       } else if (!lists_valid) {
@@ -1489,7 +1540,7 @@ ChainLaunch chain_launch_shape(const DevParams &p) {
 #define CGPE_DISPATCH(items, expr1, expr2) ((items) == 1 ? (expr1) : (expr2))
 
 cudaError_t launch_md_run(const DevParams &p, const DevState &g, const ChainLaunch &L, int n_steps, cudaStream_t st) {
-  auto k = L.items == 1 ? k_md_run<1> : k_md_run<2>;
+  auto k = p.frame_every > 0 ? (L.items == 1 ? k_md_run<1, true> : k_md_run<2, true>) : (L.items == 1 ? k_md_run<1, false> : k_md_run<2, false>);
   cudaError_t e = opt_in_smem(k, L.smem);
   if (e != cudaSuccess) return e;
   k<<<p.R, L.threads, L.smem, st>>>(p, g, n_steps);
@@ -1533,8 +1584,11 @@ cudaError_t launch_list_stats(const DevParams &p, const DevState &g, const Chain
 cudaError_t launch_sample_loop(const DevParams &p, const DevState &g, const ChainLaunch &L,
                                const cgpe_sample_params &sp, uint32_t thr1, uint32_t thr2, double *obs,
                                float *qdist, cudaStream_t st) {
-  auto k = p.n_ions > 0 ? (L.items == 1 ? k_sample_loop<1, true, 1024> : k_sample_loop<2, true, 1024>)
-                        : (L.items == 1 ? k_sample_loop<1, false, 1024> : L.threads <= 512 ? k_sample_loop<2, false, 512> : k_sample_loop<2, false, 1024>);
+  auto k = p.n_ions > 0 ? (L.items == 1 ? k_sample_loop<1, true, 1024, false> : k_sample_loop<2, true, 1024, false>)
+                        : (L.items == 1 ? k_sample_loop<1, false, 1024, false> : L.threads <= 512 ? k_sample_loop<2, false, 512, false> : k_sample_loop<2, false, 1024, false>);
+  if (p.frame_every > 0)   // the frame recorder armed (cgpe_frames_begin): its own instantiations, so that the common path carries none of it
+    k = p.n_ions > 0 ? (L.items == 1 ? k_sample_loop<1, true, 1024, true> : k_sample_loop<2, true, 1024, true>)
+                     : (L.items == 1 ? k_sample_loop<1, false, 1024, true> : L.threads <= 512 ? k_sample_loop<2, false, 512, true> : k_sample_loop<2, false, 1024, true>);
   cudaError_t e = opt_in_smem(k, L.smem);
   if (e != cudaSuccess) return e;
   k<<<p.R, L.threads, L.smem, st>>>(p, g, sp, thr1, thr2, obs, qdist);
