@@ -325,6 +325,10 @@ def secondary_workload(name, w, torch, stream, steps, warmup, equil_steps, peaks
     out = {"workload": name, "replicas": w.R, "n_mon": n_mon, "engine": info["engine"], "steps": steps,
            "value": value, "unit": UNIT, "ms_per_step": ms / steps, "mc_sweeps_per_s": trials / sum(w.n_sites) / (ms * 1e-3),
            "gpu_launches": eng.last_call_ms()[1]}
+    ns = info["cta_ns"].astype(np.float64)
+    busy = (ns[:, :, 1] - ns[:, :, 0]) * 1e-6
+    if info["engine"] != "wide" and (busy > 0).any():
+        out["sm_time_used_frac"] = float(busy[busy > 0].sum()) / (ms * sm_count) / (2.0 if info["engine"] == "duo" else 1.0)
     if info["engine"] == "wide":
         # global-memory engine: every MD step streams positions and velocities (float4 each, read + write) = 64 B per bead-step
         gbs = 64.0 * value / 1e9
@@ -540,12 +544,16 @@ def main():
     eng.close()
     if world == 1 and not args.no_secondary and args.scaling == "weak" and args.n_mon == 1000:
         sec = {}
-        for name, mk, st in (
-                ("N100", lambda: workloads.Workload(workloads.example_parameters(100, c_salt=2e-2), pH=np.linspace(2.0, 12.0, 128), device=local_rank), 60),
-                ("N10000", lambda: workloads.Workload(workloads.example_parameters(10000, c_salt=1e-3), pH=np.linspace(2.0, 12.0, 128), device=local_rank), 3)):
+        for name, label, mk, st in (
+                ("N100", "128 pH replicas x N=100 chain, same protocol",
+                 lambda: workloads.Workload(workloads.example_parameters(100, c_salt=2e-2), pH=np.linspace(2.0, 12.0, 128), device=local_rank), 60),
+                ("N10000", "128 pH replicas x N=10000 chain, same protocol",
+                 lambda: workloads.Workload(workloads.example_parameters(10000, c_salt=1e-3), pH=np.linspace(2.0, 12.0, 128), device=local_rank), 3),
+                ("C3_whole_grid", "BASELINE configs[2] whole on this one GPU: 128 pH x 8 ionic strengths = 1024 replicas x N=1000 "
+                                  "(what --scaling strong times at N=1)",
+                 lambda: workloads.config_c3_shard(0, 1, n_ph=args.replicas_per_gpu, n_mon=1000, device=local_rank, all_salts=True), args.steps)):
             try:
-                sec[name] = secondary_workload(f"128 pH replicas x N={name[1:]} chain, same protocol", mk(), torch, stream, st, 3,
-                                               min(args.equil_steps, 1000), peaks, sm_count)
+                sec[name] = secondary_workload(label, mk(), torch, stream, st, 3, min(args.equil_steps, 1000), peaks, sm_count)
             except Exception as exc:  # noqa: BLE001  (the headline must still print)
                 sec[name] = {"error": repr(exc)}
         line["secondary"] = sec

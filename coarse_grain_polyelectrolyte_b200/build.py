@@ -29,18 +29,30 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _obj_stale(src, obj):
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    deps = [src] + [os.path.join(CSRC, h) for h in HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
 def build(force=False, verbose=False, extra_flags=()):
-    """Compile csrc/*.cu into libcgpe.so; returns the path."""
+    """Compile csrc/*.cu into libcgpe.so (stale objects only, one nvcc per source in parallel); returns the path."""
     if not force and not is_stale():
         return LIB
-    objs = []
+    objs, jobs = [], []
     for s in SOURCES:
-        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, s), "-o", obj]
-        if verbose:
-            print(" ".join(cmd), file=sys.stderr)
-        subprocess.run(cmd, check=True)
+        src, obj = os.path.join(CSRC, s), os.path.join(CSRC, s.replace(".cu", ".o"))
         objs.append(obj)
+        if force or extra_flags or _obj_stale(src, obj):
+            cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            jobs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, proc in jobs:
+        if proc.wait() != 0:
+            raise subprocess.CalledProcessError(proc.returncode, cmd)
     cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-cudart", "static"]
     subprocess.run(cmd, check=True)
     return LIB

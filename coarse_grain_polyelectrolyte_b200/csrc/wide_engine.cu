@@ -544,10 +544,11 @@ __device__ __forceinline__ float wwarp_min(float v) {
 
 // Work a trial hands to the whole CTA (explicit ions): the sums over all particles.
 struct McOrder { int op, b, cbi, ci, t_new; float q_new, dqb; float4 pb; };
-enum { kMcExit = 0, kMcIonEnergy = 1, kMcIonPhi = 2 };
+enum { kMcExit = 0, kMcIonEnergy = 1, kMcIonPhi = 2, kMcSitePhi = 3 };
+constexpr int kMcSiteRowMin = 96;     // accepted flips with a longer Debye-Hueckel row are shared with the helper warps
 constexpr int kMcThreads = 512;       // CTA of a block of trials with explicit ions
 constexpr int kMcChunk = 256;          // trials per launch when the ion sums come from the cell grids (IONS = 2)
-constexpr int kMcLoadThreads = 256;   // without ions: threads that fill the mirrors, then warp 0 runs alone
+constexpr int kMcLoadThreads = 512;   // without ions: threads that fill the mirrors, then help with the rows of accepted flips
 
 __device__ __forceinline__ void mc_bar(int n_threads) { asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); }
 
@@ -656,10 +657,45 @@ __device__ __forceinline__ void mc_ion_phi_share(const DevParams &p, const DevSt
   }
 }
 
+// the cached potentials of the listed partners of site o.ci after its charge changed by o.dqb (accepted flip): this
+// thread's share of the row, four entries in flight (row entry -> chargeable index -> position are dependent loads)
+template <bool STAGED>
+__device__ __forceinline__ void mc_site_phi_share(const DevParams &p, const DevState &g, const WideState &w, const McView &v,
+                                                  size_t base, size_t cb, int ci, float dq, float4 pi4, float kappa, float nkl,
+                                                  float rc2, int tid, int n_threads) {
+  const int n = w.dn[cb + ci];
+  const uint32_t *row = w.dl + (cb + ci) * w.cap_d;
+  for (int e0 = tid; e0 < n; e0 += 4 * n_threads) {
+    int jj[4], ck[4];
+    float4 pj[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) jj[q] = e0 + n_threads * q < n ? (int)row[e0 + n_threads * q] : -1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (jj[q] >= 0) {
+        ck[q] = v.cidx[jj[q]];
+        pj[q] = STAGED ? v.cpos[ck[q]] : g.pos[base + jj[q]];
+      }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (jj[q] < 0) continue;
+      V3 d;
+      const float r2 = wdist2(p, pi4, pj[q], &d);
+      if (r2 < rc2) {
+        float fr;
+        const float ph = fmaf(dq, dh_energy_unit(r2, kappa, nkl, &fr), v.phi[ck[q]]);
+        v.phi[ck[q]] = ph;
+        if (STAGED) w.phi[cb + ck[q]] = ph;
+      }
+    }
+  }
+}
+
 // One CTA per replica: warp 0 runs the trial loop of chain_engine.cu::mc_block.  With explicit ions
 // (IONS, blockDim = kMcThreads) an insertion / deletion needs sums over all particles; warp 0
 // posts them as orders and the other warps, parked at a named barrier, take their share.  Without
-// ions the other warps only help to fill the mirrors.
+// ions the other warps fill the mirrors and then take their share of the partner row of every accepted flip (long rows:
+// N = 10^4 at low salt lists hundreds of partners per site, one warp alone spends microseconds on them).
 //
 // IONS = 2 (replicas too large for the mirrors, e.g. a multi-chain box of 10^5 beads): the sums of
 // an ion move are local - charged particles within r_cut, any particle within the exclusion range
@@ -668,7 +704,7 @@ __device__ __forceinline__ void mc_ion_phi_share(const DevParams &p, const DevSt
 // is except the ions inserted during the chunk: those are marked `stale` (skipped in the buckets)
 // and kept in a journal that every ion move also scans.
 template <int IONS, bool STAGED>
-__global__ void __launch_bounds__(IONS == 1 ? kMcThreads : kMcLoadThreads)
+__global__ void __launch_bounds__(kMcThreads)
 wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
             int m, int n_trials, cgpe_trial_record *trace_all, int trace_stride, int trace_offset) {
   const int r = blockIdx.x, lane = threadIdx.x & 31, tid = threadIdx.x, n_threads = blockDim.x, n_warps = n_threads >> 5;
@@ -725,8 +761,17 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
     v.phi = w.phi + cb; v.wcache = w.wcache + cb; v.wflag = w.wflag + cb; v.cidx = w.cidx + base;
     v.lp = g_lp; v.ld = g_ld; v.ion_active = g_active; v.ion_free = g_free;
   }
-  if (IONS != 1 && tid >= 32) return;
-  if (IONS == 1 && tid >= 32) {   // helpers
+  const bool site_helpers = IONS == 0 && p.use_dh && n_threads > 32;   // uniform
+  if constexpr (IONS != 1) if (tid >= 32) {
+    if (!site_helpers) return;
+    for (;;) {
+      mc_bar(n_threads);   // an order is posted
+      if (ord.op == kMcExit) return;
+      mc_site_phi_share<STAGED>(p, g, w, v, base, cb, ord.ci, ord.dqb, ord.pb, kappa, nkl, rc2, tid, n_threads);
+      mc_bar(n_threads);   // the potentials are current
+    }
+  }
+  if constexpr (IONS == 1) if (tid >= 32) {   // helpers
     for (;;) {
       mc_bar(n_threads);   // an order is posted
       const McOrder o = ord;
@@ -865,7 +910,12 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
         }
         if (fwd) { n_p -= 1; n_d += 1; } else { n_d -= 1; n_p += 1; }
         acc += 1;
-        if (p.use_dh && dq != 0.f) {
+        if (p.use_dh && dq != 0.f && site_helpers && w.dn[cb + ci] > kMcSiteRowMin) {
+          if (lane == 0) { ord.op = kMcSitePhi; ord.ci = ci; ord.dqb = dq; ord.pb = pi4; }
+          mc_bar(n_threads);
+          mc_site_phi_share<STAGED>(p, g, w, v, base, cb, ci, dq, pi4, kappa, nkl, rc2, tid, n_threads);
+          mc_bar(n_threads);
+        } else if (p.use_dh && dq != 0.f) {
           const int n = w.dn[cb + ci];
           const uint32_t *row = w.dl + (cb + ci) * w.cap_d;
           // four row entries in flight per lane: the loads of a batch do not wait for one another
@@ -982,7 +1032,7 @@ wk_mc_block(const __grid_constant__ DevParams p, const __grid_constant__ DevStat
       }
     }
   }
-  if (IONS == 1) {   // release the helpers
+  if (IONS == 1 || site_helpers) {   // release the helpers
     if (lane == 0) ord.op = kMcExit;
     mc_bar(n_threads);
   }
