@@ -304,6 +304,12 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
   CU(alloc((void **)&w.wl, sizeof(uint32_t) * RP * w.cap_w));
   CU(alloc((void **)&w.wn, sizeof(int) * RP));
   CU(alloc((void **)&w.dl, sizeof(uint32_t) * RC * w.cap_d));
+  if (p.use_dh && p.n_chg >= 64 && p.n_chg < 65536 && sizeof(float4) * (size_t)p.n_chg <= 96 * 1024 && !std::getenv("CGPE_NO_DH_TILE"))
+  {   // tile mode (wide_engine.cu): rows by chargeable index, all and charged-only
+    CU(alloc((void **)&w.dlc, sizeof(uint16_t) * RC * w.cap_d));
+    CU(alloc((void **)&w.dlq, sizeof(uint16_t) * RC * w.cap_d));
+    CU(alloc((void **)&w.dnq, sizeof(int) * RC));
+  }
   CU(alloc((void **)&w.dn, sizeof(int) * RC));
   CU(alloc((void **)&w.fdh, sizeof(float4) * RC));
   CU(alloc((void **)&w.cidx, sizeof(int) * RP));

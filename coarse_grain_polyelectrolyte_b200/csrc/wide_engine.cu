@@ -325,10 +325,158 @@ wk_dh_rows(const __grid_constant__ DevParams p, const __grid_constant__ DevState
   }
 }
 
+// ---- tile mode: replicas whose chargeable particles fit one CTA's shared memory --------------------
+// A chain of N = 10^4 beads has 3334 chargeable particles: 53 KB as float4.  Every CTA stages ALL of them once
+// (position + charge, one gather) and then serves kTileSites sites, one warp per site, from shared memory:
+//   wk_rows_tile    Verlet rows by brute force over the staged set (ascending chargeable index; 15x faster than the
+//                   cell walk when the list radius is a good part of the chain's extent), written three ways: particle
+//                   ids (dl: trial moves, statistics), chargeable indices (dlc) and the CHARGED partners only (dlq)
+//   wk_dh_compact   dlq again from dlc after trial moves changed the charges (burst start, start of a reaction block)
+//   wk_dh_tile      force / potential sums over dlq
+// wk_dh_rows pays a dependent 16-byte L2 gather per listed partner, charged or not; averaged over a titration most
+// listed partners carry no charge, and at low salt (hundreds of partners per site) that walk bounded the MD step.
+constexpr int kTileThreads = 256, kTileSites = 256;
+
+__host__ __device__ inline size_t tile_smem_bytes(int n_chg) { return sizeof(float4) * (size_t)n_chg + (size_t)((n_chg + 15) / 16 * 16); }
+
+__global__ void __launch_bounds__(kTileThreads)
+wk_rows_tile(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w, int step) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  float4 *tcpos = reinterpret_cast<float4 *>(tile_smem);
+  uint8_t *vis = tile_smem + sizeof(float4) * (size_t)p.n_chg;
+  const int r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!rebuild_due(p, w, r, step)) return;
+  const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
+  const int *chg = g.chg + cb;
+  for (int ck = tid; ck < p.n_chg; ck += kTileThreads) {
+    const int j = chg[ck];
+    tcpos[ck] = g.pos[base + j];
+    vis[ck] = g.type[base + j] < p.T ? 1 : 0;   // hidden slots build no rows and are nobody's partner
+  }
+  __syncthreads();
+  const float rl = g.rcut[r] + p.skin, rlist_d2 = rl * rl;
+  const int c1 = min((int)(blockIdx.x + 1) * kTileSites, p.n_chg);
+  for (int ci = blockIdx.x * kTileSites + warp; ci < c1; ci += kTileThreads / 32) {
+    int nd = 0, nq = 0;
+    if (vis[ci]) {
+      const float4 pi = tcpos[ci];
+      uint32_t *dl = w.dl + (cb + ci) * w.cap_d;
+      uint16_t *dlc = w.dlc + (cb + ci) * w.cap_d, *dlq = w.dlq + (cb + ci) * w.cap_d;
+      for (int c0 = 0; c0 < p.n_chg; c0 += 32) {
+        const int ck = c0 + lane;
+        bool hit = false, charged = false;
+        if (ck < p.n_chg && ck != ci && vis[ck]) {
+          const float4 pj = tcpos[ck];
+          V3 d;
+          hit = wdist2(p, pi, pj, &d) < rlist_d2;
+          charged = hit && pj.w != 0.f;
+        }
+        const uint32_t mh = __ballot_sync(0xffffffffu, hit), mq = __ballot_sync(0xffffffffu, charged);
+        const uint32_t below = (1u << lane) - 1u;
+        const int slot = nd + __popc(mh & below), slotq = nq + __popc(mq & below);
+        if (hit && slot < w.cap_d) { dl[slot] = (uint32_t)chg[ck]; dlc[slot] = (uint16_t)ck; }
+        if (charged && slotq < w.cap_d) dlq[slotq] = (uint16_t)ck;
+        nd += __popc(mh);
+        nq += __popc(mq);
+      }
+      if (nd > w.cap_d) { if (lane == 0) atomicOr(&g.err[r], kErrDhCap); nd = w.cap_d; nq = min(nq, w.cap_d); }
+    }
+    if (lane == 0) { w.dn[cb + ci] = nd; w.dnq[cb + ci] = nq; }
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+wk_dh_compact(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w) {
+  const int r = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
+  const int *chg = g.chg + cb;
+  const int c1 = min((int)(blockIdx.x + 1) * kTileSites, p.n_chg);
+  for (int ci = blockIdx.x * kTileSites + warp; ci < c1; ci += kTileThreads / 32) {
+    const uint16_t *dlc = w.dlc + (cb + ci) * w.cap_d;
+    uint16_t *dlq = w.dlq + (cb + ci) * w.cap_d;
+    const int n = w.dn[cb + ci];
+    int nq = 0;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      int ck = -1;
+      bool charged = false;
+      if (e < n) { ck = dlc[e]; charged = g.pos[base + chg[ck]].w != 0.f; }
+      const uint32_t mq = __ballot_sync(0xffffffffu, charged);
+      if (charged) dlq[nq + __popc(mq & ((1u << lane) - 1u))] = (uint16_t)ck;
+      nq += __popc(mq);
+    }
+    if (lane == 0) w.dnq[cb + ci] = nq;
+  }
+}
+
+// Lane striding and arithmetic are those of wk_dh_rows<32> (over the charged partners only).
+__global__ void __launch_bounds__(kTileThreads)
+wk_dh_tile(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w,
+           int step, int mode) {
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  float4 *tcpos = reinterpret_cast<float4 *>(tile_smem);
+  const int r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (step == kStepFromDevice) step = w.step[1];
+  if (mode == 0 && step >= w.nsteps[r]) return;
+  const size_t base = (size_t)r * p.P, cb = (size_t)r * p.n_chg;
+  for (int ck = tid; ck < p.n_chg; ck += kTileThreads) tcpos[ck] = g.pos[base + g.chg[cb + ck]];
+  __syncthreads();
+  const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
+  const int c1 = min((int)(blockIdx.x + 1) * kTileSites, p.n_chg);
+  for (int ci = blockIdx.x * kTileSites + warp; ci < c1; ci += kTileThreads / 32) {
+    const float4 pi4 = tcpos[ci];
+    float fx = 0.f, fy = 0.f, fz = 0.f, ph = 0.f;
+    if (mode == 1 || pi4.w != 0.f) {
+      const uint16_t *row = w.dlq + (cb + ci) * w.cap_d;
+      const int n = w.dnq[cb + ci];
+      for (int e0 = lane; e0 < n; e0 += 128) {
+        int ck[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ck[q] = e0 + 32 * q < n ? (int)row[e0 + 32 * q] : -1;   // four entries in flight
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (ck[q] < 0) continue;
+          const float4 pj4 = tcpos[ck[q]];
+          V3 d;
+          const float r2 = wdist2(p, pi4, pj4, &d);
+          if (r2 < rc2) {
+            float fr;
+            const float en = dh_energy_unit(r2, kappa, nkl, &fr);
+            ph = fmaf(pj4.w, en, ph);
+            fr *= pj4.w;
+            fx = fmaf(fr, d.x, fx); fy = fmaf(fr, d.y, fy); fz = fmaf(fr, d.z, fz);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (mode == 1) ph += __shfl_xor_sync(0xffffffffu, ph, o);
+      else {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
+      }
+    }
+    if (lane != 0) continue;
+    if (mode == 1) w.phi[cb + ci] = ph;
+    else {
+      const float sc = p.dh_pref * pi4.w;
+      w.fdh[cb + ci] = make_float4(sc * fx, sc * fy, sc * fz, 0.f);
+    }
+  }
+}
+
+inline bool short_dh_rows(const DevParams &p, const WideState &w);
+inline bool tile_mode(const DevParams &p, const WideState &w) { return p.use_dh && w.dlc != nullptr && !short_dh_rows(p, w); }
+inline dim3 grid_tiles(const DevParams &p) { return dim3((p.n_chg + kTileSites - 1) / kTileSites, p.R); }
+
 // rows are short when a uniform box would put fewer than ~2 dozen chargeable particles in the list sphere
 inline bool short_dh_rows(const DevParams &p, const WideState &w) { return w.dh_rows_short != 0; }
 void launch_dh_rows(const DevParams &p, const DevState &g, const WideState &w, int step, int mode, cudaStream_t st) {
-  if (short_dh_rows(p, w)) {
+  if (tile_mode(p, w)) {
+    const int bytes = (int)tile_smem_bytes(p.n_chg);
+    cudaFuncSetAttribute(wk_dh_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    wk_dh_tile<<<grid_tiles(p), kTileThreads, bytes, st>>>(p, g, w, step, mode);
+  } else if (short_dh_rows(p, w)) {
     const int per = kWT / 8;
     wk_dh_rows<8><<<dim3((p.n_chg + per - 1) / per > 0 ? (p.n_chg + per - 1) / per : 1, p.R), kWT, 0, st>>>(p, g, w, step, mode);
   } else {
@@ -1133,9 +1281,20 @@ cudaError_t set_ints(int *a, int n, int v, cudaStream_t st) {
 
 // cell grids + rows of the replicas whose flag is set (2 launches)
 void launch_rebuild(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st, int step = -1) {
-  const int nbw = (p.P + kWT - 1) / kWT, per = kWT / 32, nbd = p.use_dh ? std::min((p.n_chg + per - 1) / per, kRowSiteBlocks) : 0;
+  const bool tile = tile_mode(p, w);
+  const int nbw = (p.P + kWT - 1) / kWT, per = kWT / 32, nbd = p.use_dh && !tile ? std::min((p.n_chg + per - 1) / per, kRowSiteBlocks) : 0;
   if (p.use_wca || p.use_dh || p.n_ions > 0) wk_cells<<<dim3(p.use_dh ? 2 : 1, p.R), kCT, 0, st>>>(p, g, w, step);
   wk_rows<<<dim3(nbw + nbd, p.R), kWT, 0, st>>>(p, g, w, nbw, step);
+  if (tile) {
+    const int bytes = (int)tile_smem_bytes(p.n_chg);
+    cudaFuncSetAttribute(wk_rows_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    wk_rows_tile<<<grid_tiles(p), kTileThreads, bytes, st>>>(p, g, w, step);
+  }
+}
+
+// tile mode: the charged-partner rows follow the charges (call where trial moves may have changed them since the last build)
+void launch_dh_compact(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st) {
+  if (tile_mode(p, w)) wk_dh_compact<<<grid_tiles(p), kTileThreads, 0, st>>>(p, g, w);
 }
 
 // lists for the current positions, then forces where the cache is stale
@@ -1233,6 +1392,7 @@ cudaError_t wide_md_forces(const DevParams &p, const DevState &g, const WideStat
 static cudaError_t wide_mc_blocks(const DevParams &p, const DevState &g, const WideState &w, int n_blocks, const int *rx,
                                   const int *trials, cgpe_trial_record *trace, cudaStream_t st, int *launches) {
   wk_mc_classify<<<grid_chargeable(p), kWT, 0, st>>>(p, g, w);
+  launch_dh_compact(p, g, w, st);
   if (p.use_dh) launch_dh_rows(p, g, w, 0, 1, st);
   wk_mc_prepare<<<grid_chargeable(p), kWT, 0, st>>>(p, g, w);
   for (int b = 0; b < n_blocks; ++b)
@@ -1302,6 +1462,7 @@ cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideSt
     *launches += 1;
     if (n_max > 0) {
       launch_rebuild(p, g, w, st);   // only replicas whose ions moved in the last MC block
+      launch_dh_compact(p, g, w, st);   // the last reaction blocks changed the charges
       if (p.use_dh) launch_dh_rows(p, g, w, -1, 0, st);
       wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, 1, nullptr);   // stale forces only
       WCK(wide_steps(p, g, w, n_max, st, launches, gc));

@@ -24,6 +24,9 @@ struct WideState {
   uint32_t *wl;       // [R][cap_w][P] WCA Verlet rows (particle ids), column per particle
   int *wn;            // [R][P]
   uint32_t *dl;       // [R][n_chg][cap_d] Debye-Hueckel rows (particle ids of chargeable particles), one contiguous row per site
+  uint16_t *dlc;      // [R][n_chg][cap_d] the same rows by chargeable index (nullptr unless all chargeable particles fit one CTA's shared memory)
+  uint16_t *dlq;      // [R][n_chg][cap_d] of those the partners that carry charge right now (wk_dh_compact)
+  int *dnq;           // [R][n_chg]
   float4 *fdh;        // [R][n_chg] Debye-Hueckel force on each chargeable particle (wk_dh_forces)
   int *dn;            // [R][n_chg]
   int *cidx;          // [R][P] particle -> chargeable index, -1 = never charged

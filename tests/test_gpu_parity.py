@@ -300,11 +300,14 @@ def test_dihedral_near_straight_angle_matches_oracle_and_divergence_is_reported(
     assert ei.value.status == _abi.ERR_NUMERIC and "diverged" in str(ei.value)
 
 
-def test_wide_engine_sample_loop_and_steepest_descent(Engine, oracle_mod):
+@pytest.mark.parametrize("c_salt", [2e-2, 1e-3])   # 1 mM: partner rows of several hundred sites, accepted flips shared over the trial CTA's warps
+def test_wide_engine_sample_loop_and_steepest_descent(Engine, oracle_mod, c_salt):
     """Replicas above 2048 particles run on the global-memory engine: same Markov chain."""
-    w = make_workload(2100, pH=[8.0, 9.5])
+    w = make_workload(2100, pH=[8.0, 9.5], c_salt=c_salt)
     state = random_state(w, seed=77, jitter=0.02)
     g, o = _pair(Engine, oracle_mod, w, state)
+    if c_salt < 1e-2:
+        assert g.list_stats()[:, 2].min() / sum(w.n_sites) > 96   # mean row length: the helper path is the one that runs
     o.set_list_mode(True, 0.8)
     sp = g.sample_params(6, md_steps_per_burst=5, use_md=True, mc_blocks=((0, 301), (1, 11)), q_snapshot_every=4,
                          q_snapshot_rows=2, p_burst1=0.7, p_burst2=0.3)
