@@ -323,6 +323,8 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
   CU(alloc((void **)&w.wflag, RC));
   CU(alloc((void **)&w.stale, RP));
   w.mc_grid_ok = 1;
+  w.cells_multi_min = 32768;
+  if (const char *e = std::getenv("CGPE_CELLS_MULTI_MIN")) w.cells_multi_min = std::atoi(e);   // diagnostics / tests
   w.mc_stage_limit = 220 * 1024;
   if (const char *e = std::getenv("CGPE_MC_STAGE_LIMIT")) w.mc_stage_limit = (size_t)std::atoll(e);   // diagnostics: force the
   if (const char *e = std::getenv("CGPE_MC_GRID")) w.mc_grid_ok = std::atoi(e);                        // other trial-loop variants
@@ -506,6 +508,7 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   ALLOC(g.rebuilds, p.R); ALLOC(g.compact_builds, p.R); ALLOC(g.cta_ns, (size_t)p.R * 4);
   ALLOC(g.n_frames, p.R); ALLOC(g.frame_phase, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
   ALLOC(g.f_valid, p.R); ALLOC(g.err, p.R);
+  ALLOC(g.plan, (size_t)p.R * 8);
   ALLOC(h->d_tmp_d, (size_t)p.R * 8); ALLOC(h->d_tmp_i, (size_t)p.R * 3); ALLOC(h->d_tmp_f4, RP);
 #undef ALLOC
   std::vector<double> d(p.R);

@@ -99,6 +99,7 @@ struct DevState {
   long long *cta_ns;           // [R][2][2] start / end (GPU global timer, ns) of the CTA(s) of each replica in the last fused sampling launch
   long long *compact_builds;   // [R] times the compact Debye-Hueckel partner lists were written (cgpe_engine_info)
   long long *trials, *accepted;                                  // [R][n_rx]
+  double *plan;                // [R][8] cluster-engine planner: [2],[3] trials / accepted at the last plan, [4] charged pairs inside the list radius, [5] acceptance, [6],[7] cost and MD steps predicted for the launch
   int *f_valid;       // [R]
   int *err;           // [R]
 };

@@ -35,6 +35,10 @@
 //   calc_rg / calc_re / number_of_particles   EnsembleDynamics.py:97-101
 #include "duo_engine.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -195,43 +199,139 @@ __device__ __forceinline__ void bind(const DuoShape &d, unsigned char *base, Sm 
 }
 
 // ---- which replica does a cluster take? ------------------------------------------------------------
-// Cost of a replica ~ its number of charged sites (Debye-Hueckel pairs, accepted flips).  With two CTAs
-// resident per SM the hardware places CTA b and CTA b + n_sm on the same SM (measured on B200:
-// smid = (b + 142) mod 148 for cluster launches, profiles/r2_ubench_issue.txt), i.e. cluster c shares its
-// two SMs with cluster c + n_sm/2.  So: the clusters that stay alone take the heaviest replicas, and a
-// cluster that shares takes the k-th heaviest of the rest next to the k-th lightest.  With more clusters
-// than the device holds at once, heaviest first (longest processing time first).  A heuristic only:
-// replicas are independent, results do not depend on it.  Its own small launch in front of every engine
-// launch: the counts it reads change while the engine kernel runs.
-__global__ void k_duo_plan(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, int n_sm, int *order) {
-  extern __shared__ int weight[];
+// With two CTAs resident per SM the hardware places CTA b and CTA b + n_sm on the same SM (measured on B200:
+// smid = (b + 142) mod 148 for cluster launches, profiles/r2_ubench_issue.txt), i.e. cluster c shares its two SMs
+// with cluster c + n_sm/2; with R <= n_sm replicas, n_sm - R clusters have their SMs to themselves.  A launch lasts as
+// long as its slowest cluster, so the plan is a small makespan problem with KNOWN job lengths:
+//   * MD steps of the launch: the burst schedule is a Philox stream of (seed, replica, sample index) - the planner
+//     draws the same numbers the kernel will draw (fused sampling launches; other launches: equal steps);
+//   * cost per MD step: a chain-local part + the charged Debye-Hueckel pairs inside the list radius, counted from the
+//     state the launch starts from (k_duo_count_pairs: all pairs of charged sites, ~10 us for 128 replicas) - not timed:
+//     a CTA's time depends on whom it shares its SM with;
+//   * trial moves: the acceptance measured so far (an accepted flip costs 2-3x a rejected trial).
+// Constants in microseconds from tools/prof_phases.py / prof_mc.py at N = 1000; only their ratios matter.
+// Assignment: n_alone consecutive replicas of the cost order stay alone, the rest pair k-th heaviest with k-th
+// lightest; the start of the alone block is the one with the smallest predicted makespan (a replica alone runs at
+// ~0.97 of its one-CTA time; two that share take ~1.2x while both run, after which the longer one finishes alone:
+// profiles/r2_timeline_solo_vs_duo.txt).  The launch cannot end before its most expensive replica does.  With more
+// clusters than the device holds at once: heaviest first.  A heuristic only: replicas are independent, results do
+// not depend on it.  Its own small launch in front of every engine launch: the counts it reads change while the
+// engine kernel runs.
+__global__ void __launch_bounds__(256) k_duo_count_pairs(const __grid_constant__ DevParams p, const __grid_constant__ DevState g) {
+  extern __shared__ float4 qpos[];   // the charged chargeable particles of the replica
+  __shared__ int n_q;
+  __shared__ unsigned warp_cnt[8];
+  const int r = blockIdx.x;
+  if (threadIdx.x == 0) n_q = 0;
+  __syncthreads();
+  for (int ci = threadIdx.x; ci < p.n_chg; ci += blockDim.x) {
+    const int i = g.chg[(size_t)r * p.n_chg + ci];
+    const float4 x = g.pos[(size_t)r * p.P + i];
+    if (x.w != 0.f && g.type[(size_t)r * p.P + i] < p.T) qpos[atomicAdd(&n_q, 1)] = x;
+  }
+  __syncthreads();
+  const int n = n_q;
+  const float rl = g.rcut[r] + p.skin, rl2 = rl * rl;
+  unsigned cnt = 0;
+  for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    const float4 pa = qpos[a];
+    for (int b = a + 1; b < n; ++b) {
+      const float4 pb = qpos[b];
+      const float dx = min_image(pa.x - pb.x, p.box_l, p.inv_box_l), dy = min_image(pa.y - pb.y, p.box_l, p.inv_box_l),
+                  dz = min_image(pa.z - pb.z, p.box_l, p.inv_box_l);
+      cnt += fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < rl2 ? 1u : 0u;
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_cnt[w];
+    g.plan[(size_t)r * 8 + 4] = 2.0 * (double)t;   // directed pairs, as the partner lists hold them
+  }
+}
+
+struct PlanJob { int n_samples, steps_per_burst, use_md, trials_per_sample; uint32_t thr1, thr2, seed; int fixed_steps; };
+
+__global__ void k_duo_plan(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, int n_sm, int *order,
+                           const __grid_constant__ PlanJob job) {
+  extern __shared__ float plan_smem[];
+  float *cost = plan_smem, *cand = plan_smem + p.R;
+  int *srt = reinterpret_cast<int *>(plan_smem + 2 * p.R);
+  __shared__ int best_j;
   const int R = p.R, hs = n_sm / 2;
+  const float kStepUs = 6.4f, kPairUs = 2.4e-4f, kTrialUs = 0.33f, kFlipUs = 0.45f, kAlone = 0.97f, kShare = 0.2f;
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
     int w = 0;
+    long long tr = 0, ac = 0;
     for (int m = 0; m < p.n_rx; ++m) {
       const int np = g.cnt[((size_t)r * p.n_rx + m) * 2], nd = g.cnt[((size_t)r * p.n_rx + m) * 2 + 1];
       w += (p.rx[m].q_prot != 0.f ? np : 0) + (p.rx[m].q_deprot != 0.f ? nd : 0);
+      tr += g.trials[(size_t)r * p.n_rx + m]; ac += g.accepted[(size_t)r * p.n_rx + m];
     }
-    weight[r] = w;
+    double *st = g.plan + (size_t)r * 8;
+    if ((double)tr > st[2]) st[5] = ((double)ac - st[3]) / ((double)tr - st[2]);
+    else if (st[2] == 0.0) st[5] = 0.5;
+    st[2] = (double)tr; st[3] = (double)ac;
+    const float pairs = p.use_dh ? (float)st[4] : 0.f;   // k_duo_count_pairs
+    long long steps = job.fixed_steps;
+    if (job.n_samples > 0 && job.use_md) {
+      steps = 0;
+      const unsigned long long s0 = (unsigned long long)g.samples_done[r];
+      for (int s = 0; s < job.n_samples; ++s) {
+        const unsigned long long sc = s0 + (unsigned long long)s;
+        const uint4 o = philox4x32_10((uint32_t)sc, (uint32_t)(sc >> 32), 0u, kTagSchedule, job.seed, (uint32_t)(p.replica_offset + r));
+        steps += ((o.x >> 8) < job.thr1 ? job.steps_per_burst : 0) + ((o.y >> 8) < job.thr2 ? job.steps_per_burst : 0);
+      }
+    }
+    cost[r] = (float)steps * (kStepUs + kPairUs * pairs)
+              + (float)job.n_samples * (float)job.trials_per_sample * (kTrialUs + kFlipUs * (float)st[5])
+              + 1.0e-3f * (float)w;   // launches without steps or trials: order by charged sites as before
+    st[6] = cost[r]; st[7] = (double)steps;
   }
   __syncthreads();
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
-    const int w = weight[r];
+    const float w = cost[r];
     int k = 0;   // sorted rank, 0 = heaviest
     for (int j = 0; j < R; ++j) {
-      const int wj = weight[j];
+      const float wj = cost[j];
       k += (wj > w || (wj == w && j < r)) ? 1 : 0;
     }
-    int cluster = k;
-    if (R <= hs) {
-      cluster = r;
-    } else if (R <= 2 * hs) {
-      const int n_pair = R - hs, n_alone = 2 * hs - R;
-      if (k < n_alone) cluster = n_pair + k;              // alone on its two SMs
-      else if (k < n_alone + n_pair) cluster = k - n_alone;   // the heavier one of a sharing pair
-      else cluster = hs + (R - 1 - k);                    // the lighter one: k-th lightest next to k-th heaviest
+    srt[k] = r;
+  }
+  __syncthreads();
+  if (R <= hs || R > 2 * hs) {
+    for (int k = threadIdx.x; k < R; k += blockDim.x) order[R <= hs ? srt[k] : k] = srt[k];   // all alone / heaviest first
+    return;
+  }
+  const int n_pair = R - hs, n_alone = 2 * hs - R;
+  // candidate j: the alone block is srt[j .. j + n_alone); rest(m) = srt[m < j ? m : m + n_alone]
+  for (int j = threadIdx.x; j <= R - n_alone; j += blockDim.x) {
+    float worst = n_alone > 0 ? kAlone * cost[srt[j]] : 0.f;
+    for (int i = 0; i < n_pair; ++i) {
+      const int a = i, b = 2 * n_pair - 1 - i;
+      // while both run they advance at ~1/(1 + kShare) of their lone pace; the longer one finishes alone
+      worst = fmaxf(worst, cost[srt[a < j ? a : a + n_alone]] + kShare * cost[srt[b < j ? b : b + n_alone]]);
     }
-    order[cluster] = r;
+    cand[j] = worst;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bj = 0;
+    for (int j = 1; j <= R - n_alone; ++j) if (cand[j] < cand[bj]) bj = j;
+    best_j = bj;
+  }
+  __syncthreads();
+  const int j0 = best_j;
+  for (int k = threadIdx.x; k < R; k += blockDim.x) {
+    int cluster;
+    if (k >= j0 && k < j0 + n_alone) cluster = n_pair + (k - j0);          // alone on its two SMs
+    else {
+      const int m = k < j0 ? k : k - n_alone;                              // index among the sharing replicas, heaviest first
+      cluster = m < n_pair ? m : hs + (2 * n_pair - 1 - m);                // m-th heaviest next to the m-th lightest
+    }
+    order[cluster] = srt[k];
   }
 }
 
@@ -1165,11 +1265,26 @@ k_duo_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ D
 }
 
 template <typename K, typename... Args>
-cudaError_t launch_cluster(K kernel, const DevParams &p, const DevState &g, const DuoShape &d, cudaStream_t st, Args... args) {
+cudaError_t launch_cluster(K kernel, const DevParams &p, const DevState &g, const DuoShape &d, cudaStream_t st, const PlanJob &job,
+                           Args... args) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.total);
   if (e != cudaSuccess) return e;
-  k_duo_plan<<<1, 256, sizeof(int) * p.R, st>>>(p, g, d.n_sm, d.order);
+  if (p.use_dh && p.R > d.n_sm / 2 && p.R <= d.n_sm) k_duo_count_pairs<<<p.R, 256, sizeof(float4) * (p.n_chg > 0 ? p.n_chg : 1), st>>>(p, g);
+  k_duo_plan<<<1, 256, 3 * sizeof(float) * p.R, st>>>(p, g, d.n_sm, d.order, job);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (std::getenv("CGPE_PLAN_DEBUG")) {   // diagnostics: the plan of this launch on stderr
+    std::vector<int> ord(p.R);
+    std::vector<double> pl((size_t)p.R * 8);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(ord.data(), d.order, sizeof(int) * p.R, cudaMemcpyDeviceToHost);
+    cudaMemcpy(pl.data(), g.plan, sizeof(double) * 8 * p.R, cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[cgpe plan] samples %d fixed_steps %d\n", job.n_samples, job.fixed_steps);
+    for (int c = 0; c < p.R; ++c) {
+      const int r = ord[c];
+      std::fprintf(stderr, "[cgpe plan] cluster %3d replica %3d cost %.0f steps %.0f pairs %.0f acc %.2f\n", c, r, pl[r * 8 + 6], pl[r * 8 + 7],
+                   pl[r * 8 + 4], pl[r * 8 + 5]);
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * p.R);
   cfg.blockDim = dim3(d.nt);
@@ -1186,25 +1301,28 @@ cudaError_t launch_cluster(K kernel, const DevParams &p, const DevState &g, cons
 }  // namespace
 
 cudaError_t duo_md_run(const DevParams &p, const DevState &g, const DuoShape &d, int n_steps, cudaStream_t st) {
-  return d.nt <= 512 ? launch_cluster(k_duo_md_run<512, 2>, p, g, d, st, p, g, d, n_steps)
-                     : launch_cluster(k_duo_md_run<1024, 1>, p, g, d, st, p, g, d, n_steps);
+  return d.nt <= 512 ? launch_cluster(k_duo_md_run<512, 2>, p, g, d, st, PlanJob{0, 0, 0, 0, 0u, 0u, 0u, n_steps}, p, g, d, n_steps)
+                     : launch_cluster(k_duo_md_run<1024, 1>, p, g, d, st, PlanJob{0, 0, 0, 0, 0u, 0u, 0u, n_steps}, p, g, d, n_steps);
 }
 
 cudaError_t duo_mc_run(const DevParams &p, const DevState &g, const DuoShape &d, int m, int n_trials,
                        cgpe_trial_record *trace, cudaStream_t st) {
-  return d.nt <= 512 ? launch_cluster(k_duo_mc_run<512, 2>, p, g, d, st, p, g, d, m, n_trials, trace)
-                     : launch_cluster(k_duo_mc_run<1024, 1>, p, g, d, st, p, g, d, m, n_trials, trace);
+  return d.nt <= 512 ? launch_cluster(k_duo_mc_run<512, 2>, p, g, d, st, PlanJob{1, 0, 0, n_trials, 0u, 0u, 0u, 0}, p, g, d, m, n_trials, trace)
+                     : launch_cluster(k_duo_mc_run<1024, 1>, p, g, d, st, PlanJob{1, 0, 0, n_trials, 0u, 0u, 0u, 0}, p, g, d, m, n_trials, trace);
 }
 
 cudaError_t duo_md_forces(const DevParams &p, const DevState &g, const DuoShape &d, float4 *out, cudaStream_t st) {
-  return d.nt <= 512 ? launch_cluster(k_duo_md_forces<512, 2>, p, g, d, st, p, g, d, out)
-                     : launch_cluster(k_duo_md_forces<1024, 1>, p, g, d, st, p, g, d, out);
+  return d.nt <= 512 ? launch_cluster(k_duo_md_forces<512, 2>, p, g, d, st, PlanJob{0, 0, 0, 0, 0u, 0u, 0u, 1}, p, g, d, out)
+                     : launch_cluster(k_duo_md_forces<1024, 1>, p, g, d, st, PlanJob{0, 0, 0, 0, 0u, 0u, 0u, 1}, p, g, d, out);
 }
 
 cudaError_t duo_sample_loop(const DevParams &p, const DevState &g, const DuoShape &d, const cgpe_sample_params &sp,
                             uint32_t thr1, uint32_t thr2, double *obs, float *qdist, cudaStream_t st) {
-  return d.nt <= 512 ? launch_cluster(k_duo_sample_loop<512, 2>, p, g, d, st, p, g, d, sp, thr1, thr2, obs, qdist)
-                     : launch_cluster(k_duo_sample_loop<1024, 1>, p, g, d, st, p, g, d, sp, thr1, thr2, obs, qdist);
+  int trials = 0;
+  for (int b = 0; b < sp.n_mc_blocks; ++b) trials += sp.mc_trials[b];
+  const PlanJob job{sp.n_samples, sp.md_steps_per_burst, sp.use_md, trials, thr1, thr2, (uint32_t)sp.schedule_seed, 0};
+  return d.nt <= 512 ? launch_cluster(k_duo_sample_loop<512, 2>, p, g, d, st, job, p, g, d, sp, thr1, thr2, obs, qdist)
+                     : launch_cluster(k_duo_sample_loop<1024, 1>, p, g, d, st, job, p, g, d, sp, thr1, thr2, obs, qdist);
 }
 
 }  // namespace cgpe

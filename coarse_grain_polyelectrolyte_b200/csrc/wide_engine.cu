@@ -15,6 +15,7 @@
 #include "wide_engine.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace cgpe {
@@ -166,6 +167,112 @@ wk_cells(const __grid_constant__ DevParams p, const __grid_constant__ DevState g
     order[lo + rank] = i;
     spos[lo + rank] = g.pos[base + i];
   }
+}
+
+// The same sort for particle sets too large for one CTA (a multi-chain box of 10^5 .. 10^6 beads with its ions is ONE
+// replica: wk_cells would walk millions of members with 1024 threads): count and scatter over the whole grid, the scan
+// on one CTA per set (four buckets per thread and round), the in-bucket ordering over the whole grid again.  The
+// cursor array is all zero between builds (allocation, then wk_cells_order), which saves a clearing pass.
+// (WideState::cells_multi_min: particles per replica from which the multi-CTA build is used)
+constexpr int kCB = 256;
+
+struct CellSet { const CellGrid *cg; GridDims gd; int M; };
+__device__ __forceinline__ bool cells_set(const DevParams &p, const DevState &g, const WideState &w, int r, int kind, int step,
+                                          const CellGrid *&cg, GridDims &gd) {
+  if (!rebuild_due(p, w, r, step) || (kind == 0 ? !(p.use_wca || p.n_ions > 0) : !p.use_dh)) return false;
+  cg = kind == 0 ? &w.cw : &w.cd;
+  gd = grid_dims(p, kind == 0 ? fmaxf(sqrtf(p.rlist_w2), p.grid_w_min) : g.rcut[r] + p.skin, cg->nc_max);
+  return true;
+}
+
+__global__ void __launch_bounds__(kCB)
+wk_cells_count(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w, int step) {
+  const int kind = blockIdx.y, r = blockIdx.z;
+  const CellGrid *cg; GridDims gd;
+  if (!cells_set(p, g, w, r, kind, step, cg, gd)) return;
+  const int n = cg->n;
+  const size_t base = (size_t)r * p.P;
+  const int *chg = g.chg + (size_t)r * p.n_chg;
+  int *cursor = cg->cursor + (size_t)r * cg->m_max, *cell_of = cg->cell_of + (size_t)r * n;
+  for (int e = blockIdx.x * kCB + threadIdx.x; e < n; e += gridDim.x * kCB) {
+    const int i = kind == 0 ? e : chg[e];
+    int c = -1;
+    if (g.type[base + i] < p.T) {   // hidden slots stay out of the grid
+      c = bucket_id(p, g.pos[base + i], gd);
+      atomicAdd(&cursor[c], 1);
+    }
+    cell_of[e] = c;
+  }
+}
+
+__global__ void __launch_bounds__(kCT)
+wk_cells_scan(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w, int step) {
+  const int kind = blockIdx.x, r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const CellGrid *cg; GridDims gd;
+  if (!cells_set(p, g, w, r, kind, step, cg, gd)) return;
+  const int M = gd.A * gd.A * gd.A;
+  int *start = cg->start + (size_t)r * (cg->m_max + 1), *cursor = cg->cursor + (size_t)r * cg->m_max;
+  __shared__ int warp_tot[2][32];
+  int carry = 0;
+  for (int c0 = 0, buf = 0; c0 < M; c0 += 4 * kCT, buf ^= 1) {
+    const int c = c0 + 4 * tid;
+    int v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = c + q < M ? cursor[c + q] : 0;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[buf][warp] = incl;
+    __syncthreads();
+    int t = warp_tot[buf][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+    const int before = __shfl_sync(0xffffffffu, t, warp > 0 ? warp - 1 : 0);
+    int excl = carry + (warp > 0 ? before : 0) + incl - mine;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (c + q < M) { start[c + q] = excl; cursor[c + q] = excl; excl += v[q]; }
+    carry += __shfl_sync(0xffffffffu, t, 31);
+  }
+  if (tid == 0) { start[M] = carry; cg->nc[r] = gd.A; cg->nf[r] = gd.nf; }
+}
+
+__global__ void __launch_bounds__(kCB)
+wk_cells_scatter(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w, int step) {
+  const int kind = blockIdx.y, r = blockIdx.z;
+  const CellGrid *cg; GridDims gd;
+  if (!cells_set(p, g, w, r, kind, step, cg, gd)) return;
+  const int n = cg->n;
+  int *cursor = cg->cursor + (size_t)r * cg->m_max, *tmp = cg->tmp + (size_t)r * n;
+  const int *cell_of = cg->cell_of + (size_t)r * n;
+  for (int e = blockIdx.x * kCB + threadIdx.x; e < n; e += gridDim.x * kCB) {
+    const int c = cell_of[e];
+    if (c >= 0) tmp[atomicAdd(&cursor[c], 1)] = e;
+  }
+}
+
+__global__ void __launch_bounds__(kCB)
+wk_cells_order(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ WideState w, int step) {
+  const int kind = blockIdx.y, r = blockIdx.z;
+  const CellGrid *cg; GridDims gd;
+  if (!cells_set(p, g, w, r, kind, step, cg, gd)) return;
+  const int n = cg->n, M = gd.A * gd.A * gd.A;
+  const size_t base = (size_t)r * p.P;
+  const int *chg = g.chg + (size_t)r * p.n_chg;
+  const int *start = cg->start + (size_t)r * (cg->m_max + 1), *cell_of = cg->cell_of + (size_t)r * n, *tmp = cg->tmp + (size_t)r * n;
+  int *order = cg->order + (size_t)r * n, *cursor = cg->cursor + (size_t)r * cg->m_max;
+  float4 *spos = cg->spos + (size_t)r * n;
+  const int members = start[M];
+  for (int s = blockIdx.x * kCB + threadIdx.x; s < members; s += gridDim.x * kCB) {
+    const int e = tmp[s], c = cell_of[e], lo = start[c], hi = start[c + 1];
+    int rank = 0;
+    for (int t = lo; t < hi; ++t) rank += tmp[t] < e ? 1 : 0;
+    const int i = kind == 0 ? e : chg[e];
+    order[lo + rank] = i;
+    spos[lo + rank] = g.pos[base + i];
+  }
+  for (int c = blockIdx.x * kCB + threadIdx.x; c < M; c += gridDim.x * kCB) cursor[c] = 0;   // nobody reads the cursors any more
 }
 
 // Runs [lo, hi) of grid slots that hold the buckets of the 27 cells around x: the buckets of one
@@ -1279,11 +1386,30 @@ cudaError_t set_ints(int *a, int n, int v, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// cell grids + rows of the replicas whose flag is set (2 launches)
+// cell grids of the replicas whose flag is set
+void launch_cells(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st, int step) {
+  if (!(p.use_wca || p.use_dh || p.n_ions > 0)) return;
+  const int kinds = p.use_dh ? 2 : 1;
+  if (p.P < w.cells_multi_min) { wk_cells<<<dim3(kinds, p.R), kCT, 0, st>>>(p, g, w, step); return; }
+  const int nb = std::max(1, std::min((p.P + 4 * kCB - 1) / (4 * kCB), 148 * 8));
+  wk_cells_count<<<dim3(nb, kinds, p.R), kCB, 0, st>>>(p, g, w, step);
+  wk_cells_scan<<<dim3(kinds, p.R), kCT, 0, st>>>(p, g, w, step);
+  wk_cells_scatter<<<dim3(nb, kinds, p.R), kCB, 0, st>>>(p, g, w, step);
+  wk_cells_order<<<dim3(nb, kinds, p.R), kCB, 0, st>>>(p, g, w, step);
+}
+
+// kernels a call of launch_rebuild / launch_dh_rows / launch_step puts on the stream (the library reports its launch count)
+inline int rebuild_launches(const DevParams &p, const WideState &w) {
+  const int cells = !(p.use_wca || p.use_dh || p.n_ions > 0) ? 0 : p.P < w.cells_multi_min ? 1 : 4;
+  return cells + 1 + (tile_mode(p, w) ? 1 : 0);
+}
+inline int step_launches(const DevParams &p, const WideState &w) { return 2 + rebuild_launches(p, w) + (p.use_dh ? 1 : 0); }
+
+// cell grids + rows of the replicas whose flag is set
 void launch_rebuild(const DevParams &p, const DevState &g, const WideState &w, cudaStream_t st, int step = -1) {
   const bool tile = tile_mode(p, w);
-  const int nbw = (p.P + kWT - 1) / kWT, per = kWT / 32, nbd = p.use_dh && !tile ? std::min((p.n_chg + per - 1) / per, kRowSiteBlocks) : 0;
-  if (p.use_wca || p.use_dh || p.n_ions > 0) wk_cells<<<dim3(p.use_dh ? 2 : 1, p.R), kCT, 0, st>>>(p, g, w, step);
+  const int nbw = (p.P + kWT - 1) / kWT, per = kWT / 32, nbd = p.use_dh && !tile ? std::min((p.n_chg + per - 1) / per, std::max(kRowSiteBlocks, 148 * 16 / std::max(p.R, 1))) : 0;
+  launch_cells(p, g, w, st, step);
   wk_rows<<<dim3(nbw + nbd, p.R), kWT, 0, st>>>(p, g, w, nbw, step);
   if (tile) {
     const int bytes = (int)tile_smem_bytes(p.n_chg);
@@ -1303,7 +1429,7 @@ cudaError_t wide_prepare(const DevParams &p, const DevState &g, const WideState 
   launch_rebuild(p, g, w, st);
   if (p.use_dh) launch_dh_rows(p, g, w, -1, 0, st);
   wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, thermostat, nullptr);
-  *launches += 5;
+  *launches += 2 + rebuild_launches(p, w) + (p.use_dh ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -1341,7 +1467,7 @@ cudaError_t wide_steps(const DevParams &p, const DevState &g, const WideState &w
     for (; done + kGraphChunk <= n_max; done += kGraphChunk) WCK(cudaGraphLaunch(gc->exec, st));
   }
   for (; done < n_max; ++done) launch_step(p, g, w, st);
-  *launches += (p.use_dh ? 5 : 4) * n_max;
+  *launches += step_launches(p, w) * n_max;
   return cudaGetLastError();
 }
 
@@ -1375,7 +1501,7 @@ cudaError_t wide_steepest_descent(const DevParams &p, const DevState &g, const W
     if (p.use_dh) launch_dh_rows(p, g, w, s, 0, st);
     wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, s, 0, 0, nullptr);
   }
-  *launches += 5 * n_steps + 1;
+  *launches += step_launches(p, w) * n_steps + 1;
   wk_finish_md<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, 0, 0);
   return cudaGetLastError();
 }
@@ -1412,16 +1538,16 @@ static cudaError_t wide_mc_blocks(const DevParams &p, const DevState &g, const W
       else if (ions && w.mc_grid_ok) {
         for (int t0 = 0; t0 < trials[b]; t0 += kMcChunk) {   // grids rebuilt before every chunk (see wk_mc_block)
           WCK(set_ints(w.flag, p.R, 1, st));
-          wk_cells<<<dim3(p.use_dh ? 2 : 1, p.R), kCT, 0, st>>>(p, g, w, -1);
+          launch_cells(p, g, w, st, -1);
           WCK(launch(wk_mc_block<2, false>, 32, std::min(kMcChunk, trials[b] - t0), t0));
-          *launches += 2;
+          *launches += 2 + rebuild_launches(p, w) - 1 - (tile_mode(p, w) ? 1 : 0);
         }
       }
       else if (ions) WCK(launch(wk_mc_block<1, false>, kMcThreads, trials[b], 0));
       else if (staged) WCK(launch(wk_mc_block<0, true>, kMcLoadThreads, trials[b], 0));
       else WCK(launch(wk_mc_block<0, false>, 32, trials[b], 0));
     }
-  *launches += 2 + n_blocks;
+  *launches += 2 + n_blocks + (p.use_dh ? 1 : 0) + (tile_mode(p, w) ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -1431,7 +1557,7 @@ cudaError_t wide_mc_run(const DevParams &p, const DevState &g, const WideState &
   WCK(set_ints(w.flag, p.R, 1, st));
   launch_rebuild(p, g, w, st);
   WCK(set_ints(w.flag, p.R, 0, st));
-  *launches += 5;
+  *launches += 3 + rebuild_launches(p, w);
   return wide_mc_blocks(p, g, w, 1, &m, &n_trials, trace, st, launches);
 }
 
@@ -1452,7 +1578,7 @@ cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideSt
   WCK(set_ints(w.flag, p.R, 1, st));
   launch_rebuild(p, g, w, st);
   WCK(set_ints(w.flag, p.R, 0, st));
-  *launches += 5;
+  *launches += 3 + rebuild_launches(p, w);
   for (int s = 0; s < sp.n_samples; ++s) {
     WCK(cudaMemsetAsync(w.sched_max, 0, sizeof(int), st));
     wk_schedule<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, sp, thr1, thr2);
@@ -1467,7 +1593,7 @@ cudaError_t wide_sample_loop(const DevParams &p, const DevState &g, const WideSt
       wk_forces<<<grid_particles(p), kWT, 0, st>>>(p, g, w, -1, 0, 1, nullptr);   // stale forces only
       WCK(wide_steps(p, g, w, n_max, st, launches, gc));
       wk_finish_md<<<(p.R + 127) / 128, 128, 0, st>>>(p, g, w, -1, 1);
-      *launches += 5;
+      *launches += 2 + rebuild_launches(p, w) + (p.use_dh ? 1 : 0) + (tile_mode(p, w) ? 1 : 0);
     }
     if (sp.n_mc_blocks > 0) WCK(wide_mc_blocks(p, g, w, sp.n_mc_blocks, sp.mc_reaction, sp.mc_trials, nullptr, st, launches));
     WCK(launch_observables(p, g, tmp_d, tmp_d + p.R, tmp_i, st));

@@ -43,6 +43,7 @@ struct WideState {
   int cap_w, cap_d;
   int mc_grid_ok;     // ion moves of replicas too large for the mirrors take their sums from the cell grids
   size_t mc_stage_limit;   // largest set of trial-loop mirrors kept in shared memory (bytes)
+  int cells_multi_min; // particles per replica from which the cell grids are built by many CTAs (wk_cells_count ...)
   int dh_rows_short;  // rows are expected to hold a few dozen entries at most: 8 lanes per site instead of a warp
 };
 

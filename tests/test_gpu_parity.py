@@ -553,12 +553,20 @@ def test_several_chains_per_box(Engine, oracle_mod, n_poly, n_mon, ions):
     assert _ion_dx(xg[..., :3], xo, w) < 1e-4 and np.abs(vg[..., :3] - vo).max() < 5e-3
 
 
-@pytest.mark.parametrize("c_salt", [2e-2, 1e-3])
-def test_cell_grid_rows_hold_every_pair_for_any_table_size(Engine, c_salt, monkeypatch):
+@pytest.mark.parametrize("c_salt,build", [(2e-2, "one CTA"), (1e-3, "one CTA"), (1e-3, "cell walk"), (2e-2, "many CTAs"), (1e-3, "many CTAs")])
+def test_cell_grid_rows_hold_every_pair_for_any_table_size(Engine, c_salt, build, monkeypatch):
     """The list build of the global-memory engine folds the cells of the box onto a table of A^3 buckets.
     Whatever A is (1 = a single bucket, 3 = every bucket is its own neighbour's neighbour, sizes that
     trigger the wrap adjustment nf mod A in {1, 2}, the default), the forces through the rows must equal
     the all-pairs forces, and the rows must hold the same pairs."""
+    # builds: the default (at 1 mM the Debye-Hueckel rows come from the shared-memory staged brute force, "tile mode"),
+    # the cell walk forced for long rows too (replicas whose chargeable set exceeds shared memory), the multi-CTA cell sort
+    # of the 10^5..10^6-particle boxes forced at this size
+    if build == "cell walk":
+        monkeypatch.setenv("CGPE_NO_DH_TILE", "1")
+    if build == "many CTAs":
+        monkeypatch.setenv("CGPE_CELLS_MULTI_MIN", "1")
+        monkeypatch.setenv("CGPE_NO_DH_TILE", "1")
     w = make_workload(2500, pH=[6.0, 9.5], c_salt=c_salt)
     state = random_state(w, seed=77, jitter=0.03)
     ref_forces, ref_stats = None, None

@@ -6,7 +6,7 @@ from coarse_grain_polyelectrolyte_b200 import workloads
 from coarse_grain_polyelectrolyte_b200.engine import Engine
 for pH in (2.0, 12.0):
     w = workloads.Workload(workloads.example_parameters(1000, c_salt=1e-3), pH=np.full(128, pH))
-    e = Engine(w.cfg); w.init_engine(e)
+    e = Engine(w.cfg); e.set_engine(os.environ.get('ENGINE', 'solo')); w.init_engine(e)
     e.md_run(4000); e.sample_loop(w.sample_params(e, 20))
     e.md_run(500); e.synchronize()
     e.md_run(5000); e.synchronize(); t_md = e.last_call_ms()[0] / 5000 * 1e3

@@ -31,7 +31,7 @@ for engine in ("solo", "duo"):
     md = (c1["md_steps"] - c0["md_steps"])
     print(f"== {info['engine']}: launch {ms:.2f} ms for {steps} samples; {md.sum() * 1000 / ms * 1e3:.3e} bead-steps/s")
     print("   replica pH   md_steps  cta0 ms (end)   cta1 ms (end)")
-    for r in range(0, w.R, 4):
+    for r in range(0, w.R, int(os.environ.get("EVERY", 4))):
         print(f"   {r:4d} {w.pH[r]:5.2f} {md[r]:8d}   {dur[r,0]:7.2f} ({end[r,0]:7.2f})  {dur[r,1]:7.2f} ({end[r,1]:7.2f})")
     busy = dur[dur > 0].sum()
     print(f"   sum of CTA times {busy:.1f} ms; launch x 148 SMs = {ms * 148:.1f} ms")
