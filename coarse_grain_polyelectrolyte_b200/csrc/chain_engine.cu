@@ -90,7 +90,7 @@ struct Ctx {
   bool wrap;          // false: every listed pair is closer directly than through any periodic image
   bool compact;       // DevState::dhc holds the partners of the current rows and charges (see build_dh_compact)
   bool dense;         // Debye-Hueckel list radius ~ replica extent: loop over all charged particles instead of the bit rows
-  int dh_g0, dh_ci0;  // this thread's first (sub-thread, row) work item of the Debye-Hueckel phase
+  int dh_g0, dh_ci0;  // this thread's first (sub-thread, particle) work item of the packed compact lists (build_dh_compact)
   int err;            // thread-local error bits, merged at exit
   long long rebuilds; // uniform
   int frame_since, frame_n;   // frame recorder: MD steps since the last frame, frames recorded so far (uniform)
@@ -395,23 +395,29 @@ __device__ void build_dh_compact(Ctx &c) {
   const DevParams &p = c.p;
   c.compact = false;
   if (!p.use_dh || c.dense || c.g.dhc == nullptr || p.n_chg < 97) return;   // short rows (<= 3 words): the walk is cheap, few warps hide the loads
-  const int G = p.dh_group;
+  // Work items exist for the particles that carry charge only (qlist, build_qlist): item idx = (sub-thread g, k-th charged
+  // particle), packed, so that the warps of the force loop are full whatever the degree of ionisation (at pH 2.5 and
+  // 1 mM a quarter of the sites is neutral: their lanes used to idle next to busy ones).  The force slots of the
+  // others are zeroed here once, nobody writes them until the next build.
+  const int G = p.dh_group, nq = c.s.flag[0];
+  for (int ci = c.tid; ci < p.n_chg; ci += c.nt)
+    if (c.s.cpos[ci].w == 0.0f)
+      for (int k = 0; k < 3 * G; ++k) c.s.fd[(size_t)k * p.n_chg + ci] = 0.0f;
   uint16_t *lst0 = c.g.dhc + (size_t)c.r * p.dhc_cap * p.dhc_stride;
-  for (int idx = c.tid; idx < G * p.n_chg; idx += c.nt) {
-    const int g = idx / p.n_chg, ci = idx - g * p.n_chg;
+  for (int idx = c.tid; idx < G * nq; idx += c.nt) {
+    const int g = idx / nq, ci = c.s.qlist[idx - g * nq];
+    if (idx == c.tid) { c.dh_g0 = g; c.dh_ci0 = ci; }
     const uint32_t sel = G == 1 ? 0xFFFFFFFFu : G == 2 ? (0x55555555u << g) : G == 3 ? (0x49249249u << g) : (0x11111111u << g);
-    uint16_t *lst = lst0 + (size_t)idx * 8;   // [k / 8][sub-thread][k % 8]: eight partners per 16-byte load
+    uint16_t *lst = lst0 + (size_t)idx * 8;   // [k / 8][item][k % 8]: eight partners per 16-byte load
     int n = 0;
-    if (c.s.cpos[ci].w != 0.0f) {
-      const int w_end = c.s.wrange[2 * ci + 1];
-      for (int w = c.s.wrange[2 * ci]; w < w_end; ++w) {
-        uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w] & sel;
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)((w * 32 + b) * 16);
-          ++n;
-        }
+    const int w_end = c.s.wrange[2 * ci + 1];
+    for (int w = c.s.wrange[2 * ci]; w < w_end; ++w) {
+      uint32_t m = c.s.dbits[(size_t)ci * p.dw + w] & c.s.qmask[w] & sel;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        lst[((size_t)(n >> 3) * p.dhc_stride) * 8 + (n & 7)] = (uint16_t)((w * 32 + b) * 16);
+        ++n;
       }
     }
     c.s.dhn[idx] = (uint16_t)n;
@@ -511,8 +517,15 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
     // word, so the backbone neighbours ci+-1, ci+-2, ... of a site land on different sub-threads;
     // each writes its partial force into its own slot plane (summed in phase 2)
     const int G = p.dh_group;
-    for (int idx = c.tid; idx < G * p.n_chg; idx += c.nt) {
-      const int g = idx == c.tid ? c.dh_g0 : idx / p.n_chg, ci = idx == c.tid ? c.dh_ci0 : idx - g * p.n_chg;
+    const int nq = c.compact ? c.s.flag[0] : p.n_chg;   // compact lists: work items of the charged particles only, packed
+    for (int idx = c.tid; idx < G * nq; idx += c.nt) {
+      int g, ci;
+      if (c.compact) {
+        if (idx == c.tid) { g = c.dh_g0; ci = c.dh_ci0; }
+        else { g = idx / nq; ci = c.s.qlist[idx - g * nq]; }
+      } else {
+        g = idx / p.n_chg; ci = idx - g * p.n_chg;
+      }
       const uint32_t sel = G == 1 ? 0xFFFFFFFFu : G == 2 ? (0x55555555u << g) : G == 3 ? (0x49249249u << g) : (0x11111111u << g);
       const float4 pi4 = c.s.cpos[ci];
       V3 f = {0.f, 0.f, 0.f};
@@ -1208,8 +1221,8 @@ __device__ void init_ctx(Ctx &c) {
   c.wrap = true;
   c.dense = false;
   c.compact = false;
-  c.dh_g0 = p.n_chg > 0 ? c.tid / p.n_chg : 0;
-  c.dh_ci0 = c.tid - c.dh_g0 * p.n_chg;
+  c.dh_g0 = 0;
+  c.dh_ci0 = 0;
   c.gamma = c.g.gamma[c.r];
   c.noise_pref = sqrtf(24.0f * c.gamma * c.g.kT[c.r] / p.dt);
   c.err = 0;

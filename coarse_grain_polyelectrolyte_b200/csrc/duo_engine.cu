@@ -87,6 +87,7 @@ size_t duo_layout(const DevParams &p, int n_loc, size_t smem_budget, int cap_w_c
   s.wflag = take(n_chg, 1);
   s.ratio = take(sizeof(float) * n_rx * (n_chg + 1), 4);
   s.ord = take(sizeof(float) * 8, 4);
+  s.qloc = take(sizeof(uint16_t) * (s.n_loc + 2), 2);   // owned chargeable particles that carry charge (local index) + their number
   // the WCA rows take what is left, up to 64 entries per particle (two CTAs per SM when nt <= 512)
   const size_t fixed = up(o, 4);
   long cap = cap_w_cfg > 0 ? cap_w_cfg : 0;
@@ -121,6 +122,7 @@ struct Sm {
   float *phi, *wcache;
   unsigned char *rxof, *wrange, *wflag;
   float *ratio, *ord;
+  uint16_t *qloc;
 };
 
 struct Thr {
@@ -196,6 +198,7 @@ __device__ __forceinline__ void bind(const DuoShape &d, unsigned char *base, Sm 
   s->wflag = base + d.wflag;
   s->ratio = reinterpret_cast<float *>(base + d.ratio);
   s->ord = reinterpret_cast<float *>(base + d.ord);
+  s->qloc = reinterpret_cast<uint16_t *>(base + d.qloc);
 }
 
 // ---- which replica does a cluster take? ------------------------------------------------------------
@@ -546,23 +549,41 @@ __device__ void build_dh_compact(Ctx &c) {
   const DevParams &p = c.p;
   c.compact = false;
   if (!p.use_dh || c.g.dhc == nullptr) return;
-  const int G = c.d.G, n_mine = c.chi - c.clo;
+  // Work items exist for the owned particles that carry charge only, packed (chain_engine.cu::build_dh_compact): warp 0
+  // lists them, the force slots of the others are zeroed once, nobody writes them until the next build.  Called by all
+  // threads of the CTA (one block barrier inside).
+  const int n_mine = c.chi - c.clo, n_loc = c.d.n_loc;
+  if (c.warp == 0) {
+    int base = 0;
+    for (int k0 = 0; k0 < n_mine; k0 += 32) {
+      const int cl = k0 + c.lane;
+      const bool q = cl < n_mine && c.s.pos[c.s.chg[c.clo + cl]].w != 0.0f;
+      const uint32_t m = __ballot_sync(0xffffffffu, q);
+      if (q) c.s.qloc[base + __popc(m & ((1u << c.lane) - 1u))] = (uint16_t)cl;
+      base += __popc(m);
+    }
+    if (c.lane == 0) c.s.qloc[n_loc] = (uint16_t)base;
+  }
+  for (int cl = c.tid; cl < n_mine; cl += c.nt)
+    if (c.s.pos[c.s.chg[c.clo + cl]].w == 0.0f)
+      for (int k = 0; k < 3 * c.d.G; ++k) c.s.fd[(size_t)k * n_loc + cl] = 0.0f;
+  __syncthreads();
+  const int nq = c.s.qloc[n_loc];
+  const int G = c.d.G;
   uint16_t *lst0 = c.g.dhc + ((size_t)c.r * 2 + c.rank) * c.d.dhc_cap * c.d.dhc_stride;
-  for (int idx = c.tid; idx < G * n_mine; idx += c.nt) {
-    const int g = idx / n_mine, ci = c.clo + (idx - g * n_mine);
+  for (int idx = c.tid; idx < G * nq; idx += c.nt) {
+    const int g = idx / nq, ci = c.clo + (int)c.s.qloc[idx - g * nq];
     const uint32_t sel = sel_mask(G, g);
     uint16_t *lst = lst0 + (size_t)idx * 8;
     int n = 0;
-    if (c.s.pos[c.s.chg[ci]].w != 0.0f) {
-      const int w_end = c.s.wrange[2 * ci + 1];
-      for (int w = c.s.wrange[2 * ci]; w < w_end; ++w) {
-        uint32_t m = c.s.dbits[(size_t)ci * c.d.dw + w] & c.s.qmask[w] & sel;
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          lst[((size_t)(n >> 3) * c.d.dhc_stride) * 8 + (n & 7)] = (uint16_t)((int)c.s.chg[w * 32 + b] * 16);
-          ++n;
-        }
+    const int w_end = c.s.wrange[2 * ci + 1];
+    for (int w = c.s.wrange[2 * ci]; w < w_end; ++w) {
+      uint32_t m = c.s.dbits[(size_t)ci * c.d.dw + w] & c.s.qmask[w] & sel;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        lst[((size_t)(n >> 3) * c.d.dhc_stride) * 8 + (n & 7)] = (uint16_t)((int)c.s.chg[w * 32 + b] * 16);
+        ++n;
       }
     }
     c.s.dhn[idx] = (uint16_t)n;
@@ -674,8 +695,9 @@ __device__ void compute_forces_impl(Ctx &c, Thr &t, bool thermostat, unsigned lo
   if (p.use_dh) {
     // Debye-Hueckel: G sub-threads per owned row, each with its own compact partner list
     const int G = c.d.G, n_mine = c.chi - c.clo, n_loc = c.d.n_loc;
-    for (int idx = c.tid; idx < G * n_mine; idx += nt) {
-      const int g = idx / n_mine, cl = idx - g * n_mine, ci = c.clo + cl;
+    const int nq = c.compact ? (int)c.s.qloc[n_loc] : n_mine;   // compact lists: items of the charged particles only, packed
+    for (int idx = c.tid; idx < G * nq; idx += nt) {
+      const int g = idx / nq, cl = c.compact ? (int)c.s.qloc[idx - g * nq] : idx - g * nq, ci = c.clo + cl;
       const float4 pi4 = c.s.pos[c.s.chg[ci]];
       V3 fd = {0.f, 0.f, 0.f};
       if (pi4.w != 0.0f && c.compact) {

@@ -19,7 +19,7 @@ struct DuoShape {
   int n_sm;        // SMs of the device (replica -> cluster placement heuristic)
   int *order;      // [R] device: replica taken by each cluster (k_duo_plan, in front of every launch)
   // byte offsets
-  int pos, tab, red, slot, fd, dhn, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, wrange, wflag, ratio, ord;
+  int pos, tab, red, slot, fd, dhn, cnt, flag, wl, db, qm, chg, cidx, lp, ld, wn, type, phi, wc, rxof, wrange, wflag, ratio, ord, qloc;
   int total;
 };
 
