@@ -222,6 +222,9 @@ int require_engine(cgpe_handle *h) {
 // 0.78x at 20 mM, 0.65x at N=100, 0.81x with 256 replicas).  So the library picks it for long Debye-Hueckel rows (list
 // radius >= 0.6 of the ideal-chain extent), chains of >= 512 beads and no more replicas than SMs; cgpe_set_engine or
 // CGPE_ENGINE=solo|duo overrides.
+// kernels of one cluster-engine call: the engine kernel, the plan, and the pair count when the plan has a choice (duo_engine.cu::launch_cluster)
+int duo_launches(const cgpe_handle *h) { return 2 + ((h->p.use_dh && h->p.R > h->duo.n_sm / 2 && h->p.R <= h->duo.n_sm) ? 1 : 0); }
+
 bool use_duo(const cgpe_handle *h) {
   if (h->wide || !h->duo.ok || h->launch.items == 0) return false;
   if (h->p.frame_every > 0) return false;   // the frame recorder lives in the one-CTA engine
@@ -857,7 +860,7 @@ int cgpe_md_run(cgpe_handle *h, int32_t n_steps) {
   begin_timing(h);
   int launches = 1;
   if (h->wide) { launches = 0; CU(wide_md_run(h->p, h->g, h->w, n_steps, h->stream, &launches, &h->wgraph)); }
-  else if (use_duo(h)) { launches = 2; CU(duo_md_run(h->p, h->g, h->duo, n_steps, h->stream)); }
+  else if (use_duo(h)) { launches = duo_launches(h); CU(duo_md_run(h->p, h->g, h->duo, n_steps, h->stream)); }
   else CU(launch_md_run(h->p, h->g, h->launch, n_steps, h->stream));
   end_timing(h, launches);
   return CGPE_OK;
@@ -899,7 +902,7 @@ int cgpe_mc_run(cgpe_handle *h, int32_t reaction_id, int32_t n_trials, cgpe_tria
   begin_timing(h);
   int launches = 1;
   if (h->wide) { launches = 0; CU(wide_mc_run(h->p, h->g, h->w, reaction_id, n_trials, d_trace, h->stream, &launches)); }
-  else if (use_duo(h)) { launches = 2; CU(duo_mc_run(h->p, h->g, h->duo, reaction_id, n_trials, d_trace, h->stream)); }
+  else if (use_duo(h)) { launches = duo_launches(h); CU(duo_mc_run(h->p, h->g, h->duo, reaction_id, n_trials, d_trace, h->stream)); }
   else CU(launch_mc_run(h->p, h->g, h->launch, reaction_id, n_trials, d_trace, h->stream));
   end_timing(h, launches);
   if (d_trace) {
@@ -945,7 +948,7 @@ int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp) {
     CU(wide_sample_loop(h->p, h->g, h->w, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                         h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->d_tmp_d, h->d_tmp_i, h->stream, &launches, &h->wgraph));
   } else if (use_duo(h)) {
-    launches = 2;   // the placement plan (k_duo_plan) + the loop itself
+    launches = duo_launches(h);   // the placement plan (k_duo_count_pairs, k_duo_plan) + the loop itself
     CU(duo_sample_loop(h->p, h->g, h->duo, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                        h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
   } else {
