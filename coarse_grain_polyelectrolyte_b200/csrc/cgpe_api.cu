@@ -16,6 +16,7 @@ using namespace cgpe;
 
 struct cgpe_handle {
   cgpe_config cfg;
+  bool solo_cap_low = false;   // the one-CTA engine's shared memory leaves too few WCA row entries for this replica size (choose_capacities)
   DevParams p;
   DevState g;
   ChainLaunch launch;
@@ -153,7 +154,10 @@ int upload_wca(cgpe_handle *h) {
 // List shapes.  The Debye-Hueckel list is a bit matrix over the chargeable particles (fixed size);
 // the WCA row capacity takes what is left of the 227 KB shared-memory budget, up to 64 entries,
 // unless the config gives one.
+constexpr long kMinAutoCapW = 12;
+
 int choose_capacities(cgpe_handle *h) {
+  h->solo_cap_low = false;
   DevParams &p = h->p;
   const int n_chg = p.n_chg;
   p.dw = ((n_chg + 31) / 32) | 1;   // odd row stride: thread-per-row reads hit distinct banks
@@ -170,6 +174,11 @@ int choose_capacities(cgpe_handle *h) {
     const size_t fixed = chain_smem_bytes(p), budget = h->smem_optin;
     long cap = budget > fixed + 64 ? (long)((budget - fixed - 64) / (2 * (size_t)p.P)) : 0;
     if (cap > 64) cap = 64;
+    // Rows of the example chains hold 6-7 entries on average, twice that at most.  Near 2000 particles the fixed arrays
+    // (Debye-Hueckel bit matrix ~ P^2/72 bytes, slots, positions) leave room for a handful only: rows overflow, pairs are
+    // dropped, the replica blows up.  Then the cluster engine (each CTA holds rows for half the particles) or the
+    // global-memory engine serves the replica; cgpe_set_engine(solo) or an explicit cap_wca still force this one.
+    h->solo_cap_low = cap < kMinAutoCapW;
     if (cap < 4) cap = 4;   // too little: chain_launch_shape / the smem check will refuse
     p.cap_w = (int)cap;
   }
@@ -178,6 +187,8 @@ int choose_capacities(cgpe_handle *h) {
   h->launch = chain_launch_shape(p);
   return CGPE_OK;
 }
+
+bool use_duo(const cgpe_handle *h);
 
 int check_device_errors(cgpe_handle *h) {
   if (h->p.frame_every > 0) {
@@ -197,6 +208,9 @@ int check_device_errors(cgpe_handle *h) {
     if (err[r]) { any |= err[r]; if (first < 0) first = r; }
   if (!any) return CGPE_OK;
   CU(cudaMemsetAsync(h->g.err, 0, sizeof(int) * h->p.R, h->stream));
+  if (any & kErrWcaCap)   // first: dropped pairs are what makes a replica blow up afterwards
+    return fail(h, CGPE_ERR_CAPACITY, "WCA neighbour list overflow (cap_wca=%d, first replica %d): raise cap_wca or lower skin",
+                h->wide ? h->w.cap_w : (use_duo(h) ? h->duo.cap_w : h->p.cap_w), first);
   if (any & kErrNonFinite) return fail(h, CGPE_ERR_NUMERIC, "non-finite coordinate or velocity (first replica %d)", first);
   if (any & kErrFene) return fail(h, CGPE_ERR_NUMERIC, "FENE bond stretched beyond d_r_max (first replica %d)", first);
   if (any & kErrDiverged)
@@ -229,6 +243,7 @@ bool use_duo(const cgpe_handle *h) {
   if (h->wide || !h->duo.ok || h->launch.items == 0) return false;
   if (h->p.frame_every > 0) return false;   // the frame recorder lives in the one-CTA engine
   if (h->engine_pref >= 0) return h->engine_pref == 1;
+  if (h->solo_cap_low) return true;   // the one-CTA engine would overflow its WCA rows
   const DevParams &p = h->p;
   const double b = h->cfg.bond_r0 > 0.0 ? h->cfg.bond_r0 : 1.0;
   const bool long_rows = p.use_dh && h->cfg.r_cut + p.skin >= 0.6 * b * std::sqrt((double)p.N);
@@ -621,6 +636,7 @@ int cgpe_set_state(cgpe_handle *h, const float *xyzq, const float *vel, const ui
     if (rc_cap) return rc_cap;
   }
   if (h->launch.items != 0 && h->launch.smem > h->smem_optin) h->launch.items = 0;   // -> global-memory engine
+  if (h->launch.items != 0 && h->solo_cap_low && p.n_ions > 0 && h->engine_pref != 0) h->launch.items = 0;   // explicit ions, too few WCA row entries: ditto
   h->g.dhc = nullptr; p.dhc_cap = 0; p.dhc_stride = 0;
   h->duo.ok = 0;
   if (h->launch.items == 0) {

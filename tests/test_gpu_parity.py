@@ -881,3 +881,28 @@ def test_both_shared_memory_engines_follow_the_same_trajectory(protonated_fracti
     np.testing.assert_array_equal(out["solo"][0][..., 3], out["duo"][0][..., 3])   # charges
     assert np.abs(out["solo"][0][..., :3] - out["duo"][0][..., :3]).max() < 1e-5
     assert np.abs(out["solo"][1] - out["duo"][1]).max() < 1e-5
+
+
+def test_replicas_near_the_shared_memory_limit_get_an_engine_with_room_for_their_rows():
+    """At ~2000 particles the one-CTA engine's fixed arrays leave 5 WCA row entries per particle: rows overflow, pairs are
+    dropped, the replica blows up.  Left to itself the library serves such a replica with the cluster engine (each CTA holds
+    the rows of half the particles); forced onto the one-CTA engine it reports the overflow, not the blow-up that follows."""
+    from coarse_grain_polyelectrolyte_b200 import _abi
+    from coarse_grain_polyelectrolyte_b200._abi import CgpeError
+    from coarse_grain_polyelectrolyte_b200.engine import Engine as E
+    w = make_workload(2000, pH=[2.0, 7.0], c_salt=1e-3)
+    e = E(w.cfg)
+    w.init_engine(e)
+    assert e.engine_info()["engine"] == "duo"
+    e.md_run(600)
+    e.mc_run(0, 1000)
+    e.md_run(150)
+    x, v, _ = e.get_state()
+    assert np.isfinite(x).all() and np.abs(v).max() < 20.0
+    forced = E(w.cfg)
+    w.init_engine(forced)
+    forced.set_engine("solo")
+    with pytest.raises(CgpeError) as ei:
+        forced.md_run(2000)
+        forced.get_state()
+    assert ei.value.status == _abi.ERR_CAPACITY and "WCA" in str(ei.value)

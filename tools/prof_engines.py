@@ -21,13 +21,16 @@ for n_mon, R, salt, ph_lo in shapes:
         e = Engine(w.cfg)
         e.set_engine(engine)
         w.init_engine(e)
-        e.md_run(2000)
-        e.sample_loop(w.sample_params(e, 3))
-        c0 = e.counters()
-        e.sample_loop(w.sample_params(e, samples))
-        ms, _ = e.last_call_ms()
-        md = (e.counters()["md_steps"] - c0["md_steps"]).sum()
-        out.append((e.engine_info()["engine"], ms / samples, md * n_mon / ms * 1e3))
+        try:
+            e.md_run(2000)
+            e.sample_loop(w.sample_params(e, 3))
+            c0 = e.counters()
+            e.sample_loop(w.sample_params(e, samples))
+            ms, _ = e.last_call_ms()
+            md = (e.counters()["md_steps"] - c0["md_steps"]).sum()
+            out.append((e.engine_info()["engine"], ms / samples, md * n_mon / ms * 1e3))
+        except Exception as exc:   # e.g. the one-CTA engine forced onto N = 2000: 5 WCA row entries per particle, overflow reported
+            out.append((engine + " (" + str(exc)[:60] + ")", float("nan"), float("nan")))
         e.close()
     print(f"N={n_mon:5d} R={R:4d} salt={salt:g}: " + "  ".join(f"{n}: {ms:7.3f} ms/sample {v:.3e} bead-steps/s" for n, ms, v in out)
           + f"  duo/solo {out[1][2] / out[0][2]:.2f}", flush=True)
