@@ -327,6 +327,7 @@ int ensure_wide(cgpe_handle *h, const std::vector<int> &chg_packed) {
     CU(alloc((void **)&w.dlc, sizeof(uint16_t) * RC * w.cap_d));
     CU(alloc((void **)&w.dlq, sizeof(uint16_t) * RC * w.cap_d));
     CU(alloc((void **)&w.dnq, sizeof(int) * RC));
+    CU(alloc((void **)&w.nowrap, sizeof(int) * p.R));
   }
   CU(alloc((void **)&w.dn, sizeof(int) * RC));
   CU(alloc((void **)&w.fdh, sizeof(float4) * RC));

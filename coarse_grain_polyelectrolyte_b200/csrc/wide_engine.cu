@@ -22,6 +22,7 @@ namespace cgpe {
 namespace {
 
 constexpr int kWT = 256;   // threads per CTA
+constexpr int kTabSmem = 128; // WCA table entries ((T+1)^2) the force kernel stages in shared memory
 constexpr int kStepFromDevice = -1000;   // kernels of a captured step read the step index from WideState::step
 constexpr int kGraphChunk = 25;          // MD steps per captured graph
 
@@ -462,6 +463,37 @@ wk_rows_tile(const __grid_constant__ DevParams p, const __grid_constant__ DevSta
   }
   __syncthreads();
   const float rl = g.rcut[r] + p.skin, rlist_d2 = rl * rl;
+  if (blockIdx.x == 0) {
+    // extent of the chargeable set: if extent + list radius + skin < L, no listed pair can be closer through a periodic
+    // image than directly until the next build (as in chain_engine.cu::build_lists), and wk_dh_tile skips the image search
+    __shared__ float bb[6][kTileThreads / 32];
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int ck = tid; ck < p.n_chg; ck += kTileThreads)
+      if (vis[ck]) {
+        const float4 x = tcpos[ck];
+        lo[0] = fminf(lo[0], x.x); hi[0] = fmaxf(hi[0], x.x); lo[1] = fminf(lo[1], x.y); hi[1] = fmaxf(hi[1], x.y);
+        lo[2] = fminf(lo[2], x.z); hi[2] = fmaxf(hi[2], x.z);
+      }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+      }
+    if (lane == 0)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { bb[a][warp] = lo[a]; bb[3 + a][warp] = hi[a]; }
+    __syncthreads();
+    if (tid == 0) {
+      float ext = 0.f;
+      for (int a = 0; a < 3; ++a) {
+        float l_ = 3.0e38f, h_ = -3.0e38f;
+        for (int wv = 0; wv < kTileThreads / 32; ++wv) { l_ = fminf(l_, bb[a][wv]); h_ = fmaxf(h_, bb[3 + a][wv]); }
+        ext = fmaxf(ext, h_ - l_);
+      }
+      w.nowrap[r] = (ext + rl + p.skin < p.box_l) ? 1 : 0;   // NaN-safe: wraps
+    }
+  }
   const int c1 = min((int)(blockIdx.x + 1) * kTileSites, p.n_chg);
   for (int ci = blockIdx.x * kTileSites + warp; ci < c1; ci += kTileThreads / 32) {
     int nd = 0, nq = 0;
@@ -529,6 +561,7 @@ wk_dh_tile(const __grid_constant__ DevParams p, const __grid_constant__ DevState
   for (int ck = tid; ck < p.n_chg; ck += kTileThreads) tcpos[ck] = g.pos[base + g.chg[cb + ck]];
   __syncthreads();
   const float kappa = g.kappa[r], rc = g.rcut[r], rc2 = rc * rc, nkl = -kappa * kLog2e;
+  const bool nowrap = w.nowrap[r] != 0;   // uniform: set by the row build in force
   const int c1 = min((int)(blockIdx.x + 1) * kTileSites, p.n_chg);
   for (int ci = blockIdx.x * kTileSites + warp; ci < c1; ci += kTileThreads / 32) {
     const float4 pi4 = tcpos[ci];
@@ -545,7 +578,9 @@ wk_dh_tile(const __grid_constant__ DevParams p, const __grid_constant__ DevState
           if (ck[q] < 0) continue;
           const float4 pj4 = tcpos[ck[q]];
           V3 d;
-          const float r2 = wdist2(p, pi4, pj4, &d);
+          float r2;
+          if (nowrap) { d.x = pi4.x - pj4.x; d.y = pi4.y - pj4.y; d.z = pi4.z - pj4.z; r2 = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z)); }
+          else r2 = wdist2(p, pi4, pj4, &d);
           if (r2 < rc2) {
             float fr;
             const float en = dh_energy_unit(r2, kappa, nkl, &fr);
@@ -617,6 +652,11 @@ wk_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState 
   __shared__ float4 tpos[kWT + 6];
   __shared__ uint8_t ttype[kWT + 6];
   __shared__ float slot[4][3][kWT];
+  __shared__ float4 stab[kTabSmem];   // WCA table: one dependent global load less per row entry
+  const bool tab_staged = S * S <= kTabSmem;
+  if (tab_staged) for (int k = tid; k < S * S; k += kWT) stab[k] = g.wca_tab[k];
+  const float4 *wca_tab = tab_staged ? stab : g.wca_tab;
+  if (t0 >= p.NC) __syncthreads();   // (the chain tiles synchronise below)
   if (t0 < p.NC) {
     for (int k = tid; k < kWT + 6; k += kWT) {
       const int j = t0 - 3 + k;
@@ -642,13 +682,13 @@ wk_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState 
       const int to = ttype[k];
       if (p.use_wca && to < p.T) {
         if (l <= N - 2 && ttype[k + 1] < p.T) {
-          const float4 tab = g.wca_tab[to * S + ttype[k + 1]];
+          const float4 tab = wca_tab[to * S + ttype[k + 1]];
           const V3 d = x0 - x1;
           const float r2 = dot(d, d);
           if (r2 < tab.z) { const V3 fw = wca_force_over_r(tab, r2) * d; fs = fs + fw; fa = fa - fw; }
         }
         if (l <= N - 3 && ttype[k + 2] < p.T) {
-          const float4 tab = g.wca_tab[to * S + ttype[k + 2]];
+          const float4 tab = wca_tab[to * S + ttype[k + 2]];
           const V3 d = x0 - x2;
           const float r2 = dot(d, d);
           if (r2 < tab.z) { const V3 fw = wca_force_over_r(tab, r2) * d; fs = fs + fw; fc = fc - fw; }
@@ -678,7 +718,7 @@ wk_forces(const __grid_constant__ DevParams p, const __grid_constant__ DevState 
     const int n = w.wn[base + i];
     for (int e = 0; e < n; ++e) {
       const int j = wl[(size_t)e * p.P + i];
-      const float4 tab = g.wca_tab[ti * S + type[j]];
+      const float4 tab = wca_tab[ti * S + type[j]];
       V3 d;
       const float r2 = wdist2(p, pi4, pos[j], &d);
       if (r2 < tab.z) f = f + wca_force_over_r(tab, r2) * d;

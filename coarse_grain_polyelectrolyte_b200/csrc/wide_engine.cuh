@@ -27,6 +27,7 @@ struct WideState {
   uint16_t *dlc;      // [R][n_chg][cap_d] the same rows by chargeable index (nullptr unless all chargeable particles fit one CTA's shared memory)
   uint16_t *dlq;      // [R][n_chg][cap_d] of those the partners that carry charge right now (wk_dh_compact)
   int *dnq;           // [R][n_chg]
+  int *nowrap;        // [R] tile mode: 1 if no listed pair of chargeable particles can be closer through a periodic image (set at every row build)
   float4 *fdh;        // [R][n_chg] Debye-Hueckel force on each chargeable particle (wk_dh_forces)
   int *dn;            // [R][n_chg]
   int *cidx;          // [R][P] particle -> chargeable index, -1 = never charged
