@@ -16,6 +16,7 @@ using namespace cgpe;
 
 struct cgpe_handle {
   cgpe_config cfg;
+  int *d_order = nullptr;      // [R] CTA -> replica of the one-CTA engine's fused sampling launch (duo_plan_waves)
   bool solo_cap_low = false;   // the one-CTA engine's shared memory leaves too few WCA row entries for this replica size (choose_capacities)
   DevParams p;
   DevState g;
@@ -527,7 +528,8 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   ALLOC(g.rebuilds, p.R); ALLOC(g.compact_builds, p.R); ALLOC(g.cta_ns, (size_t)p.R * 4);
   ALLOC(g.n_frames, p.R); ALLOC(g.frame_phase, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
   ALLOC(g.f_valid, p.R); ALLOC(g.err, p.R);
-  ALLOC(g.plan, (size_t)p.R * 8);
+  ALLOC(g.plan, (size_t)p.R * 8); ALLOC(h->d_order, p.R);
+  g.order = nullptr;
   ALLOC(h->d_tmp_d, (size_t)p.R * 8); ALLOC(h->d_tmp_i, (size_t)p.R * 3); ALLOC(h->d_tmp_f4, RP);
 #undef ALLOC
   std::vector<double> d(p.R);
@@ -969,7 +971,15 @@ int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp) {
     CU(duo_sample_loop(h->p, h->g, h->duo, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                        h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
   } else {
-    CU(launch_sample_loop(h->p, h->g, h->launch, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
+    DevState g = h->g;
+    g.order = nullptr;
+    // more replicas than SMs (and few enough for the planner's shared memory): the launch runs in waves, most expensive first
+    if (h->p.R > h->n_sm && h->p.R <= 4096 && h->p.n_ions == 0 && !std::getenv("CGPE_NO_WAVE_PLAN")) {
+      CU(duo_plan_waves(h->p, h->g, h->d_order, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2), h->stream));
+      g.order = h->d_order;
+      launches += h->p.use_dh ? 2 : 1;
+    }
+    CU(launch_sample_loop(h->p, g, h->launch, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                           h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
   }
   end_timing(h, launches);

@@ -100,6 +100,7 @@ struct DevState {
   long long *compact_builds;   // [R] times the compact Debye-Hueckel partner lists were written (cgpe_engine_info)
   long long *trials, *accepted;                                  // [R][n_rx]
   double *plan;                // [R][8] cluster-engine planner: [2],[3] trials / accepted at the last plan, [4] charged pairs inside the list radius, [5] acceptance, [6],[7] cost and MD steps predicted for the launch
+  const int *order;            // [R] or NULL: replica taken by each CTA of the one-CTA engine's fused sampling launch (most expensive first when the launch runs in waves)
   int *f_valid;       // [R]
   int *err;           // [R]
 };

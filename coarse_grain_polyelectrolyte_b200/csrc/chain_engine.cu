@@ -1446,7 +1446,7 @@ k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevSt
               const __grid_constant__ cgpe_sample_params sp, uint32_t thr1, uint32_t thr2, double *obs,
               float *qdist) {
   Ctx c{p, g};
-  c.r = blockIdx.x;
+  c.r = g.order ? g.order[blockIdx.x] : (int)blockIdx.x;   // more replicas than SMs: the most expensive start first (duo_plan_waves)
   bind_smem(p, &c.s);
   init_ctx(c);
   Thr<ITEMS> t;

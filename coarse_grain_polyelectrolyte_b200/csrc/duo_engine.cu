@@ -1322,6 +1322,19 @@ cudaError_t launch_cluster(K kernel, const DevParams &p, const DevState &g, cons
 
 }  // namespace
 
+// Order of the replicas for a fused sampling launch of the one-CTA engine that runs in waves (more replicas than SMs):
+// predicted cost as in k_duo_plan, most expensive first, so that the last wave holds the cheap ones (longest processing
+// time first).  order: device array of R ints.  Two small launches.
+cudaError_t duo_plan_waves(const DevParams &p, const DevState &g, int *order, const cgpe_sample_params &sp, uint32_t thr1,
+                           uint32_t thr2, cudaStream_t st) {
+  int trials = 0;
+  for (int b = 0; b < sp.n_mc_blocks; ++b) trials += sp.mc_trials[b];
+  const PlanJob job{sp.n_samples, sp.md_steps_per_burst, sp.use_md, trials, thr1, thr2, (uint32_t)sp.schedule_seed, 0};
+  if (p.use_dh) k_duo_count_pairs<<<p.R, 256, sizeof(float4) * (p.n_chg > 0 ? p.n_chg : 1), st>>>(p, g);
+  k_duo_plan<<<1, 256, 3 * sizeof(float) * p.R, st>>>(p, g, 0, order, job);   // n_sm = 0: every launch is "more clusters than the device holds"
+  return cudaGetLastError();
+}
+
 cudaError_t duo_md_run(const DevParams &p, const DevState &g, const DuoShape &d, int n_steps, cudaStream_t st) {
   return d.nt <= 512 ? launch_cluster(k_duo_md_run<512, 2>, p, g, d, st, PlanJob{0, 0, 0, 0, 0u, 0u, 0u, n_steps}, p, g, d, n_steps)
                      : launch_cluster(k_duo_md_run<1024, 1>, p, g, d, st, PlanJob{0, 0, 0, 0, 0u, 0u, 0u, n_steps}, p, g, d, n_steps);

@@ -27,6 +27,8 @@ struct DuoShape {
 // particles of the fuller half.  Returns the bytes of dynamic shared memory per CTA.
 size_t duo_layout(const DevParams &p, int n_loc, size_t smem_budget, int cap_w_cfg, DuoShape *d);
 
+cudaError_t duo_plan_waves(const DevParams &p, const DevState &g, int *order, const cgpe_sample_params &sp, uint32_t thr1,
+                           uint32_t thr2, cudaStream_t st);
 cudaError_t duo_md_run(const DevParams &p, const DevState &g, const DuoShape &d, int n_steps, cudaStream_t st);
 cudaError_t duo_mc_run(const DevParams &p, const DevState &g, const DuoShape &d, int m, int n_trials,
                        cgpe_trial_record *trace, cudaStream_t st);

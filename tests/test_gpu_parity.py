@@ -906,3 +906,26 @@ def test_replicas_near_the_shared_memory_limit_get_an_engine_with_room_for_their
         forced.md_run(2000)
         forced.get_state()
     assert ei.value.status == _abi.ERR_CAPACITY and "WCA" in str(ei.value)
+
+
+def test_wave_order_of_the_one_cta_engine_does_not_change_results(monkeypatch):
+    """With more replicas than SMs the fused sampling launch of the one-CTA engine starts the most expensive replicas first
+    (predicted from the burst schedule, the charged pairs and the acceptance).  Replicas are independent: same results."""
+    from coarse_grain_polyelectrolyte_b200.engine import Engine as E
+    w = make_workload(100, pH=np.linspace(2.0, 12.0, 200), c_salt=2e-2)
+    state = random_state(w, seed=9)
+    out = []
+    for planned in (True, False):
+        if planned:
+            monkeypatch.delenv("CGPE_NO_WAVE_PLAN", raising=False)
+        else:
+            monkeypatch.setenv("CGPE_NO_WAVE_PLAN", "1")
+        e = load(E(w.cfg), w, state)
+        e.set_engine("solo")
+        sp = e.sample_params(4, md_steps_per_burst=40, use_md=True, mc_blocks=((0, 171), (1, 11)), p_burst1=0.7, p_burst2=0.2)
+        obs, _ = e.sample_loop(sp)
+        out.append((obs, e.get_state(), e.last_call_ms()[1]))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        np.testing.assert_array_equal(a, b)
+    assert out[0][2] == 3 and out[1][2] == 1   # pair count + plan + loop against the loop alone
