@@ -310,7 +310,8 @@ __global__ void k_duo_plan(const __grid_constant__ DevParams p, const __grid_con
   }
   const int n_pair = R - hs, n_alone = 2 * hs - R;
   // candidate j: the alone block is srt[j .. j + n_alone); rest(m) = srt[m < j ? m : m + n_alone]
-  for (int j = threadIdx.x; j <= R - n_alone; j += blockDim.x) {
+  const int n_cand = n_alone > 0 ? R - n_alone + 1 : 1;   // no cluster alone: one way to pair
+  for (int j = threadIdx.x; j < n_cand; j += blockDim.x) {
     float worst = n_alone > 0 ? kAlone * cost[srt[j]] : 0.f;
     for (int i = 0; i < n_pair; ++i) {
       const int a = i, b = 2 * n_pair - 1 - i;
@@ -322,7 +323,7 @@ __global__ void k_duo_plan(const __grid_constant__ DevParams p, const __grid_con
   __syncthreads();
   if (threadIdx.x == 0) {
     int bj = 0;
-    for (int j = 1; j <= R - n_alone; ++j) if (cand[j] < cand[bj]) bj = j;
+    for (int j = 1; j < n_cand; ++j) if (cand[j] < cand[bj]) bj = j;
     best_j = bj;
   }
   __syncthreads();

@@ -929,3 +929,24 @@ def test_wave_order_of_the_one_cta_engine_does_not_change_results(monkeypatch):
     for a, b in zip(out[0][1], out[1][1]):
         np.testing.assert_array_equal(a, b)
     assert out[0][2] == 3 and out[1][2] == 1   # pair count + plan + loop against the loop alone
+
+
+@pytest.mark.parametrize("R", [74, 75, 147, 148, 149, 200])
+def test_cluster_plan_covers_every_replica_for_any_replica_count(R):
+    """The launch plan of the cluster engine has three regimes on a 148-SM device -- every cluster alone (R <= 74), some alone
+    and the others sharing in pairs (74 < R <= 148; at exactly 148 none alone), waves (R > 148): in each of them every replica
+    must be run exactly once, i.e. the results equal the one-CTA engine's, replica by replica."""
+    from coarse_grain_polyelectrolyte_b200.engine import Engine as E
+    w = make_workload(100, pH=np.linspace(2.0, 12.0, R), c_salt=2e-2)
+    state = random_state(w, seed=11)
+    out = []
+    for name in ("duo", "solo"):
+        e = load(E(w.cfg), w, state)
+        e.set_engine(name)
+        sp = e.sample_params(3, md_steps_per_burst=30, use_md=True, mc_blocks=((0, 171), (1, 11)), p_burst1=0.7, p_burst2=0.2)
+        obs, _ = e.sample_loop(sp)
+        out.append((obs, e.counters()))
+    np.testing.assert_array_equal(out[0][0][..., :3], out[1][0][..., :3])
+    np.testing.assert_allclose(out[0][0][..., 3:5], out[1][0][..., 3:5], rtol=1e-5)
+    for k in ("md_steps", "trials", "accepted"):
+        np.testing.assert_array_equal(out[0][1][k], out[1][1][k])
