@@ -592,10 +592,12 @@ def main():
                 sec[name] = secondary_workload(label, mk(), torch, stream, st, 3, min(args.equil_steps, 1000), peaks, sm_count)
             except Exception as exc:  # noqa: BLE001  (the headline must still print)
                 sec[name] = {"error": repr(exc)}
-        try:
-            sec["C5_box"] = secondary_c5(torch, stream, peaks, local_rank)
-        except Exception as exc:  # noqa: BLE001
-            sec["C5_box"] = {"error": repr(exc)}
+        for name, kw in (("C5_box", dict(n_poly=200, n_mon=500, md_steps=1000, trials=2000)),           # 10^5 beads, 4.0e5 particles
+                         ("C5_box_1e6_beads", dict(n_poly=2000, n_mon=500, md_steps=300, trials=1000))):   # 10^6 beads, 4.0e6 particles
+            try:
+                sec[name] = secondary_c5(torch, stream, peaks, local_rank, **kw)
+            except Exception as exc:  # noqa: BLE001
+                sec[name] = {"error": repr(exc)}
         line["secondary"] = sec
     if not args.no_cpu_baseline:
         try:
