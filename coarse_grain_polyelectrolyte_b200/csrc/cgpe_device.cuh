@@ -292,4 +292,25 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Bounding spheres of the blocks of 32 consecutive particles (sph[b] = centre, .w = radius with a safety margin for FP32
+// rounding).  Chain neighbours are spatial neighbours, so a list build tests a block's sphere before its 32 members and skips
+// the block when even the nearest point of the sphere is out of range - with minimum-image arithmetic where the caller uses
+// it: |x_i - x_m| >= |x_i - c_b| - rho_b holds image by image.  All threads of the block call it (nt a multiple of 32); the
+// caller puts barriers around it.  Rows keep their order (partners ascending), so results do not change.
+__device__ __forceinline__ void block_spheres(const float4 *pos, int P, float4 *sph, int tid, int nt) {
+  const int lane = tid & 31, nb = (P + 31) >> 5;
+  for (int b = tid >> 5; b < nb; b += nt >> 5) {
+    const int j = b * 32 + lane;
+    const bool in = j < P;
+    const float4 x = in ? pos[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float inv = 1.0f / (float)min(32, P - b * 32);
+    const float cx = warp_sum(x.x) * inv, cy = warp_sum(x.y) * inv, cz = warp_sum(x.z) * inv;
+    const float ex = x.x - cx, ey = x.y - cy, ez = x.z - cz;
+    float d2 = in ? fmaf(ex, ex, fmaf(ey, ey, ez * ez)) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    if (lane == 0) sph[b] = make_float4(cx, cy, cz, sqrtf(d2) * 1.0001f + 1.0e-3f);
+  }
+}
+
 }  // namespace cgpe

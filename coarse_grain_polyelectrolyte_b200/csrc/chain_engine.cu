@@ -40,7 +40,7 @@ size_t chain_smem_bytes(DevParams &p) {
   SmemOff &f = p.off;
   f.pos = take(sizeof(float4) * p.P, 16);
   f.tab = take(sizeof(float4) * TT, 16);
-  f.red = take(sizeof(double) * 32 * 4, 8);
+  f.red = take(sizeof(double) * 32 * 4, 16);   // also holds the block spheres of a list build (float4)
   f.slot = take(sizeof(float) * 9 * p.NC, 4);
   f.fd = take(sizeof(float) * 3 * grp * n_chg, 4);
   f.dhn = take(sizeof(uint16_t) * grp * n_chg, 2);
@@ -247,6 +247,9 @@ __device__ void store_state(Ctx &c, Thr<ITEMS> &t, bool store_forces) {
 template <int ITEMS, bool WRAP>
 __device__ void build_rows(Ctx &c, Thr<ITEMS> &t) {
   const DevParams &p = c.p;
+  const float4 *sph = reinterpret_cast<const float4 *>(c.s.red);   // block spheres (build_lists)
+  const int nb = (p.P + 31) >> 5;
+  const float rl_w = sqrtf(p.rlist_w2);
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
     const int i = c.tid + k * c.nt;
@@ -260,12 +263,18 @@ __device__ void build_rows(Ctx &c, Thr<ITEMS> &t) {
         int ex_lo = i, ex_hi = i;
         if (t.l[k] >= 0) { ex_lo = i - min(2, t.l[k]); ex_hi = i + min(2, p.N - 1 - t.l[k]); }
         int n = 0;
-        for (int j = 0; j < p.P; ++j) {
+        for (int b = 0; b < nb; ++b) {   // blocks of 32 consecutive particles: sphere first (block_spheres)
+          const float4 sb = sph[b];
           V3 d;
-          const float r2 = dist2<WRAP>(c, pi, c.s.pos[j], &d);
-          if (r2 < p.rlist_w2 && (j < ex_lo || j > ex_hi)) {
-            if (n < p.cap_w) c.s.wl[(size_t)n * p.P + i] = (uint16_t)j;
-            ++n;
+          const float reach = sb.w + rl_w;
+          if (dist2<WRAP>(c, pi, sb, &d) > reach * reach) continue;
+          const int j1 = min(p.P, b * 32 + 32);
+          for (int j = b * 32; j < j1; ++j) {
+            const float r2 = dist2<WRAP>(c, pi, c.s.pos[j], &d);
+            if (r2 < p.rlist_w2 && (j < ex_lo || j > ex_hi)) {
+              if (n < p.cap_w) c.s.wl[(size_t)n * p.P + i] = (uint16_t)j;
+              ++n;
+            }
           }
         }
         if (p.rlist_wf2 > p.rlist_w2)   // fixed particles sit in slots and may be large: their own list radius
@@ -362,6 +371,9 @@ __device__ void build_lists(Ctx &c, Thr<ITEMS> &t) {
   }
   c.wrap = !(ext + c.rlist_max + p.skin < p.box_l);   // NaN-safe: wraps
   c.dense = p.use_dh && (p.dense_policy == 2 || (p.dense_policy == 0 && c.rlist_d2 >= ext * ext));   // list radius >= extent: the rows prune nothing (measured: no gain below that)
+  __syncthreads();   // every thread has read the bounding-box scratch: it now takes the block spheres
+  block_spheres(c.s.pos, p.P, reinterpret_cast<float4 *>(c.s.red), c.tid, c.nt);
+  __syncthreads();
   if (c.wrap) build_rows<ITEMS, true>(c, t); else build_rows<ITEMS, false>(c, t);
   __syncthreads();   // Debye-Hueckel rows are read by other threads (sub-thread split, MC warp)
   c.rebuilds += 1;

@@ -66,7 +66,7 @@ size_t duo_layout(const DevParams &p, int n_loc, size_t smem_budget, int cap_w_c
   auto take = [&](size_t bytes, size_t align) { o = up(o, align); size_t at = o; o += bytes; return (int)at; };
   s.pos = take(sizeof(float4) * (p.P + 1), 16);   // +1: far-away, uncharged dummy that pads the compact partner lists
   s.tab = take(sizeof(float4) * TT, 16);
-  s.red = take(sizeof(double) * 32 * 4, 8);
+  s.red = take(sizeof(double) * 32 * 4, 16);   // also holds the block spheres of a list build (float4)
   s.slot = take(sizeof(float) * 9 * s.nt, 4);
   s.fd = take(sizeof(float) * 3 * s.G * s.n_loc, 4);
   s.dhn = take(sizeof(uint16_t) * s.G * s.n_loc, 2);
@@ -464,12 +464,20 @@ __device__ void build_rows(Ctx &c, Thr &t) {
       int ex_lo = i, ex_hi = i;
       if (t.l >= 0) { ex_lo = i - min(2, t.l); ex_hi = i + min(2, p.N - 1 - t.l); }
       int n = 0;
-      for (int j = 0; j < p.P; ++j) {
+      const float4 *sph = reinterpret_cast<const float4 *>(c.s.red);   // block spheres (build_lists)
+      const float rl_w = sqrtf(p.rlist_w2);
+      for (int b = 0, nb = (p.P + 31) >> 5; b < nb; ++b) {   // blocks of 32 consecutive particles: sphere first
+        const float4 sb = sph[b];
         V3 dd;
-        const float r2 = dist2<WRAP>(c, pi, c.s.pos[j], &dd);
-        if (r2 < p.rlist_w2 && (j < ex_lo || j > ex_hi)) {
-          if (n < c.d.cap_w) c.s.wl[(size_t)n * c.nt + li] = (uint16_t)j;
-          ++n;
+        const float reach = sb.w + rl_w;
+        if (dist2<WRAP>(c, pi, sb, &dd) > reach * reach) continue;
+        const int j1 = min(p.P, b * 32 + 32);
+        for (int j = b * 32; j < j1; ++j) {
+          const float r2 = dist2<WRAP>(c, pi, c.s.pos[j], &dd);
+          if (r2 < p.rlist_w2 && (j < ex_lo || j > ex_hi)) {
+            if (n < c.d.cap_w) c.s.wl[(size_t)n * c.nt + li] = (uint16_t)j;
+            ++n;
+          }
         }
       }
       if (n > c.d.cap_w) { c.err |= kErrWcaCap; n = c.d.cap_w; }
@@ -537,6 +545,9 @@ __device__ void build_lists(Ctx &c, Thr &t) {
     }
   }
   c.wrap = !(ext + c.rlist_max + p.skin < p.box_l);   // NaN-safe: wraps
+  __syncthreads();   // every thread has read the bounding-box scratch: it now takes the block spheres
+  block_spheres(c.s.pos, p.P, reinterpret_cast<float4 *>(c.s.red), c.tid, c.nt);
+  __syncthreads();
   if (c.wrap) build_rows<true>(c, t); else build_rows<false>(c, t);
   __syncthreads();
   c.rebuilds += 1;
