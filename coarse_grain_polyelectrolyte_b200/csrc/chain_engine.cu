@@ -630,7 +630,7 @@ __device__ void compute_forces_impl(Ctx &c, Thr<ITEMS> &t, bool thermostat, unsi
       }
       if (p.use_dh) {
         const int ci = c.s.cidx[i];
-        if (ci != 0xFFFF)
+        if (ci != 0xFFFF && c.s.cpos[ci].w != 0.0f)   // a particle without charge feels no Debye-Hueckel force: its slots hold zeros
           for (int g = 0; g < p.dh_group; ++g) {
             const float *fdg = c.s.fd + (size_t)g * 3 * p.n_chg;
             fx += fdg[ci]; fy += fdg[p.n_chg + ci]; fz += fdg[2 * p.n_chg + ci];

@@ -783,7 +783,7 @@ __device__ void compute_forces_impl(Ctx &c, Thr &t, bool thermostat, unsigned lo
     }
     if (p.use_dh) {
       const int ci = c.s.cidx[i];
-      if (ci != 0xFFFF) {
+      if (ci != 0xFFFF && c.s.pos[i].w != 0.0f) {   // a particle without charge feels no Debye-Hueckel force: its slots hold zeros
         const int cl = ci - c.clo, n_loc = c.d.n_loc;
         for (int g = 0; g < c.d.G; ++g) {
           const float *fdg = c.s.fd + (size_t)g * 3 * n_loc;
