@@ -16,6 +16,8 @@ using namespace cgpe;
 
 struct cgpe_handle {
   cgpe_config cfg;
+  int *d_choice = nullptr;     // [1] engine the plan picked for the last fused sampling launch issued on both shared-memory engines
+  bool choice_live = false;    // ... and whether that launch was such a one
   int *d_order = nullptr;      // [R] CTA -> replica of the one-CTA engine's fused sampling launch (duo_plan_waves)
   bool solo_cap_low = false;   // the one-CTA engine's shared memory leaves too few WCA row entries for this replica size (choose_capacities)
   DevParams p;
@@ -528,8 +530,9 @@ int cgpe_create(const cgpe_config *cfg, cgpe_handle **out) {
   ALLOC(g.rebuilds, p.R); ALLOC(g.compact_builds, p.R); ALLOC(g.cta_ns, (size_t)p.R * 4);
   ALLOC(g.n_frames, p.R); ALLOC(g.frame_phase, p.R); ALLOC(g.trials, (size_t)p.R * nrx); ALLOC(g.accepted, (size_t)p.R * nrx);
   ALLOC(g.f_valid, p.R); ALLOC(g.err, p.R);
-  ALLOC(g.plan, (size_t)p.R * 8); ALLOC(h->d_order, p.R);
+  ALLOC(g.plan, (size_t)p.R * 8); ALLOC(h->d_order, p.R); ALLOC(h->d_choice, 1);
   g.order = nullptr;
+  g.engine_choice = nullptr;
   ALLOC(h->d_tmp_d, (size_t)p.R * 8); ALLOC(h->d_tmp_i, (size_t)p.R * 3); ALLOC(h->d_tmp_f4, RP);
 #undef ALLOC
   std::vector<double> d(p.R);
@@ -962,14 +965,26 @@ int cgpe_sample_loop_async(cgpe_handle *h, const cgpe_sample_params *sp) {
   h->last_ns = sp->n_samples; h->last_qrows = rows;
   begin_timing(h);
   int launches = 1;
+  h->choice_live = false;
   if (h->wide) {
     launches = 0;
     CU(wide_sample_loop(h->p, h->g, h->w, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                         h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->d_tmp_d, h->d_tmp_i, h->stream, &launches, &h->wgraph));
   } else if (use_duo(h)) {
     launches = duo_launches(h);   // the placement plan (k_duo_count_pairs, k_duo_plan) + the loop itself
-    CU(duo_sample_loop(h->p, h->g, h->duo, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
+    DevState g = h->g;
+    // left to itself (no cgpe_set_engine, no CGPE_ENGINE) the library issues the launch on both shared-memory engines and
+    // the plan decides on the device which one runs it (the other kernel returns at once): no host round trip
+    const bool both = h->engine_pref < 0 && !h->solo_cap_low && h->p.R <= h->n_sm && h->launch.items != 0;
+    g.engine_choice = both ? h->d_choice : nullptr;
+    CU(duo_sample_loop(h->p, g, h->duo, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
                        h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
+    if (both) {
+      CU(launch_sample_loop(h->p, g, h->launch, *sp, bernoulli_threshold(sp->p_burst1), bernoulli_threshold(sp->p_burst2),
+                            h->d_obs, n_q > 0 ? h->d_qdist : nullptr, h->stream));
+      launches += 1;
+    }
+    h->choice_live = both;
   } else {
     DevState g = h->g;
     g.order = nullptr;
@@ -1103,7 +1118,15 @@ int cgpe_engine_info(cgpe_handle *h, int32_t *engine, int64_t *compact_builds, i
   if (!h) return fail(nullptr, CGPE_ERR_INVALID, "handle is NULL");
   if (!h->have_state) return fail(h, CGPE_ERR_STATE, "set_state has not been called");
   DeviceGuard guard(h->device);
-  if (engine) *engine = h->wide ? 2 : use_duo(h) ? 1 : 0;
+  if (engine) {
+    *engine = h->wide ? 2 : use_duo(h) ? 1 : 0;
+    if (*engine == 1 && h->choice_live) {   // the last fused sampling launch chose on the device
+      int choice = 1;
+      CU(cudaMemcpyAsync(&choice, h->d_choice, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      *engine = choice;
+    }
+  }
   if (compact_builds) CU(cudaMemcpyAsync(compact_builds, h->g.compact_builds, sizeof(int64_t) * h->p.R, cudaMemcpyDeviceToHost, h->stream));
   if (cta_ns) CU(cudaMemcpyAsync(cta_ns, h->g.cta_ns, sizeof(int64_t) * h->p.R * 4, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

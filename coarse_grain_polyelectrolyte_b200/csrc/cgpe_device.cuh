@@ -101,6 +101,7 @@ struct DevState {
   long long *trials, *accepted;                                  // [R][n_rx]
   double *plan;                // [R][8] cluster-engine planner: [2],[3] trials / accepted at the last plan, [4] charged pairs inside the list radius, [5] acceptance, [6],[7] cost and MD steps predicted for the launch
   const int *order;            // [R] or NULL: replica taken by each CTA of the one-CTA engine's fused sampling launch (most expensive first when the launch runs in waves)
+  int *engine_choice;          // NULL, or: the fused sampling launch was issued on both shared-memory engines and the plan (k_duo_plan) wrote which one runs - 0 one CTA per replica, 1 cluster; the other kernel returns at once
   int *f_valid;       // [R]
   int *err;           // [R]
 };

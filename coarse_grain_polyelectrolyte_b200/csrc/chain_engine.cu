@@ -1457,6 +1457,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 k_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevState g,
               const __grid_constant__ cgpe_sample_params sp, uint32_t thr1, uint32_t thr2, double *obs,
               float *qdist) {
+  if (g.engine_choice && *g.engine_choice != 0) return;   // the plan of this launch gave it to the cluster engine
   Ctx c{p, g};
   c.r = g.order ? g.order[blockIdx.x] : (int)blockIdx.x;   // more replicas than SMs: the most expensive start first (duo_plan_waves)
   bind_smem(p, &c.s);

@@ -306,6 +306,7 @@ __global__ void k_duo_plan(const __grid_constant__ DevParams p, const __grid_con
   __syncthreads();
   if (R <= hs || R > 2 * hs) {
     for (int k = threadIdx.x; k < R; k += blockDim.x) order[R <= hs ? srt[k] : k] = srt[k];   // all alone / heaviest first
+    if (threadIdx.x == 0 && g.engine_choice) *g.engine_choice = 1;
     return;
   }
   const int n_pair = R - hs, n_alone = 2 * hs - R;
@@ -325,6 +326,11 @@ __global__ void k_duo_plan(const __grid_constant__ DevParams p, const __grid_con
     int bj = 0;
     for (int j = 1; j < n_cand; ++j) if (cand[j] < cand[bj]) bj = j;
     best_j = bj;
+    // Which engine for this launch?  One CTA per replica: every replica on its own SM, the launch lasts as long as the most
+    // expensive one.  Clusters: cand[bj].  A short launch has a few outliers (long burst schedules) that gain from two SMs of
+    // their own; over a long one all highly charged replicas cost about the same, only n_alone of them can be alone and the
+    // others lose more by sharing than the alone ones gain (measured: full 4571-sample protocol 21.1 s against 24.1 s).
+    if (g.engine_choice) *g.engine_choice = cand[bj] < cost[srt[0]] ? 1 : 0;
   }
   __syncthreads();
   const int j0 = best_j;
@@ -1218,6 +1224,7 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_duo_sample_loop(const __grid_constant__ DevParams p, const __grid_constant__ DevState g, const __grid_constant__ DuoShape d,
                   const __grid_constant__ cgpe_sample_params sp, uint32_t thr1, uint32_t thr2, double *obs, float *qdist) {
+  if (g.engine_choice && *g.engine_choice != 1) return;   // the plan of this launch gave it to the one-CTA engine (whole clusters leave)
   Ctx c{p, g, d};
   prologue(c);
   Thr t;

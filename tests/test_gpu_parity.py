@@ -950,3 +950,27 @@ def test_cluster_plan_covers_every_replica_for_any_replica_count(R):
     np.testing.assert_allclose(out[0][0][..., 3:5], out[1][0][..., 3:5], rtol=1e-5)
     for k in ("md_steps", "trials", "accepted"):
         np.testing.assert_array_equal(out[0][1][k], out[1][1][k])
+
+
+def test_fused_launch_issued_on_both_engines_runs_on_exactly_one():
+    """Left to itself the library issues the fused sampling launch of a long-chain shard on both shared-memory engines and
+    the plan picks one on the device: the results must be those of that engine (not twice the samples, not none), and
+    engine_info names it."""
+    from coarse_grain_polyelectrolyte_b200.engine import Engine as E
+    w = make_workload(1000, pH=np.linspace(2.0, 12.0, 100), c_salt=1e-3)
+    state = random_state(w, seed=21, jitter=0.02)
+    runs = {}
+    for name in ("auto", "solo", "duo"):
+        e = load(E(w.cfg), w, state)
+        if name != "auto":
+            e.set_engine(name)
+        sp = e.sample_params(3, md_steps_per_burst=20, use_md=True, mc_blocks=((0, 501), (1, 11)), p_burst1=0.7, p_burst2=0.2)
+        obs, _ = e.sample_loop(sp)
+        runs[name] = (obs, e.counters(), e.last_call_ms()[1], e.engine_info()["engine"])
+    picked = runs["auto"][3]
+    assert picked in ("solo", "duo") and runs["auto"][2] == 4   # pair count, plan, two loop kernels (one of them returns at once)
+    np.testing.assert_array_equal(runs["auto"][0][..., :3], runs[picked][0][..., :3])
+    np.testing.assert_allclose(runs["auto"][0][..., 3:5], runs[picked][0][..., 3:5], rtol=1e-6)
+    for k in ("md_steps", "trials", "accepted"):
+        np.testing.assert_array_equal(runs["auto"][1][k], runs[picked][1][k])
+    assert runs["auto"][1]["md_steps"].max() <= 3 * 40
