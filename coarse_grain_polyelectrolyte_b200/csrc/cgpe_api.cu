@@ -235,9 +235,10 @@ int require_engine(cgpe_handle *h) {
 
 // The cluster engine serves implicit-ion replicas without spectator particles.  Its step carries two cluster barriers
 // and the mirrored position stores (~1.2 us), which it earns back only where the step is long and the launch leaves SMs
-// idle (measured, tools/prof_engines.py -> profiles/r2_engines.txt: 128 x N=1000 at 1 mM 1.03x, 64 x N=1000 1.05x; but
-// 0.78x at 20 mM, 0.65x at N=100, 0.81x with 256 replicas).  So the library picks it for long Debye-Hueckel rows (list
-// radius >= 0.6 of the ideal-chain extent), chains of >= 512 beads and no more replicas than SMs; cgpe_set_engine or
+// idle (measured, tools/prof_engines.py -> profiles/r2_engines.txt, final library: 128 x N=1000 at 1 mM 1.04x, 64 x N=1000
+// 1.04x, 20 mM 1.01x; but 0.65x at N=100, 0.77x at N=300, 0.85x with 256 replicas).  So the library considers it for long
+// Debye-Hueckel rows (list radius >= 0.6 of the ideal-chain extent), chains of >= 512 beads and no more replicas than SMs;
+// for a fused sampling launch the plan then decides on the device (cgpe_sample_loop, k_duo_plan).  cgpe_set_engine or
 // CGPE_ENGINE=solo|duo overrides.
 // kernels of one cluster-engine call: the engine kernel, the plan, and the pair count when the plan has a choice (duo_engine.cu::launch_cluster)
 int duo_launches(const cgpe_handle *h) { return 2 + ((h->p.use_dh && h->p.R > h->duo.n_sm / 2 && h->p.R <= h->duo.n_sm) ? 1 : 0); }
