@@ -242,7 +242,20 @@ def config_c3_shard(rank=0, world=8, n_ph=128, n_mon=1000, all_salts=False, **kw
     lo = rank * per
     idx = np.arange(lo, lo + per)
     pH_grid = np.linspace(2.0, 12.0, n_ph)
-    pH = pH_grid[idx % n_ph]
-    c_salt = np.array(salts)[idx // n_ph]
+    if all_salts and n_ph & (n_ph - 1) == 0 and n_ph > 1:
+        # Strong scaling: which grid cell a global replica index (= Philox key) names is a convention, independent of the
+        # number of GPUs: ionic strength = g mod 8, pH point = bit-reversed(g div 8).  Any contiguous block of indices a rank
+        # holds then covers every ionic strength and the whole pH axis evenly, so the ranks cost the same (the salt-major order
+        # gave rank 0 the four lowest ionic strengths, the expensive half: 1.72x on two GPUs).
+        bits = n_ph.bit_length() - 1
+        slot = idx // len(salts)
+        rev = np.zeros_like(slot)
+        for b in range(bits):
+            rev |= ((slot >> b) & 1) << (bits - 1 - b)
+        pH = pH_grid[rev]
+        c_salt = np.array(salts)[idx % len(salts)]
+    else:
+        pH = pH_grid[idx % n_ph]
+        c_salt = np.array(salts)[idx // n_ph]
     return Workload(example_parameters(n_mon, c_salt=float(c_salt[0])), pH=pH, c_salt=c_salt,
                     replica_offset=int(lo), **kw)

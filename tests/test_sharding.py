@@ -165,3 +165,22 @@ def test_gloo_world2_replica_exchange_matches_single_process(tmp_path, oracle_mo
     np.testing.assert_array_equal(l0, labels)
     np.testing.assert_array_equal(np.load(tmp_path / "obs_0.npy"), obs)
     assert (labels != pH[:, None]).any()            # labels really moved
+
+
+def test_strong_scaling_cells_are_a_world_independent_balanced_convention():
+    """config_c3_shard(all_salts=True): which (pH, ionic strength) cell a global replica index names does not depend on the
+    number of ranks (the index is the Philox key), all 1024 cells appear once, and every rank's contiguous block covers every
+    ionic strength and the whole pH axis evenly."""
+    from coarse_grain_polyelectrolyte_b200 import workloads
+    ref = None
+    for world in (1, 2, 4, 8):
+        cells = []
+        for r in range(world):
+            w = workloads.config_c3_shard(r, world, n_ph=128, n_mon=30, all_salts=True)
+            off = int(w.cfg.replica_offset)
+            cells += [(off + k, round(float(w.pH[k]), 6), round(float(w.kappa[k]), 6)) for k in range(w.R)]
+            assert abs(w.pH.mean() - 7.0) < 0.35 and len(set(np.round(w.kappa, 6))) == 8
+        cells.sort()
+        assert len(set(c[1:] for c in cells)) == 1024
+        ref = ref or cells
+        assert cells == ref
