@@ -279,7 +279,10 @@ __global__ void k_duo_plan(const __grid_constant__ DevParams p, const __grid_con
     st[2] = (double)tr; st[3] = (double)ac;
     const float pairs = p.use_dh ? (float)st[4] : 0.f;   // k_duo_count_pairs
     long long steps = job.fixed_steps;
-    if (job.n_samples > 0 && job.use_md) {
+    if (job.n_samples > 20000 && job.use_md) {
+      // a very long launch: the schedules of the replicas differ by less than a per cent, the expectation will do
+      steps = (long long)((double)job.n_samples * job.steps_per_burst * ((double)job.thr1 + (double)job.thr2) / 16777216.0);
+    } else if (job.n_samples > 0 && job.use_md) {
       steps = 0;
       const unsigned long long s0 = (unsigned long long)g.samples_done[r];
       for (int s = 0; s < job.n_samples; ++s) {
